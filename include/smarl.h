@@ -1,0 +1,261 @@
+/*
+ * smarl.h -- C ABI of the B200-native batched env-step hot path (libsmarl.so).
+ *
+ * The reference (advilema/safe_multiagent_RL) is pure Python and has no FFI; the
+ * boundary it offers for this path is the duck-typed env protocol
+ * reset()/step(actions) -> (state, reward, constraint, done) consumed by main.py:28-57,
+ * plus MetaAgent.act / Buffer.append / Buffer.step / *.compute_returns.  Each entry
+ * point below names the reference function(s) it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ * -----------
+ *  - Every pointer is a DEVICE pointer unless the name ends in _h (then pageable or
+ *    pinned HOST memory).  The caller owns all buffers; nothing here allocates except
+ *    the smarl_host_* staging helpers, which say so.
+ *  - All batched arrays are agent-major SoA: element (row r, env e) lives at
+ *    base[r * ld + e].  `ld` (row stride in ELEMENTS, shared by every array of a call)
+ *    must be a multiple of 16 and >= n_envs; every base pointer must be 16-byte
+ *    aligned.  Lanes n_envs..ld-1 of a row are padding: they may be read and written
+ *    with garbage, never fault, and never enter a reduction.
+ *  - Calls enqueue work on `stream` (a cudaStream_t passed as void*) and return
+ *    without synchronising.  They are re-entrant; distinct state buffers may be driven
+ *    from different host threads / streams.
+ *  - Return value: SMARL_OK or a negative error; smarl_last_error() gives a
+ *    thread-local message.  There is no CPU fallback.
+ *  - n_agents is limited to 1..32, grid size to 1..254 (coordinates are uint8).
+ */
+#ifndef SMARL_H_
+#define SMARL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMARL_ABI_VERSION 1
+#define SMARL_MAX_AGENTS 32
+
+enum {
+  SMARL_OK = 0,
+  SMARL_EINVAL = -1,        /* bad shape / alignment / null pointer */
+  SMARL_ECUDA = -2,         /* a CUDA runtime call failed (see smarl_last_error) */
+  SMARL_EUNSUPPORTED = -3   /* valid request outside the compiled envelope */
+};
+
+typedef void* smarl_stream_t;   /* cudaStream_t */
+
+int smarl_abi_version(void);
+const char* smarl_last_error(void);
+/* SM count and compute capability of the current device. */
+int smarl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * Grid envs share start/reset: replaces CoverageContinuous.reset/_restart
+ * (envs/coverage.py:28-52) and Congestion.reset/_restart (envs/congestion.py:34-47) for
+ * shuffle=False: state <- start, and the float observation the policies read
+ * (np.array(state).flatten(), main.py:33) is rebuilt.
+ *   start_x,start_y,pos_x,pos_y  u8 [A][ld]      obs  f32 [2A][ld] rows x0,y0,x1,y1,... (may be NULL)
+ * ---------------------------------------------------------------------------------- */
+int smarl_grid_reset(const uint8_t* start_x, const uint8_t* start_y, uint8_t* pos_x,
+                     uint8_t* pos_y, float* obs, int32_t n_agents, int64_t n_envs, int64_t ld,
+                     smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * CoverageDiscrete ("Explore")
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t size;         /* coordinates clamp to [0,size]                 coverage.py:185-186 */
+  int32_t n_agents;     /* A; also K = A constraints                     coverage.py:22      */
+  int32_t lut_len;      /* penalties for squared distance q >= lut_len are 0                 */
+  int32_t reserved;
+  const float* lut;     /* [lut_len] pen(q) = (fv - sqrt(q))^2 if sqrt(q) < fv else 0, f32
+                           rounding of the reference's f64 value         coverage.py:80-83   */
+  const float* weights; /* [A] per-agent reward weight, NULL = 1         coverage.py:86-87   */
+} SmarlCoverageParams;
+
+/* One CoverageDiscrete.step (coverage.py:100-106 = transition :174-189 + reward :76-89 +
+ * constraint :191-196 + check_done :97-98) for n_envs environments, with MetaAgent.act's
+ * penalty <lambda, c> (safe_multi_agent_RL/meta_agent.py:21-22) fused in.
+ *   pos_x,pos_y u8 [A][ld] in/out     actions u8 [A][ld] in 0..4
+ *   obs     f32 [2A][ld]  out, NULL to skip
+ *   reward  f32 [A][ld]   out   w_a * -(sum of pair penalties)
+ *   cost    u8  [A][ld]   out   1 for a non-stay action
+ *   done    u8  [A][ld]   out, NULL to skip (always 0 for Coverage)
+ *   lambdas f64 [A]  in, penalty f32 [ld] out = sum_k lambda_k c_k; both NULL to skip
+ * For a rollout buffer pass reward/cost/done/penalty offset to step t's slab. */
+int smarl_coverage_step(const SmarlCoverageParams* p, uint8_t* pos_x, uint8_t* pos_y,
+                        const uint8_t* actions, float* obs, float* reward, uint8_t* cost,
+                        uint8_t* done, const double* lambdas, float* penalty, int64_t n_envs,
+                        int64_t ld, smarl_stream_t stream);
+
+/* Parameters of the per-episode accounting shared by every *_rollout / returns call. */
+typedef struct {
+  double gamma;           /* discount                              buffer.py:31             */
+  int32_t n_steps;        /* T = max_t                             main.py:29               */
+  int32_t g_mode;         /* what G holds: 0 none, 1 reward-to-go G_t = m_t + gamma G_{t+1}
+                             (ACAgent.compute_returns agent.py:200-206), 2 gamma^t m_t
+                             (AbstractAgent.compute_returns agent.py:129-132)               */
+  const double* thresholds; /* [K] device, for violation counts; NULL = skip  buffer.py:47  */
+} SmarlAccounting;
+
+/* Number of f64 slots in a stats vector for (A agents, K constraints):
+ *   [0,K) sum_e C_k   [K,2K) #{e : C_k > thr_k}   [2K,2K+A) sum_e R_a
+ *   [2K+A,2K+2A) sum_e modR_a   [2K+2A] episode count. */
+int32_t smarl_stats_len(int32_t n_agents, int32_t n_constraints);
+/* Scratch (in f64 elements) the accounting kernels need for deterministic block partials. */
+int64_t smarl_stats_scratch_len(int32_t n_agents, int32_t n_constraints, int64_t n_envs);
+
+/* Whole open-loop episode in one launch: reset + T x (step + MetaAgent.act) + Buffer.step
+ * + compute_returns, state register-resident (main.py:28-57 without the policy nets).
+ *   start_x,start_y u8 [A][ld]     actions u8 [T][A][ld]     lambdas f64 [A] (NULL = 0)
+ *   final_x,final_y u8 [A][ld] out (NULL to skip)
+ *   R, modR f32 [A][ld] out        C i32 [A][ld] out
+ *   G f32 [T][A][ld] out if acc->g_mode != 0    g_scratch f32 [2][T][ld] then required
+ *   stats f64 [smarl_stats_len] out (NULL to skip), stats_scratch f64 [smarl_stats_scratch_len] */
+int smarl_coverage_rollout(const SmarlCoverageParams* p, const SmarlAccounting* acc,
+                           const uint8_t* start_x, const uint8_t* start_y,
+                           const uint8_t* actions, const double* lambdas, uint8_t* final_x,
+                           uint8_t* final_y, float* R, float* modR, int32_t* C, float* G,
+                           float* g_scratch, double* stats, double* stats_scratch,
+                           int64_t n_envs, int64_t ld, smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Congestion
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t size;          /* coordinates clamp to [0,size]                 congestion.py:70-71 */
+  int32_t n_agents;      /* A; K = 1                                      congestion.py:26    */
+  const double* demand;  /* [(size+1)*(size+1)] row-major [x][y], f64     congestion.py:28,86 */
+  /* action noise (congestion.py:64-67): move = a if u1 < 1-noise else int(u2*5)              */
+  int32_t noise_mode;    /* 0 = none, 1 = recorded effective moves, 2 = on-device Philox      */
+  int32_t reserved;
+  uint64_t keep_threshold; /* mode 2: keep action iff w1 < keep_threshold, = ceil((1-noise)*2^32) */
+  uint64_t seed;         /* mode 2: Philox4x32-10 key                                         */
+  int64_t env_offset;    /* mode 2: global id of env 0 (counter = (id, t, agent>>1)), so the
+                            stream does not depend on how envs are sharded over GPUs          */
+} SmarlCongestionParams;
+
+/* One Congestion.step (congestion.py:106-111 = transition :49-75 + reward :77-90 with
+ * _congestions :113-137 + constraint :93-100 + check_done :103-104) with MetaAgent.act fused.
+ *   pos_x,pos_y u8 [A][ld] in/out    actions u8 [A][ld] intended 0..4
+ *   moves u8 [A][ld]: noise_mode 1 in (recorded), else NULL or out (the effective move taken)
+ *   obs f32 [2A][ld], reward f32 [A][ld], cost i32 [ld], done u8 [A][ld] (NULL ok)
+ *   lambdas f64 [1], penalty f32 [ld];  t = step index (Philox counter). */
+int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* pos_x, uint8_t* pos_y,
+                          const uint8_t* actions, uint8_t* moves, float* obs, float* reward,
+                          int32_t* cost, uint8_t* done, const double* lambdas, float* penalty,
+                          int32_t t, int64_t n_envs, int64_t ld, smarl_stream_t stream);
+
+/* Fused open-loop episode, as smarl_coverage_rollout.  moves u8 [T][A][ld] (mode 1) or NULL.
+ * C i32 [1][ld]. */
+int smarl_congestion_rollout(const SmarlCongestionParams* p, const SmarlAccounting* acc,
+                             const uint8_t* start_x, const uint8_t* start_y,
+                             const uint8_t* actions, const uint8_t* moves,
+                             const double* lambdas, uint8_t* final_x, uint8_t* final_y, float* R,
+                             float* modR, int32_t* C, float* G, float* g_scratch, double* stats,
+                             double* stats_scratch, int64_t n_envs, int64_t ld,
+                             smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * CollisionAvoidance (continuous, float64 state)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t size;          /* positions clamp to [0,size]          collision_avoidance.py:118-119 */
+  int32_t n_agents;      /* A; K = 1                             collision_avoidance.py:69      */
+  int32_t n_landmarks;   /* L >= 1                               collision_avoidance.py:62,101  */
+  int32_t obs_landmarks; /* 1: obs has 2L extra rows (shuffle=True layout, :65-68,:141-142)    */
+  double agents_size;    /* 0.25: reach radius, 2x = collision distance   :49,:123,:155        */
+} SmarlCollisionParams;
+
+/* CollisionAvoidance.reset/_restart (:72-98) for shuffle=False: state <- start, done <- 0.
+ *   start_x,start_y,pos_x,pos_y f64 [A][ld]   done u8 [A][ld]   landmarks f64 [2L][ld] rows
+ *   lx0,ly0,lx1,...   obs f32 [2A(+2L)][ld] (NULL ok) */
+int smarl_collision_reset(const SmarlCollisionParams* p, const double* start_x,
+                          const double* start_y, const double* landmarks, double* pos_x,
+                          double* pos_y, uint8_t* done, float* obs, int64_t n_envs, int64_t ld,
+                          smarl_stream_t stream);
+
+/* One CollisionAvoidance.step (:139-148 = transition :103-125 + reward :127-130/:158-162 +
+ * constraint :132-133/:150-156 + check_done :135-136) with MetaAgent.act fused.  Envs whose
+ * agents were all done before the call are past their episode end (main.py:51): frozen,
+ * reward/cost/penalty 0.
+ *   pos_x,pos_y f64 [A][ld] in/out   done u8 [A][ld] in/out
+ *   actions f32 [2A][ld] rows dx0,dy0,dx1,... (the reference's policies emit fp32, agent.py:124-125)
+ *   landmarks f64 [2L][ld]   obs f32 [2A(+2L)][ld]   reward f32 [A][ld]   cost i32 [ld]
+ *   done_out u8 [A][ld]: this step's done flags for a rollout buffer (NULL ok) */
+int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x, double* pos_y,
+                         uint8_t* done, const float* actions, const double* landmarks, float* obs,
+                         float* reward, int32_t* cost, uint8_t* done_out, const double* lambdas,
+                         float* penalty, int64_t n_envs, int64_t ld, smarl_stream_t stream);
+
+/* Fused open-loop episode.  actions f32 [T][2A][ld].  n_active i32 [ld] out = episode length
+ * T' (steps until all agents done, NULL ok).  C i32 [1][ld]. */
+int smarl_collision_rollout(const SmarlCollisionParams* p, const SmarlAccounting* acc,
+                            const double* start_x, const double* start_y, const double* landmarks,
+                            const float* actions, const double* lambdas, double* final_x,
+                            double* final_y, uint8_t* final_done, int32_t* n_active, float* R,
+                            float* modR, int32_t* C, float* G, float* g_scratch, double* stats,
+                            double* stats_scratch, int64_t n_envs, int64_t ld,
+                            smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Rollout accounting over a device rollout buffer filled by the *_step calls
+ * (closed-loop mode: a policy chooses actions between steps).
+ * ---------------------------------------------------------------------------------- */
+enum { SMARL_COST_U8 = 0, SMARL_COST_I32 = 1 };
+
+/* MetaAgent.act's penalty for rewards/costs that did not come from a *_step call
+ * (meta_agent.py:21-22): penalty[t][e] = sum_k lambda_k cost[t][k][e].
+ *   cost [T][K][ld] u8 or i32, lambdas f64 [K], penalty f32 [T][ld] */
+int smarl_rollout_penalty(const void* cost, int32_t cost_dtype, const double* lambdas,
+                          float* penalty, int32_t n_constraints, int32_t n_steps, int64_t n_envs,
+                          int64_t ld, smarl_stream_t stream);
+
+/* Buffer.step (safe_multi_agent_RL/buffer.py:30-39), MetaAgent.step (meta_agent.py:25-30)
+ * and compute_returns (agent.py:129-132, :200-206) for n_envs episodes at once:
+ *   R_a = sum_t gamma^t r[t,a]   modR_a = sum_t gamma^t (r[t,a] - pen[t])   C_k = sum_t c[t,k]
+ *   reward f32 [T][A][ld]   cost [T][K][ld]   penalty f32 [T][ld] (NULL = 0)
+ *   R, modR f32 [A][ld]     C i32 [K][ld]     G f32 [T][A][ld] per acc->g_mode
+ *   stats/stats_scratch as above (NULL to skip). */
+int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const void* cost,
+                          int32_t cost_dtype, const float* penalty, float* R, float* modR,
+                          int32_t* C, float* G, double* stats, double* stats_scratch,
+                          int32_t n_agents, int32_t n_constraints, int64_t n_envs, int64_t ld,
+                          smarl_stream_t stream);
+
+/* MetaAgent.update (meta_agent.py:32-39, leq=True) from an (all-reduced) stats vector:
+ *   lambda_k <- max(0, lambda_k + lr * (stats[k] / stats[count] - thr_k)).
+ * stats may be the sum of several GPUs' / rollouts' vectors (every slot is additive). */
+int smarl_lambda_update(double* lambdas, const double* stats, const double* thresholds, double lr,
+                        int32_t n_agents, int32_t n_constraints, smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a host-side caller with numpy arrays binds).  Inputs are
+ * HOST arrays (pageable, or pinned for full PCIe speed) in the same agent-major layout with
+ * ld = smarl_host_session_ld(); the call pipelines env chunks over two streams (H2D copy,
+ * fused rollout, D2H copy overlap) on the current device and returns when the episode
+ * products are in the host arrays.  Synchronous; one call at a time per session.
+ * ---------------------------------------------------------------------------------- */
+typedef struct SmarlHostSession SmarlHostSession;   /* opaque: streams + device buffers */
+
+int smarl_host_session_create(SmarlHostSession** out, int32_t n_agents, int32_t n_constraints,
+                              int32_t n_steps, int64_t n_envs);
+void smarl_host_session_destroy(SmarlHostSession* s);
+/* ld (= padded n_envs) the host arrays of this session must use. */
+int64_t smarl_host_session_ld(const SmarlHostSession* s);
+
+/* CoverageDiscrete episode from host buffers.  p->lut / p->weights and lambdas_h are HOST
+ * pointers here.  start_x_h,start_y_h u8 [A][ld]; actions_h u8 [T][A][ld];
+ * R_h, modR_h f32 [A][ld]; C_h i32 [A][ld]; stats_h f64 [smarl_stats_len] (NULL ok). */
+int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                const uint8_t* start_y_h, const uint8_t* actions_h,
+                                const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
+                                double* stats_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMARL_H_ */

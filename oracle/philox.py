@@ -1,0 +1,73 @@
+"""Philox4x32-10 (Salmon et al., SC'11) in numpy.  TEST INFRASTRUCTURE ONLY.
+
+The reference draws Congestion's action noise from Python's unseeded ``random``
+(envs/congestion.py:4,64,67), so it has no reproducible stream to match.  The B200
+path uses a counter-based generator keyed by the *global* env id, so results do not
+depend on how envs are sharded over GPUs:
+
+    out = philox4x32_10(counter=(env_lo, env_hi, t, agent >> 1), key=(seed_lo, seed_hi))
+    agent a uses words (w1, w2) = (out[2*(a&1)], out[2*(a&1)+1])
+    u1 = w1 * 2**-32,  u2 = w2 * 2**-32          (exact in f64)
+    move = action if u1 < 1 - noise else int(u2 * 5)      (congestion.py:64-67)
+
+In integers:  keep <=> w1 < ceil((1-noise) * 2**32);  int(u2*5) == (w2 * 5) >> 32.
+This file restates the generator so the test-suite can replay the very same
+uniforms through the reference's ``random()`` hook and through the oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """All arguments broadcastable integer arrays holding uint32 values; returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)), lo1, (hi0 ^ c3 ^ np.uint64(k1)), lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def congestion_words(seed, env_ids, t, n_agents):
+    """uint32 words (w1, w2), each [E, A], for global env ids ``env_ids`` at step ``t``."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    E = env_ids.shape[0]
+    pairs = (n_agents + 1) // 2
+    c0 = (env_ids & MASK)[:, None]
+    c1 = (env_ids >> np.uint64(32))[:, None]
+    c2 = np.full((1, 1), t, dtype=np.uint64)
+    c3 = np.arange(pairs, dtype=np.uint64)[None, :]
+    o = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)   # 4 x [E, pairs]
+    w1 = np.empty((E, 2 * pairs), dtype=np.uint32)
+    w2 = np.empty((E, 2 * pairs), dtype=np.uint32)
+    w1[:, 0::2], w2[:, 0::2] = o[0], o[1]
+    w1[:, 1::2], w2[:, 1::2] = o[2], o[3]
+    return w1[:, :n_agents], w2[:, :n_agents]
+
+
+def congestion_uniforms(seed, env_ids, t, n_agents):
+    """The f64 uniforms (u1, u2) in [0,1) equivalent to the device's integer tests."""
+    w1, w2 = congestion_words(seed, env_ids, t, n_agents)
+    return w1.astype(np.float64) * 2.0 ** -32, w2.astype(np.float64) * 2.0 ** -32
+
+
+def keep_threshold(noise):
+    """Smallest integer thr with  (w * 2**-32 < 1 - noise)  <=>  (w < thr)  for uint32 w."""
+    import math
+    from fractions import Fraction
+    lim = Fraction(1 - noise) * (1 << 32)        # exact value of the f64 ``1 - noise`` times 2**32
+    return min(1 << 32, max(0, math.ceil(lim)))

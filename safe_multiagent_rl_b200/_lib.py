@@ -1,0 +1,118 @@
+"""ctypes binding of libsmarl.so (include/smarl.h).  No CPU fallback: if the library is
+missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_ptr = C.c_void_p
+
+
+class CoverageParams(C.Structure):
+    _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("lut_len", C.c_int32),
+                ("reserved", C.c_int32), ("lut", c_ptr), ("weights", c_ptr)]
+
+
+class Accounting(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("n_steps", C.c_int32), ("g_mode", C.c_int32),
+                ("thresholds", c_ptr)]
+
+
+class CongestionParams(C.Structure):
+    _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("demand", c_ptr),
+                ("noise_mode", C.c_int32), ("reserved", C.c_int32),
+                ("keep_threshold", C.c_uint64), ("seed", C.c_uint64), ("env_offset", C.c_int64)]
+
+
+class CollisionParams(C.Structure):
+    _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("n_landmarks", C.c_int32),
+                ("obs_landmarks", C.c_int32), ("agents_size", C.c_double)]
+
+
+P = C.POINTER
+i32, i64, f64 = C.c_int32, C.c_int64, C.c_double
+
+# name -> (restype, argtypes); every symbol include/smarl.h declares.
+PROTOTYPES = {
+    "smarl_abi_version": (C.c_int, []),
+    "smarl_last_error": (C.c_char_p, []),
+    "smarl_device_info": (C.c_int, [P(C.c_int), P(C.c_int), P(C.c_int)]),
+    "smarl_grid_reset": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
+    "smarl_coverage_step": (C.c_int, [P(CoverageParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                      c_ptr, c_ptr, i64, i64, c_ptr]),
+    "smarl_stats_len": (i32, [i32, i32]),
+    "smarl_stats_scratch_len": (i64, [i32, i32, i64]),
+    "smarl_coverage_rollout": (C.c_int, [P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         i64, i64, c_ptr]),
+    "smarl_congestion_step": (C.c_int, [P(CongestionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                        c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
+    "smarl_congestion_rollout": (C.c_int, [P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
+                                           c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                           c_ptr, i64, i64, c_ptr]),
+    "smarl_collision_reset": (C.c_int, [P(CollisionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                        c_ptr, i64, i64, c_ptr]),
+    "smarl_collision_step": (C.c_int, [P(CollisionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, i64, i64, c_ptr]),
+    "smarl_collision_rollout": (C.c_int, [P(CollisionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
+                                          c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                          c_ptr, c_ptr, c_ptr, i64, i64, c_ptr]),
+    "smarl_rollout_penalty": (C.c_int, [c_ptr, i32, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
+    "smarl_rollout_returns": (C.c_int, [P(Accounting), c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr,
+                                        c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
+    "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
+    "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64]),
+    "smarl_host_session_destroy": (None, [c_ptr]),
+    "smarl_host_session_ld": (i64, [c_ptr]),
+    "smarl_host_coverage_rollout": (C.c_int, [c_ptr, P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr,
+                                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+}
+
+COST_U8, COST_I32 = 0, 1
+_lib = None
+
+
+class SmarlError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.environ.get("SMARL_LIB", _build.LIB_PATH)
+
+
+def load():
+    """Load libsmarl.so and bind every prototype.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SmarlError(f"{path} not found: build it with `python -m safe_multiagent_rl_b200.build` "
+                         "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.smarl_abi_version() != 1:
+        raise SmarlError("libsmarl ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().smarl_last_error().decode()
+        raise SmarlError(f"libsmarl error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,247 @@
+// CollisionAvoidance on sm_100a (float64 state).  One thread owns one env: a warp moves
+// 32 x 8 B = 256 contiguous bytes per f64 row and 128 B per f32 / i32 row, all agent-major SoA.
+//
+// This file restates the reference's float64 arithmetic operation by operation so that
+// positions, done flags and collision counts are bit-exact; it is compiled with -fmad=false
+// and uses the _rn intrinsics wherever a contraction would change a rounding.
+#include "common.cuh"
+#include "stats.cuh"
+
+namespace smarl {
+
+struct CollisionStepArgs {
+  double* pos_x;
+  double* pos_y;
+  uint8_t* done;
+  const float* actions;       // [2A][ld]
+  const double* landmarks;    // [2L][ld]
+  float* obs;
+  float* reward;
+  int32_t* cost;
+  uint8_t* done_out;
+  const double* lambdas;
+  float* penalty;
+  int64_t n_envs;
+  int64_t ld;
+  double size;
+  double agents_size;
+  int32_t L;
+  int32_t obs_landmarks;
+};
+
+constexpr int kCollThreads = 128;
+
+// numpy's pairwise float64 sum of n <= 128 contiguous values (what np.sum does to the A
+// per-agent minima at collision_avoidance.py:161): n < 8 sequential; otherwise 8 running
+// accumulators over blocks of 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail.
+template <int N>
+__device__ __forceinline__ double numpy_sum(const double (&v)[N]) {
+  if (N < 8) {
+    double s = 0.0;   // np.sum starts from the first element; 0.0 + v0 == v0 exactly (v0 >= 0)
+#pragma unroll
+    for (int i = 0; i < N; ++i) s = __dadd_rn(s, v[i]);
+    return s;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j < N ? j : 0];
+  constexpr int kFull = N - (N % 8);
+#pragma unroll
+  for (int i = 8; i < kFull; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], v[(i + j) < N ? (i + j) : 0]);
+  }
+  double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+  for (int i = kFull; i < N; ++i) s = __dadd_rn(s, v[i]);
+  return s;
+}
+
+// One CollisionAvoidance.step for one env held in registers.  Returns the env reward (same for
+// every agent) and the collision count; updates px/py/done_mask in place.
+template <int A>
+__device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)[A], uint32_t& done_mask,
+                                                   const float (&adx)[A], const float (&ady)[A],
+                                                   const double* __restrict__ lm, int64_t ld, int L,
+                                                   double size, double agents_size, double& reward,
+                                                   int& collisions) {
+  // transition, collision_avoidance.py:103-121
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    if ((done_mask >> i) & 1u) continue;
+    double dx = (double)adx[i], dy = (double)ady[i];
+    // :113  fp32-origin components: dx**2 == dx*dx exactly, so this is the reference's norm
+    const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    if (norm > 1.0) {                                       // :114-117
+      dx = __ddiv_rn(dx, norm);
+      dy = __ddiv_rn(dy, norm);
+    }
+    px[i] = fmax(0.0, fmin(size, __dadd_rn(px[i], dx)));   // :118
+    py[i] = fmax(0.0, fmin(size, __dadd_rn(py[i], dy)));   // :119
+  }
+  // landmark reach (:122-124) and per-agent min landmark distance (:158-161)
+  double mind[A];
+  uint32_t reach = 0u;
+#pragma unroll
+  for (int i = 0; i < A; ++i) mind[i] = 1.0e300;
+  for (int l = 0; l < L; ++l) {
+    const double lx = lm[(2 * l) * ld], ly = lm[(2 * l + 1) * ld];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const double ax = __dadd_rn(px[i], -lx), ay = __dadd_rn(py[i], -ly);
+      // np.linalg.norm(state - land) = sqrt(ddot) = sqrt(fma(ay, ay, ax*ax))   [probed, OpenBLAS]
+      const double nrm = __dsqrt_rn(__fma_rn(ay, ay, __dmul_rn(ax, ax)));
+      reach |= (nrm < agents_size) ? (1u << i) : 0u;
+      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2)
+      const double bx = __dadd_rn(lx, -px[i]), by = __dadd_rn(ly, -py[i]);
+      const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)));
+      mind[i] = fmin(mind[i], d);
+    }
+  }
+  done_mask |= reach & ~done_mask;   // only agents that moved this step are tested; done ones stay done
+  reward = -numpy_sum<A>(mind);      // :127-130, all agents incl. done ones
+  // collisions among agents not done after this step (:150-156)
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+#pragma unroll
+    for (int j = i + 1; j < A; ++j) {
+      const double dx = __dadd_rn(px[i], -px[j]), dy = __dadd_rn(py[i], -py[j]);
+      const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      bool hit = false;
+      const double lim = 2.0 * agents_size;
+      const double lim2 = lim * lim;
+      if (q < lim2 * 1.000001) hit = (q < lim2 * 0.999999) || (__dsqrt_rn(q) < lim);
+      n += (hit && !((done_mask >> i) & 1u) && !((done_mask >> j) & 1u)) ? 1 : 0;
+    }
+  }
+  collisions = n;
+}
+
+template <int A>
+__global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const CollisionStepArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
+  if (e >= a.n_envs) return;
+  const int64_t ld = a.ld;
+  double px[A], py[A];
+  float adx[A], ady[A];
+  uint32_t done_mask = 0u;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    px[i] = a.pos_x[i * ld + e];
+    py[i] = a.pos_y[i * ld + e];
+    adx[i] = a.actions[(2 * i) * ld + e];
+    ady[i] = a.actions[(2 * i + 1) * ld + e];
+    done_mask |= a.done[i * ld + e] ? (1u << i) : 0u;
+  }
+  const uint32_t all = A == 32 ? 0xFFFFFFFFu : ((1u << A) - 1u);
+  const bool active = done_mask != all;                       // main.py:51: episode already over
+  double reward = 0.0;
+  int collisions = 0;
+  if (active)
+    collision_env_step<A>(px, py, done_mask, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size,
+                          reward, collisions);
+  const float rf = (float)reward;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    if (active) {
+      a.pos_x[i * ld + e] = px[i];
+      a.pos_y[i * ld + e] = py[i];
+      a.done[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
+    }
+    if (a.done_out) a.done_out[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
+    a.reward[i * ld + e] = rf;
+    if (a.obs) {
+      a.obs[(2 * i) * ld + e] = (float)px[i];
+      a.obs[(2 * i + 1) * ld + e] = (float)py[i];
+    }
+  }
+  if (a.obs && a.obs_landmarks) {                             // :141-142 (shuffle=True layout)
+    for (int l = 0; l < 2 * a.L; ++l) a.obs[(2 * A + l) * ld + e] = (float)a.landmarks[l * ld + e];
+  }
+  a.cost[e] = collisions;
+  if (a.penalty) a.penalty[e] = (float)(__ldg(a.lambdas) * (double)collisions);   // meta_agent.py:21-22
+}
+
+__global__ void collision_reset_kernel(const double* __restrict__ start_x, const double* __restrict__ start_y,
+                                       const double* __restrict__ landmarks, double* __restrict__ pos_x,
+                                       double* __restrict__ pos_y, uint8_t* __restrict__ done,
+                                       float* __restrict__ obs, int A, int L, int obs_landmarks,
+                                       int64_t n_envs, int64_t ld) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  for (int i = 0; i < A; ++i) {
+    const double x = start_x[i * ld + e], y = start_y[i * ld + e];
+    pos_x[i * ld + e] = x;
+    pos_y[i * ld + e] = y;
+    done[i * ld + e] = 0;
+    if (obs) {
+      obs[(2 * i) * ld + e] = (float)x;
+      obs[(2 * i + 1) * ld + e] = (float)y;
+    }
+  }
+  if (obs && obs_landmarks)
+    for (int l = 0; l < 2 * L; ++l) obs[(2 * A + l) * ld + e] = (float)landmarks[l * ld + e];
+}
+
+static int check_collision(const SmarlCollisionParams* p) {
+  SMARL_REQUIRE(p != nullptr, "params is NULL");
+  SMARL_REQUIRE(p->size >= 1, "size=%d must be >= 1", p->size);
+  SMARL_REQUIRE(p->n_landmarks >= 1 && p->n_landmarks <= 64, "n_landmarks=%d outside 1..64", p->n_landmarks);
+  SMARL_REQUIRE(p->agents_size > 0.0, "agents_size must be positive");
+  return SMARL_OK;
+}
+
+}  // namespace smarl
+
+using namespace smarl;
+
+extern "C" int smarl_collision_reset(const SmarlCollisionParams* p, const double* start_x,
+                                     const double* start_y, const double* landmarks, double* pos_x,
+                                     double* pos_y, uint8_t* done, float* obs, int64_t n_envs, int64_t ld,
+                                     smarl_stream_t stream) {
+  if (int rc = check_collision(p)) return rc;
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(start_x && start_y && landmarks && pos_x && pos_y && done, "null required pointer");
+  SMARL_REQUIRE(p->n_agents >= 1 && p->n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", p->n_agents);
+  const unsigned grid = (unsigned)((n_envs + 255) / 256);
+  collision_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(start_x, start_y, landmarks, pos_x, pos_y,
+                                                                 done, obs, p->n_agents, p->n_landmarks,
+                                                                 p->obs_landmarks, n_envs, ld);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
+extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x, double* pos_y,
+                                    uint8_t* done, const float* actions, const double* landmarks,
+                                    float* obs, float* reward, int32_t* cost, uint8_t* done_out,
+                                    const double* lambdas, float* penalty, int64_t n_envs, int64_t ld,
+                                    smarl_stream_t stream) {
+  if (int rc = check_collision(p)) return rc;
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(pos_x && pos_y && done && actions && landmarks && reward && cost, "null required pointer");
+  SMARL_REQUIRE((lambdas == nullptr) == (penalty == nullptr), "lambdas and penalty go together");
+  CollisionStepArgs a;
+  a.pos_x = pos_x; a.pos_y = pos_y; a.done = done; a.actions = actions; a.landmarks = landmarks;
+  a.obs = obs; a.reward = reward; a.cost = cost; a.done_out = done_out; a.lambdas = lambdas;
+  a.penalty = penalty; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size;
+  a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
+  const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
+  SMARL_DISPATCH_A(p->n_agents,
+                   collision_step_kernel<kA><<<grid, kCollThreads, 0, (cudaStream_t)stream>>>(a));
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
+extern "C" int smarl_collision_rollout(const SmarlCollisionParams* p, const SmarlAccounting* acc,
+                                       const double* start_x, const double* start_y,
+                                       const double* landmarks, const float* actions,
+                                       const double* lambdas, double* final_x, double* final_y,
+                                       uint8_t* final_done, int32_t* n_active, float* R, float* modR,
+                                       int32_t* C, float* G, float* g_scratch, double* stats,
+                                       double* stats_scratch, int64_t n_envs, int64_t ld,
+                                       smarl_stream_t stream) {
+  set_error("smarl_collision_rollout: fused Collision rollout not built yet; use the step + returns path");
+  return SMARL_EUNSUPPORTED;
+}

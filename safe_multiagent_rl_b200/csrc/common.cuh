@@ -1,0 +1,162 @@
+// Shared device/host helpers for libsmarl (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/smarl.h"
+
+namespace smarl {
+
+// ---------------------------------------------------------------------------------------
+// Error plumbing (thread-local message behind smarl_last_error()).
+// ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define SMARL_REQUIRE(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::smarl::set_error(__VA_ARGS__);          \
+      return SMARL_EINVAL;                      \
+    }                                           \
+  } while (0)
+
+#define SMARL_CUDA(call)                                                                  \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      ::smarl::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__),       \
+                         __FILE__, __LINE__);                                             \
+      return SMARL_ECUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Checks the shared layout contract of smarl.h for one call.
+int check_layout(int64_t n_envs, int64_t ld);
+
+int sm_count();
+
+// Dispatch a compile-time agent count 1..32.
+#define SMARL_CASE_A(N, ...) \
+  case N: {                  \
+    constexpr int kA = N;    \
+    __VA_ARGS__;             \
+  } break;
+#define SMARL_DISPATCH_A(value, ...)                                                         \
+  switch (value) {                                                                           \
+    SMARL_CASE_A(1, __VA_ARGS__) SMARL_CASE_A(2, __VA_ARGS__) SMARL_CASE_A(3, __VA_ARGS__)   \
+    SMARL_CASE_A(4, __VA_ARGS__) SMARL_CASE_A(5, __VA_ARGS__) SMARL_CASE_A(6, __VA_ARGS__)   \
+    SMARL_CASE_A(7, __VA_ARGS__) SMARL_CASE_A(8, __VA_ARGS__) SMARL_CASE_A(9, __VA_ARGS__)   \
+    SMARL_CASE_A(10, __VA_ARGS__) SMARL_CASE_A(11, __VA_ARGS__) SMARL_CASE_A(12, __VA_ARGS__) \
+    SMARL_CASE_A(13, __VA_ARGS__) SMARL_CASE_A(14, __VA_ARGS__) SMARL_CASE_A(15, __VA_ARGS__) \
+    SMARL_CASE_A(16, __VA_ARGS__) SMARL_CASE_A(17, __VA_ARGS__) SMARL_CASE_A(18, __VA_ARGS__) \
+    SMARL_CASE_A(19, __VA_ARGS__) SMARL_CASE_A(20, __VA_ARGS__) SMARL_CASE_A(21, __VA_ARGS__) \
+    SMARL_CASE_A(22, __VA_ARGS__) SMARL_CASE_A(23, __VA_ARGS__) SMARL_CASE_A(24, __VA_ARGS__) \
+    SMARL_CASE_A(25, __VA_ARGS__) SMARL_CASE_A(26, __VA_ARGS__) SMARL_CASE_A(27, __VA_ARGS__) \
+    SMARL_CASE_A(28, __VA_ARGS__) SMARL_CASE_A(29, __VA_ARGS__) SMARL_CASE_A(30, __VA_ARGS__) \
+    SMARL_CASE_A(31, __VA_ARGS__) SMARL_CASE_A(32, __VA_ARGS__)                               \
+    default:                                                                                 \
+      ::smarl::set_error("n_agents=%d outside 1..32", (int)(value));                         \
+      return SMARL_EUNSUPPORTED;                                                             \
+  }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// Streaming global access.  Every byte of the batched state is touched once per launch,
+// so loads bypass L1 allocation and stores are marked evict-first ("streaming").
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const void* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_i4(void* p, int4 v) {
+  asm volatile("st.global.cs.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_d2(void* p, double2 v) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// Byte k (0..3) of a packed word as float, exact: PRMT builds 0x4B0000bb (= 2^23 + b), one FADD.
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k) {
+  uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k);
+  return __uint_as_float(bits) - 8388608.0f;
+}
+__device__ __forceinline__ float4 bytes_to_float4(uint32_t w) {
+  return make_float4(byte_to_float(w, 0), byte_to_float(w, 1), byte_to_float(w, 2),
+                     byte_to_float(w, 3));
+}
+
+// ---------------------------------------------------------------------------------------
+// Grid moves on four envs at once (one byte per env).  Direction table shared by
+// envs/coverage.py:176 and envs/congestion.py:55:  0:(+1,0) 1:(-1,0) 2:(0,-1) 3:(0,+1) 4:stay,
+// then clamp to [0,size] (coverage.py:185-186, congestion.py:70-71).  Valid bytes are <= 254,
+// so +1 never carries into the neighbouring env; padding lanes may hold garbage, which the
+// clamp pulls into range (and a carry out of a padding byte only reaches higher padding bytes).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_move4(uint32_t& xw, uint32_t& yw, uint32_t aw, uint32_t size4) {
+  const uint32_t k1 = 0x01010101u;
+  const uint32_t b0 = aw & k1, b1 = (aw >> 1) & k1, b2 = (aw >> 2) & k1;
+  const uint32_t inc_x = (b0 | b1 | b2) ^ k1;   // a == 0
+  const uint32_t dec_x = b0 & ~b1;              // a == 1  (a <= 4, so b0 => !b2)
+  const uint32_t dec_y = b1 & ~b0;              // a == 2
+  const uint32_t inc_y = b0 & b1;               // a == 3
+  xw = __vsubus4(__vminu4(xw + inc_x, size4), dec_x);
+  yw = __vsubus4(__vminu4(yw + inc_y, size4), dec_y);
+}
+// cost byte = 1 for a non-stay action (coverage.py:191-196: [1,1,1,1,0][a]).
+__device__ __forceinline__ uint32_t move_cost4(uint32_t aw) { return ((aw >> 2) & 0x01010101u) ^ 0x01010101u; }
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (oracle/philox.py restates it; Random123 known answers are tested there).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------
+// Deterministic block reduction of NV doubles per thread -> partial[blockIdx.x][NV] written
+// by thread 0.  Fixed shuffle tree + fixed warp order: bit-reproducible for a given launch
+// shape.  `smem` needs NV * (blockDim.x/32) doubles.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace smarl

@@ -1,0 +1,333 @@
+// Rollout accounting over a device rollout buffer + library plumbing (errors, device info).
+//
+// Replaces, for n_envs episodes at once: Buffer.step (safe_multi_agent_RL/buffer.py:30-39),
+// MetaAgent.act's penalty and MetaAgent.step/update (meta_agent.py:18-39) and the learners'
+// compute_returns (agent.py:129-132, :200-206).  All sums are carried in f64 like the
+// reference; only the stored products are f32.
+#include <stdarg.h>
+
+#include "stats.cuh"
+
+namespace smarl {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_layout(int64_t n_envs, int64_t ld) {
+  SMARL_REQUIRE(n_envs >= 1, "n_envs=%lld must be >= 1", (long long)n_envs);
+  SMARL_REQUIRE(ld >= n_envs && ld % 16 == 0, "ld=%lld must be a multiple of 16 and >= n_envs=%lld",
+                (long long)ld, (long long)n_envs);
+  return SMARL_OK;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      cached = n;
+  }
+  return cached ? cached : 148;
+}
+
+constexpr int kAccThreads = 128;
+
+template <typename CT> struct CostVec;
+template <> struct CostVec<uint8_t> {
+  static __device__ __forceinline__ void load(const uint8_t* p, int (&c)[4]) {
+    const uint32_t w = ld_stream_u32(p);
+    c[0] = w & 0xFF; c[1] = (w >> 8) & 0xFF; c[2] = (w >> 16) & 0xFF; c[3] = w >> 24;
+  }
+};
+template <> struct CostVec<int32_t> {
+  static __device__ __forceinline__ void load(const int32_t* p, int (&c)[4]) {
+    const float4 f = ld_stream_f4(p);
+    c[0] = __float_as_int(f.x); c[1] = __float_as_int(f.y); c[2] = __float_as_int(f.z); c[3] = __float_as_int(f.w);
+  }
+};
+
+// penalty[t][e] = sum_k lambda_k * cost[t][k][e]          (meta_agent.py:21-22)
+template <typename CT>
+__global__ void __launch_bounds__(kAccThreads)
+penalty_kernel(const CT* __restrict__ cost, const double* __restrict__ lambdas, float* __restrict__ penalty,
+               int K, int64_t n_groups, int64_t ld) {
+  const int64_t g = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
+  if (g >= n_groups) return;
+  const int64_t e0 = g * 4;
+  const int64_t t = blockIdx.y;
+  double pen[4] = {0, 0, 0, 0};
+  for (int k = 0; k < K; ++k) {
+    int c[4];
+    CostVec<CT>::load(cost + (t * K + k) * ld + e0, c);
+    const double lam = __ldg(lambdas + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pen[j] += lam * (double)c[j];
+  }
+  st_stream_f4(penalty + t * ld + e0, make_float4((float)pen[0], (float)pen[1], (float)pen[2], (float)pen[3]));
+}
+
+struct ReturnsArgs {
+  const float* reward;     // [T][A][ld]
+  const void* cost;        // [T][K][ld]
+  const float* penalty;    // [T][ld] or NULL
+  float* R;
+  float* modR;
+  int32_t* C;
+  float* G;
+  double* partials;        // [n_chunks][stats_len] or NULL
+  const double* thresholds;
+  double gamma;
+  int64_t n_groups;
+  int64_t n_envs;
+  int64_t ld;
+  int32_t A, K, T, g_mode;
+};
+
+// One CTA = one row (agent a, or constraint k) x 512 envs.  Rows of the same env chunk get
+// consecutive block ids so that they run together and share the chunk's penalty rows in L2.
+template <typename CT>
+__global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs a) {
+  __shared__ double s_red[kAccThreads / 32];
+  const int rows = a.A + a.K;
+  const int row = blockIdx.x % rows;
+  const int64_t chunk = blockIdx.x / rows;
+  const int64_t g = chunk * kAccThreads + threadIdx.x;
+  const bool live = g < a.n_groups;
+  const int64_t e0 = (live ? g : 0) * 4;
+  const int64_t ld = a.ld;
+  const int T = a.T;
+  bool valid[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) valid[k] = live && (e0 + k < a.n_envs);
+  double* out = a.partials ? a.partials + chunk * stats_len(a.A, a.K) : nullptr;
+
+  if (row < a.A) {
+    double raw[4] = {0, 0, 0, 0}, mod[4] = {0, 0, 0, 0};
+    const double gamma = a.gamma;
+    if (a.g_mode != 2) {
+      // Backward Horner: G_t = m_t + gamma G_{t+1} (agent.py:200-206); G_0 is the discounted
+      // episode return of buffer.py:31-35.
+#pragma unroll 4
+      for (int t = T - 1; t >= 0; --t) {
+        const float4 r = ld_stream_f4(a.reward + ((int64_t)t * a.A + row) * ld + e0);
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+        const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          raw[k] = (double)rr[k] + gamma * raw[k];
+          mod[k] = ((double)rr[k] - (double)pp[k]) + gamma * mod[k];
+        }
+        if (a.g_mode == 1 && live)
+          st_stream_f4(a.G + ((int64_t)t * a.A + row) * ld + e0,
+                       make_float4((float)mod[0], (float)mod[1], (float)mod[2], (float)mod[3]));
+      }
+    } else {
+      // Forward: gamma^t * m_t per step (agent.py:129-132) and their running sums.
+      double disc = 1.0;
+#pragma unroll 4
+      for (int t = 0; t < T; ++t) {
+        const float4 r = ld_stream_f4(a.reward + ((int64_t)t * a.A + row) * ld + e0);
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+        const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+        double term[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          raw[k] += disc * (double)rr[k];
+          term[k] = disc * ((double)rr[k] - (double)pp[k]);
+          mod[k] += term[k];
+        }
+        if (live)
+          st_stream_f4(a.G + ((int64_t)t * a.A + row) * ld + e0,
+                       make_float4((float)term[0], (float)term[1], (float)term[2], (float)term[3]));
+        disc *= gamma;
+      }
+    }
+    if (live) {
+      st_stream_f4(a.R + (int64_t)row * ld + e0, make_float4((float)raw[0], (float)raw[1], (float)raw[2], (float)raw[3]));
+      st_stream_f4(a.modR + (int64_t)row * ld + e0, make_float4((float)mod[0], (float)mod[1], (float)mod[2], (float)mod[3]));
+    }
+    if (out) {
+      double v_raw = 0.0, v_mod = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v_raw += valid[k] ? raw[k] : 0.0;
+        v_mod += valid[k] ? mod[k] : 0.0;
+      }
+      const double b_raw = block_sum<kAccThreads>(v_raw, s_red);
+      const double b_mod = block_sum<kAccThreads>(v_mod, s_red);
+      if (threadIdx.x == 0) {
+        out[2 * a.K + row] = b_raw;
+        out[2 * a.K + a.A + row] = b_mod;
+        if (row == 0) out[2 * a.K + 2 * a.A] = 0.0;
+      }
+    }
+  } else {
+    // C_k = sum_t c[t,k]  (buffer.py:39, meta_agent.py:28)
+    const int k = row - a.A;
+    const CT* cost = static_cast<const CT*>(a.cost);
+    int sum[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+      int c[4];
+      CostVec<CT>::load(cost + ((int64_t)t * a.K + k) * ld + e0, c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sum[j] += c[j];
+    }
+    if (live) st_stream_i4(a.C + (int64_t)k * ld + e0, make_int4(sum[0], sum[1], sum[2], sum[3]));
+    if (out) {
+      const double thr = a.thresholds ? __ldg(a.thresholds + k) : 0.0;
+      double c = 0.0, viol = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c += valid[j] ? (double)sum[j] : 0.0;
+        viol += (valid[j] && a.thresholds && (double)sum[j] > thr) ? 1.0 : 0.0;
+      }
+      const double bc = block_sum<kAccThreads>(c, s_red);
+      const double bv = block_sum<kAccThreads>(viol, s_red);
+      if (threadIdx.x == 0) {
+        out[k] = bc;
+        out[a.K + k] = bv;
+      }
+    }
+  }
+}
+
+// stats[j] = sum over rows of partials[row][j], fixed order; the count slot is n_envs.
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const double* __restrict__ partials, int64_t n_rows, int n_stats, double count,
+                      double* __restrict__ stats) {
+  __shared__ double s_red[256 / 32];
+  const int j = blockIdx.x;
+  if (j == n_stats - 1) {
+    if (threadIdx.x == 0) stats[j] = count;
+    return;
+  }
+  double v = 0.0;
+  for (int64_t r = threadIdx.x; r < n_rows; r += 256) v += partials[r * n_stats + j];
+  const double b = block_sum<256>(v, s_red);
+  if (threadIdx.x == 0) stats[j] = b;
+}
+
+int launch_stats_finalize(const double* partials, int64_t n_rows, int n_agents, int n_constraints,
+                          int64_t n_envs, double* stats, cudaStream_t stream) {
+  const int n = stats_len(n_agents, n_constraints);
+  stats_finalize_kernel<<<n, 256, 0, stream>>>(partials, n_rows, n, (double)n_envs, stats);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
+// lambda_k <- max(0, lambda_k + lr * (mean C_k - thr_k))      (meta_agent.py:32-36)
+__global__ void lambda_update_kernel(double* lambdas, const double* __restrict__ stats,
+                                     const double* __restrict__ thresholds, double lr, int A, int K) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  const double count = stats[2 * K + 2 * A];
+  const double mean = stats[k] / count;
+  lambdas[k] = fmax(lambdas[k] + lr * (mean - thresholds[k]), 0.0);
+}
+
+}  // namespace smarl
+
+using namespace smarl;
+
+extern "C" int smarl_abi_version(void) { return SMARL_ABI_VERSION; }
+extern "C" const char* smarl_last_error(void) { return g_error; }
+
+extern "C" int smarl_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  SMARL_CUDA(cudaGetDevice(&dev));
+  if (sm) SMARL_CUDA(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+  if (major) SMARL_CUDA(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (minor) SMARL_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return SMARL_OK;
+}
+
+extern "C" int32_t smarl_stats_len(int32_t n_agents, int32_t n_constraints) {
+  return stats_len(n_agents, n_constraints);
+}
+
+extern "C" int64_t smarl_stats_scratch_len(int32_t n_agents, int32_t n_constraints, int64_t n_envs) {
+  const int64_t n_groups = (n_envs + 3) / 4;
+  const int64_t n_chunks = (n_groups + kAccThreads - 1) / kAccThreads;
+  return n_chunks * stats_len(n_agents, n_constraints);
+}
+
+extern "C" int smarl_rollout_penalty(const void* cost, int32_t cost_dtype, const double* lambdas,
+                                     float* penalty, int32_t K, int32_t T, int64_t n_envs, int64_t ld,
+                                     smarl_stream_t stream) {
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(cost && lambdas && penalty, "null pointer");
+  SMARL_REQUIRE(K >= 1 && K <= SMARL_MAX_AGENTS && T >= 1 && T <= 65535, "bad K=%d or T=%d", K, T);
+  SMARL_REQUIRE(aligned16(cost) && aligned16(penalty), "pointers must be 16-byte aligned");
+  const int64_t n_groups = (n_envs + 3) / 4;
+  dim3 grid((unsigned)((n_groups + kAccThreads - 1) / kAccThreads), (unsigned)T);
+  if (cost_dtype == SMARL_COST_U8)
+    penalty_kernel<uint8_t><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint8_t*>(cost), lambdas, penalty, K, n_groups, ld);
+  else if (cost_dtype == SMARL_COST_I32)
+    penalty_kernel<int32_t><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<const int32_t*>(cost), lambdas, penalty, K, n_groups, ld);
+  else
+    SMARL_REQUIRE(false, "bad cost_dtype %d", cost_dtype);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
+extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const void* cost,
+                                     int32_t cost_dtype, const float* penalty, float* R, float* modR,
+                                     int32_t* C, float* G, double* stats, double* stats_scratch,
+                                     int32_t n_agents, int32_t n_constraints, int64_t n_envs,
+                                     int64_t ld, smarl_stream_t stream) {
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(acc != nullptr, "accounting params is NULL");
+  SMARL_REQUIRE(acc->n_steps >= 1, "n_steps=%d must be >= 1", acc->n_steps);
+  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 2, "bad g_mode %d", acc->g_mode);
+  SMARL_REQUIRE(n_agents >= 1 && n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", n_agents);
+  SMARL_REQUIRE(n_constraints >= 1 && n_constraints <= SMARL_MAX_AGENTS, "n_constraints=%d outside 1..32",
+                n_constraints);
+  SMARL_REQUIRE(reward && cost && R && modR && C, "null required pointer");
+  SMARL_REQUIRE(acc->g_mode == 0 || G, "g_mode != 0 needs G");
+  SMARL_REQUIRE((stats == nullptr) == (stats_scratch == nullptr), "stats and stats_scratch go together");
+  SMARL_REQUIRE(aligned16(reward) && aligned16(cost) && aligned16(penalty) && aligned16(R) &&
+                    aligned16(modR) && aligned16(C) && aligned16(G), "pointers must be 16-byte aligned");
+  ReturnsArgs a;
+  a.reward = reward; a.cost = cost; a.penalty = penalty; a.R = R; a.modR = modR; a.C = C; a.G = G;
+  a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma;
+  a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
+  a.A = n_agents; a.K = n_constraints; a.T = acc->n_steps; a.g_mode = acc->g_mode;
+  const int64_t n_chunks = (a.n_groups + kAccThreads - 1) / kAccThreads;
+  const int64_t blocks = n_chunks * (n_agents + n_constraints);
+  SMARL_REQUIRE(blocks <= 0x7fffffffLL, "too many blocks");
+  if (cost_dtype == SMARL_COST_U8)
+    returns_kernel<uint8_t><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
+  else if (cost_dtype == SMARL_COST_I32)
+    returns_kernel<int32_t><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
+  else
+    SMARL_REQUIRE(false, "bad cost_dtype %d", cost_dtype);
+  SMARL_CUDA(cudaGetLastError());
+  if (stats)
+    return launch_stats_finalize(stats_scratch, n_chunks, n_agents, n_constraints, n_envs, stats,
+                                 (cudaStream_t)stream);
+  return SMARL_OK;
+}
+
+extern "C" int smarl_lambda_update(double* lambdas, const double* stats, const double* thresholds,
+                                   double lr, int32_t n_agents, int32_t n_constraints,
+                                   smarl_stream_t stream) {
+  SMARL_REQUIRE(lambdas && stats && thresholds, "null pointer");
+  SMARL_REQUIRE(n_constraints >= 1 && n_constraints <= SMARL_MAX_AGENTS, "n_constraints=%d outside 1..32",
+                n_constraints);
+  lambda_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(lambdas, stats, thresholds, lr, n_agents,
+                                                          n_constraints);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}

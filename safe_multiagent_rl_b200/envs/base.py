@@ -1,0 +1,128 @@
+"""Shared host logic of the batched envs: buffers in the agent-major SoA layout, action ingest,
+reference-oriented views, closed-loop rollout helper and the single-env list adaptor."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..layout import alloc, env_major, pad_ld, require_cuda
+from ..rollout import G_REWARD_TO_GO, RolloutBuffer
+
+
+class BatchedEnv:
+    """Base of the batched drop-ins.  Subclasses set ``n_constraints``, ``cost_dtype``,
+    ``action_rows``/``action_dtype`` and implement ``_reset_impl`` / ``_step_impl``."""
+
+    cost_dtype = torch.uint8
+    action_dtype = torch.uint8
+
+    def _init_common(self, size, n_agents, n_envs, device, env_offset):
+        if not (1 <= int(n_agents) <= 32):
+            raise ValueError("n_agents must be in 1..32")
+        self.size, self.n_agents, self.n_envs = int(size), int(n_agents), int(n_envs)
+        self.device = require_cuda(device)
+        self.ld = pad_ld(self.n_envs)
+        self.env_offset = int(env_offset)       # global id of env 0 when sharded over GPUs
+        self.lib = _lib.load()
+        self.t = 0
+
+    # ---- buffers --------------------------------------------------------------------------------
+    def _alloc(self, rows, dtype, lead=()):
+        return alloc(rows, self.n_envs, dtype, self.device, lead)
+
+    def _ingest_actions(self, actions, agent_major):
+        """Return an ``[action_rows, ld]`` device tensor in the kernel layout (zero-copy when the
+        caller already hands one over, e.g. ``env.action_buffer`` filled by the policies)."""
+        rows = self.action_rows
+        if isinstance(actions, torch.Tensor) and actions.device == self.device and \
+                actions.dtype == self.action_dtype and tuple(actions.shape) == (rows, self.ld) and \
+                actions.is_contiguous():
+            return actions
+        a = torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
+        a = a.to(self.device)
+        if not agent_major:                                   # reference orientation: [E, A(, 2)]
+            a = a.reshape(self.n_envs, rows).t()
+        else:
+            a = a.reshape(rows, -1)[:, : self.n_envs]
+        self.action_buffer[:, : self.n_envs].copy_(a)
+        return self.action_buffer
+
+    def _views(self, reward, cost, done):
+        E = self.n_envs
+        return (env_major(self.obs, E), env_major(reward, E), env_major(cost, E), env_major(done, E))
+
+    # ---- reference protocol ---------------------------------------------------------------------
+    def reset(self):
+        """``env.reset()`` for every env: returns the observation ``[n_envs, state_space]`` (a view;
+        row e is ``np.array(state).flatten()`` of env e, main.py:33)."""
+        self.t = 0
+        self._reset_impl()
+        return env_major(self.obs, self.n_envs)
+
+    def step(self, actions, lambdas=None, out=None, agent_major=False):
+        """``env.step(actions)`` for every env.
+
+        actions  ``[n_envs, n_agents(, 2)]`` (reference orientation) or, with ``agent_major=True``
+                 / the env's own ``action_buffer``, the kernel layout.
+        lambdas  optional f64 device tensor [K]: fuses MetaAgent.act's penalty <lambda, c> into the
+                 step (written to ``out.penalty[t]`` / ``self.penalty``).
+        out      optional (RolloutBuffer, t): write reward/cost/done/penalty into slab t.
+        Returns (obs [E, S], reward [E, A], cost [E, K], done [E, A]) -- views, valid until the
+        next step.
+        """
+        act = self._ingest_actions(actions, agent_major)
+        if out is not None:
+            buf, t = out
+            reward, cost, done, penalty = buf.reward[t], buf.cost[t], buf.done[t], buf.penalty[t]
+        else:
+            reward, cost, done, penalty = self.reward, self.cost, self.done, self.penalty
+        self._step_impl(act, reward, cost, done, lambdas, penalty if lambdas is not None else None)
+        self.t += 1
+        return self._views(reward, cost, done)
+
+    def new_rollout_buffer(self, n_steps, g_mode=G_REWARD_TO_GO):
+        return RolloutBuffer(n_steps, self.n_agents, self.n_constraints, self.n_envs, self.cost_dtype,
+                             self.device, g_mode)
+
+    def rollout_closed_loop(self, policy, n_steps, lambdas, gamma, thresholds=None, buffer=None,
+                            g_mode=G_REWARD_TO_GO):
+        """main.py:28-57 for all envs: ``policy(obs, t) -> actions`` is called between steps (it may
+        write ``env.action_buffer`` in place and return it).  Returns RolloutBuffer.finish()."""
+        buf = buffer if buffer is not None else self.new_rollout_buffer(n_steps, g_mode)
+        obs = self.reset()
+        for t in range(n_steps):
+            actions = policy(obs, t)
+            agent_major = isinstance(actions, torch.Tensor) and actions.data_ptr() == self.action_buffer.data_ptr()
+            obs, _, _, _ = self.step(actions, lambdas=lambdas, out=(buf, t), agent_major=agent_major)
+        out = buf.finish(gamma, thresholds, g_mode)
+        out["buffer"] = buf
+        return out
+
+
+class SingleEnvAdapter:
+    """Wrap a batched env with n_envs == 1 so the reference's unmodified driver loop
+    (main.py:28-57) can drive it: Python lists in, Python lists out."""
+
+    def __init__(self, env):
+        if env.n_envs != 1:
+            raise ValueError("SingleEnvAdapter needs n_envs == 1")
+        self.env = env
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self):
+        self.env.reset()
+        return self.env.state()[0].cpu().numpy().astype(np.float64).tolist()
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64).reshape(1, self.env.n_agents, -1)
+        if self.env.action_dtype == torch.uint8:
+            a = a.reshape(1, self.env.n_agents).astype(np.uint8)
+        else:
+            a = a.astype(np.float32)
+        obs, r, c, d = self.env.step(a)
+        state = self.env.state()[0].cpu().numpy().astype(np.float64).tolist()
+        return (state, r[0].cpu().numpy().astype(np.float64).tolist(),
+                c[0].cpu().numpy().astype(np.float64).tolist(), d[0].cpu().numpy().astype(bool).tolist())

@@ -1,0 +1,87 @@
+"""BatchedCollisionAvoidance -- n_envs instances of the reference's CollisionAvoidance env
+(envs/collision_avoidance.py:6-165) stepped by one CUDA launch.  State is float64 like the
+reference; actions are float32, which is what its policies emit (agent.py:124-125)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .base import BatchedEnv
+
+
+class BatchedCollisionAvoidance(BatchedEnv):
+    """Constructor mirrors ``CollisionAvoidance(size, n_agents, n_landmarks, shuffle, agents_size,
+    normalize_state)`` (collision_avoidance.py:49) plus ``n_envs`` / ``device``.
+
+    starts / landmarks  optional ``[n_envs, n_agents, 2]`` / ``[n_envs, n_landmarks, 2]`` float64.
+        Defaults follow the reference ctor per env: agents ``rand(2) * size`` in index order, then
+        ONE landmark (:60-62; n_landmarks only matters on shuffle, :100-101).
+    """
+
+    action_space = 2
+    cost_dtype = torch.int32
+    action_dtype = torch.float32
+
+    def __init__(self, size, n_agents, n_envs=1, n_landmarks=1, shuffle=False, agents_size=0.25,
+                 normalize_state=False, device="cuda", starts=None, landmarks=None, env_offset=0):
+        assert type(size) == int and type(n_agents) == int and type(n_landmarks) == int   # :51-53
+        assert type(agents_size) in (float, int)
+        self._init_common(size, n_agents, n_envs, device, env_offset)
+        if shuffle:
+            raise NotImplementedError("shuffle=True (re-randomised starts/landmarks per episode) is not built yet")
+        if normalize_state:
+            raise NotImplementedError("normalize_state=True is not built yet")
+        self.shuffle, self.normalize_state = False, False
+        self.agents_size = float(agents_size)
+        A, E, dev = self.n_agents, self.n_envs, self.device
+        self.n_landmarks = int(n_landmarks)
+        self.state_space = 2 * A
+        self.constraint_space = [1]
+        self.n_constraints = 1
+        self.action_rows = 2 * A
+        if starts is None or landmarks is None:
+            L0 = 1                                              # the ctor draws a single landmark (:62)
+            draws = np.random.rand(E, A + L0, 2) * self.size
+            if starts is None:
+                starts = draws[:, :A]
+            if landmarks is None:
+                landmarks = draws[:, A:]
+        starts = np.asarray(starts, dtype=np.float64)
+        landmarks = np.asarray(landmarks, dtype=np.float64)
+        assert starts.shape == (E, A, 2) and landmarks.shape[0] == E and landmarks.shape[2] == 2
+        self.L = landmarks.shape[1]
+        f64 = torch.float64
+        self.start_x, self.start_y = self._alloc(A, f64), self._alloc(A, f64)
+        self.start_x[:, :E] = torch.as_tensor(starts[:, :, 0].T.copy()).to(dev)
+        self.start_y[:, :E] = torch.as_tensor(starts[:, :, 1].T.copy()).to(dev)
+        self.landmarks = self._alloc(2 * self.L, f64)           # rows lx0, ly0, lx1, ...
+        self.landmarks[:, :E] = torch.as_tensor(landmarks.reshape(E, 2 * self.L).T.copy()).to(dev)
+        self.pos_x, self.pos_y = self.start_x.clone(), self.start_y.clone()
+        self.agent_done = self._alloc(A, torch.uint8)
+        self.action_buffer = self._alloc(2 * A, torch.float32)  # rows dx0, dy0, dx1, ...
+        self.obs = self._alloc(2 * A, torch.float32)
+        self.reward = self._alloc(A, torch.float32)
+        self.cost = self._alloc(1, torch.int32)
+        self.done = self._alloc(A, torch.uint8)
+        self.penalty = self._alloc(1, torch.float32)[0]
+        self._params = _lib.CollisionParams(self.size, A, self.L, 0, self.agents_size)
+
+    def state(self):
+        """[n_envs, n_agents, 2] float64 positions (a copy)."""
+        E = self.n_envs
+        return torch.stack([self.pos_x[:, :E].t(), self.pos_y[:, :E].t()], dim=-1)
+
+    def _reset_impl(self):
+        _lib.check(self.lib.smarl_collision_reset(
+            C.byref(self._params), _lib.ptr(self.start_x), _lib.ptr(self.start_y), _lib.ptr(self.landmarks),
+            _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done), _lib.ptr(self.obs),
+            self.n_envs, self.ld, _lib.stream_ptr()))
+
+    def _step_impl(self, act, reward, cost, done, lambdas, penalty):
+        _lib.check(self.lib.smarl_collision_step(
+            C.byref(self._params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done),
+            _lib.ptr(act), _lib.ptr(self.landmarks), _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost),
+            _lib.ptr(done), _lib.ptr(lambdas), _lib.ptr(penalty), self.n_envs, self.ld, _lib.stream_ptr()))

@@ -1,0 +1,143 @@
+"""BatchedCoverageDiscrete -- n_envs instances of the reference's CoverageDiscrete ("Explore",
+envs/coverage.py:166-196 on top of CoverageContinuous :8-106) stepped by one CUDA launch."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..layout import env_major
+from ..rollout import G_NONE, G_REWARD_TO_GO, Stats, make_accounting
+from .base import BatchedEnv
+
+
+def penalty_table(size, n_agents, fieldview_size=None):
+    """(fv, table) with table[q] = (fv - sqrt(q))**2 for integer squared distances q whose
+    distance is inside the field of view, truncated after the last non-zero entry.
+
+    Same numpy *scalar* expression as the reference (coverage.py:15-18, :82-83) so the f64 values
+    are the reference's; the kernel reads their f32 rounding.
+    """
+    fv = size / (np.sqrt(n_agents)) if fieldview_size is None else fieldview_size
+    vals = []
+    for q in range(2 * size * size + 1):
+        d = np.sqrt(np.float64(q))
+        if fv - d > 0:
+            vals.append(float((fv - d) ** 2))
+        else:
+            break                      # sqrt is monotone: every later q is outside the field of view
+    return fv, np.asarray(vals, dtype=np.float64)
+
+
+class BatchedCoverageDiscrete(BatchedEnv):
+    """Constructor mirrors ``CoverageDiscrete(size, n_agents, shuffle, agents_size, fieldview_size,
+    weights)`` (coverage.py:167) plus ``n_envs`` / ``device``.
+
+    starts  optional ``[n_envs, n_agents, 2]`` integer array.  By default they are drawn from the
+            global ``np.random`` stream exactly as constructing n_envs reference envs one after
+            another would (each ctor first builds and discards n_agents continuous agents,
+            coverage.py:19,:170, then floors ``rand(2) * size``, :267-269).
+    """
+
+    action_space = 5
+    cost_dtype = torch.uint8
+    action_dtype = torch.uint8
+
+    def __init__(self, size, n_agents, n_envs=1, shuffle=False, agents_size=0.5, fieldview_size=None,
+                 weights=None, device="cuda", starts=None, env_offset=0):
+        self._init_common(size, n_agents, n_envs, device, env_offset)
+        if not (1 <= self.size <= 254):
+            raise ValueError("size must be in 1..254 (uint8 coordinates)")
+        if shuffle:
+            raise NotImplementedError("shuffle=True (per-episode re-randomised starts) is not built yet")
+        self.shuffle = False
+        self.agents_size = agents_size
+        A, E = self.n_agents, self.n_envs
+        self.state_space = 2 * A
+        self.constraint_space = [1 for _ in range(A)]
+        self.n_constraints = A
+        self.action_rows = A
+        self.fieldview_size, table = penalty_table(self.size, A, fieldview_size)
+        if A == 1:
+            table = table[:0]
+        if len(table) > 12287:
+            raise NotImplementedError("fieldview_size > 110 needs a penalty table larger than shared memory")
+        self.weights = None if weights is None else list(weights)
+        if self.weights is not None and len(self.weights) < A:
+            # the reference zips rewards with weights and silently returns fewer rewards than agents
+            # (coverage.py:86-87); that breaks its own driver, so it is rejected here
+            raise ValueError("need at least n_agents weights")
+        dev = self.device
+        self._lut = torch.as_tensor(table, dtype=torch.float32).to(dev) if len(table) else None
+        self._weights = None if self.weights is None else \
+            torch.as_tensor(np.asarray(self.weights[:A], dtype=np.float64), dtype=torch.float32).to(dev)
+        self._params = _lib.CoverageParams(self.size, A, len(table), 0, _lib.ptr(self._lut),
+                                           _lib.ptr(self._weights))
+        if starts is None:
+            draws = np.random.rand(E, 2 * A, 2)
+            starts = np.floor(draws[:, A:, :] * self.size)
+        starts = np.asarray(starts)
+        assert starts.shape == (E, A, 2)
+        if starts.min() < 0 or starts.max() > self.size:
+            raise ValueError("start coordinates must lie in [0, size]")
+        self.start_x, self.start_y = self._alloc(A, torch.uint8), self._alloc(A, torch.uint8)
+        self.start_x[:, :E] = torch.as_tensor(starts[:, :, 0].T.astype(np.uint8)).to(dev)
+        self.start_y[:, :E] = torch.as_tensor(starts[:, :, 1].T.astype(np.uint8)).to(dev)
+        self.pos_x, self.pos_y = self.start_x.clone(), self.start_y.clone()
+        self.action_buffer = self._alloc(A, torch.uint8)
+        self.obs = self._alloc(2 * A, torch.float32)
+        self.reward = self._alloc(A, torch.float32)
+        self.cost = self._alloc(A, torch.uint8)
+        self.done = self._alloc(A, torch.uint8)
+        self.penalty = self._alloc(1, torch.float32)[0]
+
+    def state(self):
+        """[n_envs, n_agents, 2] integer positions (a copy)."""
+        E = self.n_envs
+        return torch.stack([self.pos_x[:, :E].t(), self.pos_y[:, :E].t()], dim=-1)
+
+    def _reset_impl(self):
+        _lib.check(self.lib.smarl_grid_reset(_lib.ptr(self.start_x), _lib.ptr(self.start_y),
+                                             _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.obs),
+                                             self.n_agents, self.n_envs, self.ld, _lib.stream_ptr()))
+
+    def _step_impl(self, act, reward, cost, done, lambdas, penalty):
+        _lib.check(self.lib.smarl_coverage_step(
+            C.byref(self._params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(act),
+            _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
+            _lib.ptr(penalty), self.n_envs, self.ld, _lib.stream_ptr()))
+
+    def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None):
+        """Open-loop fused episode (one launch): reset + T steps + accounting, state in registers.
+
+        actions ``[T, n_agents, ld]`` uint8 device tensor (kernel layout).  Returns dict with
+        R/modR [E,A], C [E,A] i32, G [T,E,A] or None, final positions, stats.
+        """
+        T = int(actions.shape[0])
+        A, E, dev = self.n_agents, self.n_envs, self.device
+        assert actions.dtype == torch.uint8 and tuple(actions.shape) == (T, A, self.ld) and actions.is_contiguous()
+        o = out if out is not None else {}
+        def buf(name, rows, dtype, lead=()):
+            if name not in o:
+                o[name] = self._alloc(rows, dtype, lead)
+            return o[name]
+        R, modR = buf("R_", A, torch.float32), buf("modR_", A, torch.float32)
+        Csum = buf("C_", A, torch.int32)
+        G = buf("G_", A, torch.float32, (T,)) if g_mode != G_NONE else None
+        gs = buf("g_scratch", 1, torch.float32, (2 * T,)) if g_mode == G_REWARD_TO_GO else None
+        if "stats_vec" not in o:
+            o["stats_vec"] = torch.zeros(self.lib.smarl_stats_len(A, A), dtype=torch.float64, device=dev)
+            o["stats_scratch"] = torch.zeros(self.lib.smarl_stats_scratch_len(A, A, E), dtype=torch.float64,
+                                             device=dev)
+        thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
+        acc = make_accounting(gamma, T, g_mode, thr)
+        _lib.check(self.lib.smarl_coverage_rollout(
+            C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),
+            _lib.ptr(actions), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(R),
+            _lib.ptr(modR), _lib.ptr(Csum), _lib.ptr(G), _lib.ptr(gs), _lib.ptr(o["stats_vec"]),
+            _lib.ptr(o["stats_scratch"]), E, self.ld, _lib.stream_ptr()))
+        o.update(R=env_major(R, E), modR=env_major(modR, E), C=env_major(Csum, E),
+                 G=None if G is None else env_major(G, E), stats=Stats(o["stats_vec"], A, A))
+        return o

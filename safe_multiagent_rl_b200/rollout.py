@@ -1,0 +1,166 @@
+"""Device rollout buffer and per-episode accounting.
+
+Host-side mirror of safe_multi_agent_RL/buffer.py:7-48 (Buffer.append/step/mean_score) and of
+the learners' compute_returns (agent.py:129-132, :200-206) for n_envs episodes at a time.
+The *_step kernels write step t's reward / cost / done / penalty straight into slab t of this
+buffer (a zero-copy ``Buffer.append``); ``finish`` runs one accounting kernel over it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .layout import alloc, env_major, pad_ld
+
+G_NONE, G_REWARD_TO_GO, G_DISCOUNTED_TERMS = 0, 1, 2
+
+
+class Stats:
+    """Decoded statistics vector (include/smarl.h smarl_stats_len layout)."""
+
+    def __init__(self, vec: torch.Tensor, n_agents: int, n_constraints: int):
+        self.vec, self.A, self.K = vec, n_agents, n_constraints
+
+    @property
+    def cost_sum(self):
+        return self.vec[: self.K]
+
+    @property
+    def violations(self):
+        return self.vec[self.K: 2 * self.K]
+
+    @property
+    def return_sum(self):
+        return self.vec[2 * self.K: 2 * self.K + self.A]
+
+    @property
+    def modified_return_sum(self):
+        return self.vec[2 * self.K + self.A: 2 * self.K + 2 * self.A]
+
+    @property
+    def count(self):
+        return self.vec[2 * self.K + 2 * self.A]
+
+
+def make_accounting(gamma, n_steps, g_mode, thresholds_dev):
+    return _lib.Accounting(float(gamma), int(n_steps), int(g_mode), _lib.ptr(thresholds_dev))
+
+
+class RolloutBuffer:
+    """[T, rows, ld] device slabs for one batch of n_envs episodes."""
+
+    def __init__(self, n_steps, n_agents, n_constraints, n_envs, cost_dtype=torch.uint8, device="cuda",
+                 g_mode=G_REWARD_TO_GO):
+        self.T, self.A, self.K, self.E = int(n_steps), int(n_agents), int(n_constraints), int(n_envs)
+        self.ld = pad_ld(n_envs)
+        self.device = torch.device(device)
+        self.g_mode = g_mode
+        assert cost_dtype in (torch.uint8, torch.int32)
+        self.cost_dtype = cost_dtype
+        self.cost_code = _lib.COST_U8 if cost_dtype == torch.uint8 else _lib.COST_I32
+        T, A, K, E = self.T, self.A, self.K, self.E
+        self.reward = alloc(A, E, torch.float32, device, (T,))
+        self.cost = alloc(K, E, cost_dtype, device, (T,))
+        self.done = alloc(A, E, torch.uint8, device, (T,))
+        self.penalty = alloc(1, E, torch.float32, device, (T,))[:, 0]
+        self.R = alloc(A, E, torch.float32, device)
+        self.modR = alloc(A, E, torch.float32, device)
+        self.Csum = alloc(K, E, torch.int32, device)
+        self.G = alloc(A, E, torch.float32, device, (T,)) if g_mode != G_NONE else None
+        lib = _lib.load()
+        self.stats_vec = torch.zeros(lib.smarl_stats_len(A, K), dtype=torch.float64, device=device)
+        self.stats_scratch = torch.zeros(max(1, lib.smarl_stats_scratch_len(A, K, E)), dtype=torch.float64,
+                                         device=device)
+
+    # ---- views in the reference's orientation ([.., env, agent]) ------------------------------
+    def rewards(self):
+        return env_major(self.reward, self.E)                # [T, E, A]
+
+    def modified_rewards(self):
+        return self.rewards() - self.penalty[:, : self.E, None]
+
+    def costs(self):
+        return env_major(self.cost, self.E)                  # [T, E, K]
+
+    def finish(self, gamma, thresholds=None, g_mode=None):
+        """Buffer.step for all envs: returns dict(R [E,A], modR [E,A], C [E,K], G [T,E,A] | None, stats)."""
+        lib = _lib.load()
+        g_mode = self.g_mode if g_mode is None else g_mode
+        if g_mode != G_NONE and self.G is None:
+            raise ValueError("buffer was created without G storage")
+        thr = None
+        if thresholds is not None:
+            thr = torch.as_tensor(thresholds, dtype=torch.float64, device=self.device).contiguous()
+        acc = make_accounting(gamma, self.T, g_mode, thr)
+        _lib.check(lib.smarl_rollout_returns(
+            C.byref(acc), _lib.ptr(self.reward), _lib.ptr(self.cost), self.cost_code, _lib.ptr(self.penalty),
+            _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum), _lib.ptr(self.G if g_mode else None),
+            _lib.ptr(self.stats_vec), _lib.ptr(self.stats_scratch), self.A, self.K, self.E, self.ld,
+            _lib.stream_ptr()))
+        return dict(R=env_major(self.R, self.E), modR=env_major(self.modR, self.E),
+                    C=env_major(self.Csum, self.E),
+                    G=env_major(self.G, self.E) if g_mode else None,
+                    stats=Stats(self.stats_vec, self.A, self.K))
+
+
+class BatchedBuffer:
+    """Reference ``Buffer`` protocol (buffer.py:7-48) fed with whole batches of episodes.
+
+    ``scores``, ``modified_scores``, ``constraints`` are ``[episodes][A|K]`` like the reference's
+    lists (materialised lazily from the device tensors); ``lambdas`` is ``[meta cycles][K]``.
+    """
+
+    def __init__(self, params=None, constrained=True, save_path=None):
+        self.params, self.constrained, self.save_path = params, constrained, save_path
+        self.lambdas = []
+        self._R, self._modR, self._C = [], [], []
+        self._steps = []          # per-step appends (compat path)
+
+    # -- compat path: per-step tensors [E, A] / [E, K], exactly the reference's call sequence ----
+    def append(self, reward, modified_reward, constraint):
+        self._steps.append((reward, modified_reward, constraint))
+
+    def step(self):
+        gamma = self.params.gamma
+        r = torch.stack([s[0] for s in self._steps]).double()
+        m = torch.stack([s[1] for s in self._steps]).double()
+        c = torch.stack([s[2] for s in self._steps]).double()
+        disc = torch.tensor([gamma ** i for i in range(r.shape[0])], dtype=torch.float64, device=r.device)
+        self._R.append((disc[:, None, None] * r).sum(0))
+        self._modR.append((disc[:, None, None] * m).sum(0))
+        self._C.append(c.sum(0))
+        self._steps = []
+
+    # -- fast path: the products of RolloutBuffer.finish / env.rollout -----------------------------
+    def extend(self, R, modR, C):
+        self._R.append(R.double())
+        self._modR.append(modR.double())
+        self._C.append(C.double())
+
+    def append_lambdas(self, lambdas):
+        self.lambdas.append(np.asarray(torch.as_tensor(lambdas).detach().cpu(), dtype=np.float64).copy())
+
+    @staticmethod
+    def _cat(chunks):
+        return torch.cat(chunks, dim=0).cpu().numpy() if chunks else np.zeros((0, 0))
+
+    @property
+    def scores(self):
+        return self._cat(self._R)
+
+    @property
+    def modified_scores(self):
+        return self._cat(self._modR)
+
+    @property
+    def constraints(self):
+        return self._cat(self._C)
+
+    def mean_score(self, n=100):
+        """buffer.py:45-48: means over the last n episodes; costs relative to the thresholds."""
+        thr = np.asarray(self.params.thresholds, dtype=np.float64)
+        return (self.scores[-n:].mean(axis=0), self.modified_scores[-n:].mean(axis=0),
+                list(self.constraints[-n:].mean(axis=0) - thr))

@@ -1,0 +1,299 @@
+"""GPU parity: the CUDA path (through the C ABI) against the numpy oracle on the same seeded
+inputs.  Bars: integer dynamics (positions, costs, done, congestions via rewards) bit-exact;
+Collision float64 positions bit-exact; float32 rewards / returns within 1e-5 relative
+(BASELINE.json north_star), written here as rtol=1e-5 with an absolute floor of 1e-5 x the
+magnitude scale of the summed terms."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_oracle as no
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def smarl():
+    import safe_multiagent_rl_b200 as s
+    return s
+
+
+def close(got, want, scale=None, rtol=RTOL):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    atol = rtol * (np.max(np.abs(want)) if scale is None else scale) + 1e-30
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+# ----------------------------------------------------------------------------- Coverage
+COVERAGE_CASES = [
+    # size, A, E, T, fieldview, seed
+    (5, 3, 50, 50, None, 0),          # BASELINE config 1
+    (32, 16, 1000, 12, None, 1),      # config 4 shape (fv = 8.0)
+    (8, 5, 333, 20, None, 2),         # ragged E (not a multiple of 4 / 16)
+    (64, 32, 130, 4, None, 3),        # maximum agents
+    (3, 2, 17, 30, 10.0, 4),          # field of view larger than the grid: every pair overlaps
+    (5, 1, 40, 5, None, 5),           # single agent: no pairs
+    (254, 4, 64, 6, 40.0, 6),         # maximum grid size
+]
+
+
+def coverage_setup(size, A, E, T, fv, seed):
+    rng = np.random.default_rng(seed)
+    starts = np.floor(rng.random((E, A, 2)) * size).astype(np.int64)
+    starts[0] = size - 1 if size > 1 else 0
+    starts[-1] = 0
+    actions = rng.integers(0, 5, size=(T, E, A))
+    weights = (1.0 + (np.arange(A) % 3)).tolist()
+    fvv = no.coverage_fieldview(size, A, fv)
+    lut = no.coverage_penalty_lut(size, fvv)
+    return starts, actions, weights, lut
+
+
+@pytest.mark.parametrize("size,A,E,T,fv,seed", COVERAGE_CASES)
+def test_coverage_step_matches_oracle(size, A, E, T, fv, seed):
+    s = smarl()
+    starts, actions, weights, lut = coverage_setup(size, A, E, T, fv, seed)
+    env = s.BatchedCoverageDiscrete(size, A, n_envs=E, weights=weights, fieldview_size=fv, starts=starts)
+    lam = torch.as_tensor(np.linspace(0.1, 0.5, A), dtype=torch.float64, device="cuda")
+    obs = env.reset()
+    assert np.array_equal(obs.cpu().numpy().reshape(E, A, 2), starts.astype(np.float32))
+    pos = starts.copy()
+    for t in range(T):
+        obs, r, c, d = env.step(actions[t].astype(np.uint8), lambdas=lam)
+        pos, r_o, c_o, d_o = no.coverage_discrete_step(pos, actions[t], size, lut, weights)
+        assert np.array_equal(env.state().cpu().numpy(), pos)                       # bit-exact
+        assert np.array_equal(obs.cpu().numpy().reshape(E, A, 2), pos.astype(np.float32))
+        assert np.array_equal(c.cpu().numpy(), c_o)
+        assert np.array_equal(d.cpu().numpy().astype(bool), d_o)
+        close(r.cpu().numpy(), r_o)
+        close(env.penalty[:E].cpu().numpy(), c_o @ lam.cpu().numpy())
+
+
+@pytest.mark.parametrize("size,A,E,T,fv,seed", COVERAGE_CASES)
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+def test_coverage_rollouts_match_oracle(size, A, E, T, fv, seed, g_mode):
+    """Closed-loop (T step launches into a RolloutBuffer + returns kernel) and fused open-loop
+    rollouts against the oracle's accounting, and against each other."""
+    s = smarl()
+    starts, actions, weights, lut = coverage_setup(size, A, E, T, fv, seed)
+    gamma = 0.999
+    lam_np = np.linspace(0.1, 0.5, A)
+    thr = np.full(A, 0.4 * T)
+    lam = torch.as_tensor(lam_np, dtype=torch.float64, device="cuda")
+    env = s.BatchedCoverageDiscrete(size, A, n_envs=E, weights=weights, fieldview_size=fv, starts=starts)
+
+    pos = starts.copy()
+    def step_fn(t):
+        nonlocal pos
+        pos, r, c, _ = no.coverage_discrete_step(pos, actions[t], size, lut, weights)
+        return r, c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    want_G = {0: None, 1: want["G"], 2: no.discounted_terms(want["mod_reward"], gamma)}[g_mode]
+    scale_R = np.max(np.abs(want["modR"])) + 1e-12
+
+    # closed loop
+    act_dev = torch.as_tensor(actions.astype(np.uint8), device="cuda")
+    out = env.rollout_closed_loop(lambda obs, t: act_dev[t], T, lam, gamma, thresholds=thr, g_mode=g_mode)
+    assert np.array_equal(env.state().cpu().numpy(), pos)
+    assert np.array_equal(out["C"].cpu().numpy(), want["C"])
+    close(out["R"].cpu().numpy(), want["R"], scale_R)
+    close(out["modR"].cpu().numpy(), want["modR"], scale_R)
+    close(out["buffer"].modified_rewards().cpu().numpy(), want["mod_reward"])
+    if g_mode:
+        close(out["G"].cpu().numpy(), want_G, scale_R)
+    st = out["stats"]
+    assert np.array_equal(st.cost_sum.cpu().numpy(), want["C"].sum(0))               # exact integers
+    assert np.array_equal(st.violations.cpu().numpy(), (want["C"] > thr[None]).sum(0))
+    close(st.return_sum.cpu().numpy(), want["R"].sum(0), scale_R * E)
+    close(st.modified_return_sum.cpu().numpy(), want["modR"].sum(0), scale_R * E)
+    assert float(st.count) == E
+    closed = {k: out[k].cpu().numpy().copy() for k in ("R", "modR", "C")}
+
+    # fused open loop
+    act_k = torch.zeros(T, A, env.ld, dtype=torch.uint8, device="cuda")
+    act_k[:, :, :E] = act_dev.permute(0, 2, 1)
+    fo = env.rollout(act_k, lambdas=lam, gamma=gamma, thresholds=thr, g_mode=g_mode)
+    assert np.array_equal(env.state().cpu().numpy(), pos)
+    assert np.array_equal(fo["C"].cpu().numpy(), want["C"])
+    close(fo["R"].cpu().numpy(), want["R"], scale_R)
+    close(fo["modR"].cpu().numpy(), want["modR"], scale_R)
+    if g_mode:
+        close(fo["G"].cpu().numpy(), want_G, scale_R)
+    st = fo["stats"]
+    assert np.array_equal(st.cost_sum.cpu().numpy(), want["C"].sum(0))
+    assert np.array_equal(st.violations.cpu().numpy(), (want["C"] > thr[None]).sum(0))
+    close(st.return_sum.cpu().numpy(), want["R"].sum(0), scale_R * E)
+    close(st.modified_return_sum.cpu().numpy(), want["modR"].sum(0), scale_R * E)
+    assert float(st.count) == E
+    close(fo["R"].cpu().numpy(), closed["R"], scale_R, rtol=2e-6)                    # two modes agree
+    assert np.array_equal(fo["C"].cpu().numpy(), closed["C"])
+
+
+# ----------------------------------------------------------------------------- Congestion
+CONGESTION_CASES = [
+    # size, A, E, T, noise, seed
+    (3, 3, 64, 10, 0.0, 0),           # paper config, no noise
+    (3, 8, 200, 30, 0.1, 1),
+    (10, 8, 515, 25, 0.1, 2),         # config 3 shape, ragged E
+    (2, 6, 33, 40, 0.5, 3),           # tiny grid: heavy edge sharing
+    (5, 32, 40, 6, 0.3, 4),           # maximum agents
+    (1, 5, 21, 20, 1.0, 5),           # all moves replaced by noise
+]
+
+
+def congestion_setup(size, A, E, T, seed):
+    rng = np.random.default_rng(seed)
+    demand = rng.random((size + 1, size + 1)) * 8 + 2
+    if size == 3:
+        demand = np.array([[2, 2, 4, 4], [3, 6, 10, 5], [3, 8, 3, 4], [4, 6, 7, 8]], dtype=np.float64)
+    starts = np.floor(rng.random((E, A, 2)) * size).astype(np.int64)
+    starts[:, 0] = 0
+    actions = rng.integers(0, 5, size=(T, E, A))
+    return demand, starts, actions
+
+
+@pytest.mark.parametrize("size,A,E,T,noise,seed", CONGESTION_CASES)
+@pytest.mark.parametrize("mode", ["philox", "recorded"])
+def test_congestion_step_matches_oracle(size, A, E, T, noise, seed, mode):
+    s = smarl()
+    demand, starts, actions = congestion_setup(size, A, E, T, seed)
+    offset = 1000 * seed + 7
+    env = s.BatchedCongestion(size, A, n_envs=E, noise=noise, starts=starts, demand_rate=demand,
+                              seed=12345 + seed, env_offset=offset)
+    lam = torch.as_tensor([0.7], dtype=torch.float64, device="cuda")
+    env.reset()
+    pos = starts.copy()
+    ids = np.arange(offset, offset + E)
+    for t in range(T):
+        u1, u2 = philox.congestion_uniforms(12345 + seed, ids, t, A)
+        moves = no.congestion_noise_moves(actions[t], u1, u2, noise)
+        if mode == "recorded":
+            obs, r, c, d = env.step(actions[t].astype(np.uint8), lambdas=lam, moves=moves.astype(np.uint8))
+        else:
+            obs, r, c, d = env.step(actions[t].astype(np.uint8), lambdas=lam)
+            assert np.array_equal(env.moves[:, :E].t().cpu().numpy(), moves)        # the Philox stream itself
+        pos, r_o, c_o, d_o, con = no.congestion_step(pos, actions[t], moves, size, demand)
+        assert np.array_equal(env.state().cpu().numpy(), pos)
+        assert np.array_equal(obs.cpu().numpy().reshape(E, A, 2), pos.astype(np.float32))
+        assert np.array_equal(c.cpu().numpy(), c_o)
+        assert not d.any()
+        # rewards are computed in f64 in the reference's operation order and rounded once to f32
+        assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))
+        close(env.penalty[:E].cpu().numpy(), 0.7 * c_o[:, 0])
+
+
+def test_congestion_closed_loop_returns():
+    s = smarl()
+    size, A, E, T, noise, seed = 10, 8, 300, 100, 0.1, 9
+    demand, starts, actions = congestion_setup(size, A, E, T, seed)
+    gamma, lam_np, thr = 0.9, np.array([0.35]), np.array([1.5])
+    env = s.BatchedCongestion(size, A, n_envs=E, noise=noise, starts=starts, demand_rate=demand, seed=3)
+    pos = starts.copy()
+    def step_fn(t):
+        nonlocal pos
+        u1, u2 = philox.congestion_uniforms(3, np.arange(E), t, A)
+        moves = no.congestion_noise_moves(actions[t], u1, u2, noise)
+        pos, r, c, _, _ = no.congestion_step(pos, actions[t], moves, size, demand)
+        return r, c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    act_dev = torch.as_tensor(actions.astype(np.uint8), device="cuda")
+    lam = torch.as_tensor(lam_np, device="cuda")
+    out = env.rollout_closed_loop(lambda obs, t: act_dev[t], T, lam, gamma, thresholds=thr)
+    scale = np.max(np.abs(want["modR"]))
+    assert np.array_equal(out["C"].cpu().numpy(), want["C"])
+    close(out["R"].cpu().numpy(), want["R"], scale)
+    close(out["modR"].cpu().numpy(), want["modR"], scale)
+    close(out["G"].cpu().numpy(), want["G"], scale)
+    assert np.array_equal(out["stats"].cost_sum.cpu().numpy(), want["C"].sum(0))
+
+
+# ----------------------------------------------------------------------------- Collision
+COLLISION_CASES = [
+    # size, A, L, E, T, seed
+    (5, 3, 1, 1000, 50, 0),           # config 2 shape
+    (2, 5, 1, 257, 20, 1),            # paper config
+    (5, 8, 3, 100, 30, 2),
+    (3, 12, 2, 64, 25, 3),
+    (4, 32, 1, 48, 6, 4),             # maximum agents
+]
+
+
+def collision_setup(size, A, L, E, T, seed):
+    rng = np.random.default_rng(seed)
+    starts = rng.random((E, A, 2)) * size
+    landmarks = rng.random((E, L, 2)) * size
+    actions = rng.normal(0, 0.5, size=(T, E, A, 2)).astype(np.float32)
+    q = E // 4
+    # a quarter of the envs: every agent walks straight to landmark 0 (agents finish, episodes end early)
+    actions[:, :q] = ((landmarks[:q, :1] - starts[:q]) / 6).astype(np.float32)[None]
+    # another quarter: agents crowded around the landmark (collisions)
+    starts[q:2 * q] = np.clip(landmarks[q:2 * q, :1] + rng.normal(0, 0.4, size=(q, A, 2)), 0, size)
+    return starts, landmarks, actions
+
+
+@pytest.mark.parametrize("size,A,L,E,T,seed", COLLISION_CASES)
+def test_collision_step_matches_oracle(size, A, L, E, T, seed):
+    s = smarl()
+    starts, landmarks, actions = collision_setup(size, A, L, E, T, seed)
+    env = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=L, starts=starts, landmarks=landmarks)
+    lam = torch.as_tensor([0.5], dtype=torch.float64, device="cuda")
+    env.reset()
+    pos, done = starts.copy(), np.zeros((E, A), dtype=bool)
+    n_done_envs = 0
+    n_coll = 0
+    for t in range(T):
+        obs, r, c, d = env.step(actions[t], lambdas=lam)
+        pos, r_o, c_o, done, active = no.collision_step(pos, done, actions[t].astype(np.float64), landmarks, size)
+        assert np.array_equal(env.state().cpu().numpy(), pos), t                      # bit-exact float64
+        assert np.array_equal(d.cpu().numpy().astype(bool), done)
+        assert np.array_equal(c.cpu().numpy(), c_o.astype(np.int64))
+        assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))                # f64-exact, rounded once
+        close(env.penalty[:E].cpu().numpy(), 0.5 * c_o[:, 0])
+        n_coll += int(c_o.sum())
+        n_done_envs = int((~active).sum())
+    assert n_coll > 0, "test inputs should provoke collisions"
+    if A <= 12:
+        assert n_done_envs > 0, "test inputs should end some episodes early"
+
+
+def test_collision_closed_loop_returns():
+    s = smarl()
+    size, A, L, E, T, seed = 5, 3, 1, 600, 50, 11
+    starts, landmarks, actions = collision_setup(size, A, L, E, T, seed)
+    gamma, lam_np, thr = 0.99, np.array([0.5]), np.array([1.0])
+    env = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=L, starts=starts, landmarks=landmarks)
+    pos, done = starts.copy(), np.zeros((E, A), dtype=bool)
+    def step_fn(t):
+        nonlocal pos, done
+        pos, r, c, done, _ = no.collision_step(pos, done, actions[t].astype(np.float64), landmarks, size)
+        return r, c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    act_dev = torch.as_tensor(actions, device="cuda")
+    lam = torch.as_tensor(lam_np, device="cuda")
+    out = env.rollout_closed_loop(lambda obs, t: act_dev[t], T, lam, gamma, thresholds=thr)
+    scale = np.max(np.abs(want["modR"]))
+    assert np.array_equal(out["C"].cpu().numpy(), want["C"].astype(np.int64))
+    close(out["R"].cpu().numpy(), want["R"], scale)
+    close(out["modR"].cpu().numpy(), want["modR"], scale)
+    close(out["G"].cpu().numpy(), want["G"], scale)
+
+
+# ----------------------------------------------------------------------------- lambda update
+def test_lambda_update_and_meta_agent():
+    s = smarl()
+    A = K = 3
+    meta = s.BatchedMetaAgent([1] * K, 0.999, 0.05, [25, 25, 25], start_learning_cycle=0, lambda_0=0.2,
+                              n_agents=A)
+    lib_len = 2 * K + 2 * A + 1
+    vec = torch.zeros(lib_len, dtype=torch.float64, device="cuda")
+    vec[:K] = torch.tensor([3000.0, 2000.0, 100.0])
+    vec[-1] = 100.0
+    meta.step(vec)
+    meta.step(vec)
+    meta.update()
+    want = no.lambda_update([0.2] * 3, np.array([30.0, 20.0, 1.0]), [25, 25, 25], 0.05)
+    np.testing.assert_allclose(meta.lambdas.cpu().numpy(), want, rtol=1e-15)
+    assert meta.learning_cycle == 0
