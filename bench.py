@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-steps/sec (env step + cost + returns) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one batch of episodes of the named workload (default: BASELINE.json configs[3],
+CoverageDiscrete 32x32 / 16 agents / T=50 with 2^22 envs PER GPU, weak scaling):
+
+  value   closed-loop mode, inputs resident in HBM: reset + T x smarl_coverage_step (each writes
+          obs / reward / cost / done / penalty, the true drop-in for env.step with a policy in the
+          loop) + smarl_rollout_returns (R, modR, C, reward-to-go G, stats) + stats all-reduce over
+          ranks + smarl_lambda_update.  Timed with CUDA events, max over ranks.
+  e2e     the same workload through the host-buffer C-ABI call smarl_host_coverage_rollout:
+          pinned HOST actions/starts in, HOST R/modR/C/stats out, copies inside the timed region.
+  roofline  dominant kernel (coverage_step_kernel): algorithmic bytes per launch (19 B per
+          agent-step x A x E) / its CUDA-event launch duration, against MEASURED_PEAKS.json.
+  fused   extra: the open-loop fused rollout kernel (state in registers for all T steps).
+  cpu_baseline  oracle/scalar_port.py (reference-structure Python loop) on all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-steps/sec (env step+cost+returns)"
+UNIT = "agent-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n_envs", type=int, default=1 << 22, help="envs per GPU")
+    ap.add_argument("--size", type=int, default=32)
+    ap.add_argument("--n_agents", type=int, default=16)
+    ap.add_argument("--max_t", type=int, default=50)
+    ap.add_argument("--gamma", type=float, default=0.999)
+    ap.add_argument("--cpu_seconds", type=float, default=12.0, help="CPU-baseline sample length")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--no_fused", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"CoverageDiscrete size={a.size} n_agents={a.n_agents} max_t={a.max_t} "
+            f"n_envs={a.n_envs}/GPU weights=1+(a%3) thresholds=25 gamma={a.gamma} (BASELINE configs[3] shape)")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's execution model (one env per process, Python loop) on all host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_rate(a, seconds):
+    from oracle import scalar_port as sp
+    procs = os.cpu_count() or 1
+    rate, used = sp.time_all_cores("coverage", a.size, a.n_agents, a.max_t, a.gamma, seconds, procs)
+    return rate, used
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(a.warmup):
+        cpu_rate(a, 1.0)
+    per_step = max(1.0, min(a.cpu_seconds, 120.0 / max(1, a.steps)))
+    rates, cores = [], 1
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r, cores = cpu_rate(a, per_step)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    v = statistics.mean(rates)
+    sample = (f"{a.steps} x {per_step:.1f}s of whole episodes (env.step + MetaAgent.act + Buffer.append/step + "
+              f"reward-to-go) on {cores} processes, one env each, recorded random actions")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU arm ignores n_envs: it steps one env per core"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, p in zip(names, parts[2:6]):
+                if p.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, a):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu --set full summary, if it was
+    captured on this workload shape."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        d = json.load(open(path)).get(kernel)
+        if d and d["n_envs"] == a.n_envs and d["n_agents"] == a.n_agents and d["size"] == a.size:
+            return d["dram_bytes_per_launch"]
+    except (ValueError, KeyError):
+        pass
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import safe_multiagent_rl_b200 as s
+    from safe_multiagent_rl_b200 import _lib
+    from safe_multiagent_rl_b200 import dist as sd
+    from safe_multiagent_rl_b200.rollout import make_accounting
+
+    rank, world, local_rank = sd.init_from_env()
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    A, E, T, S = a.n_agents, a.n_envs, a.max_t, a.size
+    K = A
+
+    # ---- synthetic workload (seeded; per-rank shard of the global env range) ----------------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    weights = [1.0 + (i % 3) for i in range(A)]
+    env = s.BatchedCoverageDiscrete(S, A, n_envs=E, weights=weights, device=dev, env_offset=rank * E,
+                                    starts=np.zeros((E, A, 2), dtype=np.uint8))
+    ld = env.ld
+    env.start_x[:, :E] = torch.randint(0, S, (A, E), generator=g, device=dev, dtype=torch.uint8)
+    env.start_y[:, :E] = torch.randint(0, S, (A, E), generator=g, device=dev, dtype=torch.uint8)
+    actions = torch.randint(0, 5, (T, A, ld), generator=g, device=dev, dtype=torch.uint8)
+    thr = torch.full((K,), 25.0, dtype=torch.float64, device=dev)
+    meta = s.BatchedMetaAgent([1] * K, a.gamma, 0.002, [25.0] * K, start_learning_cycle=0, lambda_0=0.1,
+                              n_agents=A, device=dev)
+    buf = env.new_rollout_buffer(T, g_mode=s.G_REWARD_TO_GO)
+    acc = make_accounting(a.gamma, T, s.G_REWARD_TO_GO, thr)
+    params = env._params
+    stream = torch.cuda.current_stream().cuda_stream
+    P = _lib.ptr
+    launches_per_step = 1 + T + 2 + 1     # reset, T steps, returns + stats finalize, lambda update
+
+    def closed_loop(ev_a=None, ev_b=None):
+        _lib.check(lib.smarl_grid_reset(P(env.start_x), P(env.start_y), P(env.pos_x), P(env.pos_y), P(env.obs),
+                                        A, E, ld, stream))
+        if ev_a is not None:
+            ev_a.record()
+        for t in range(T):
+            _lib.check(lib.smarl_coverage_step(C.byref(params), P(env.pos_x), P(env.pos_y), P(actions[t]),
+                                               P(env.obs), P(buf.reward[t]), P(buf.cost[t]), P(buf.done[t]),
+                                               P(meta.lambdas), P(buf.penalty[t]), E, ld, stream))
+        if ev_b is not None:
+            ev_b.record()
+        _lib.check(lib.smarl_rollout_returns(C.byref(acc), P(buf.reward), P(buf.cost), buf.cost_code,
+                                             P(buf.penalty), P(buf.R), P(buf.modR), P(buf.Csum), P(buf.G),
+                                             P(buf.stats_vec), P(buf.stats_scratch), A, K, E, ld, stream))
+        sd.allreduce_stats(buf.stats_vec)                       # the only inter-GPU traffic
+        _lib.check(lib.smarl_lambda_update(P(meta.lambdas), P(buf.stats_vec), P(thr), 0.002, A, K, stream))
+
+    def timed(fn, steps, warmup, per_step_events=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            if per_step_events:
+                fn(*evs[i])
+            else:
+                fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        inner = sum(x.elapsed_time(y) for x, y in evs) if per_step_events else None
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), inner
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    total_ms, step_kernel_ms = timed(closed_loop, a.steps, a.warmup, per_step_events=True)
+    clocks = sampler.stop() if sampler else None
+
+    agent_steps = float(E) * A * T
+    ms_per_step = total_ms / a.steps
+    value = world * agent_steps / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peak, peak_src = measured_peak()
+    launch_ms = step_kernel_ms / (a.steps * T)
+    bytes_per_launch = 19.0 * A * E
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "coverage_step_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("coverage_step_kernel", a),
+                "bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms, "peak_source": peak_src,
+                "share_of_step": step_kernel_ms / total_ms}
+
+    # ---- fused open-loop rollout (extra) ------------------------------------------------------------
+    fused = None
+    if not a.no_fused:
+        out = {}
+        def fused_fn():
+            env.rollout(actions, lambdas=meta.lambdas, gamma=a.gamma, thresholds=thr, g_mode=s.G_NONE, out=out)
+        f_ms, _ = timed(fused_fn, a.steps, a.warmup)
+        f_ms /= a.steps
+        f_bytes = (1.0 + 16.0 / T) * A * E * T                 # 1 + 16/T B per agent-step
+        fused = {"value": world * agent_steps / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms,
+                 "kernel": "coverage_rollout_kernel (open loop, g_mode 0)",
+                 "roofline": {"bound": "hbm", "achieved": f_bytes / (f_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": f_bytes / (f_ms * 1e-3) / 1e9 / peak,
+                              "note": "issue-bound by design: 1.32 algorithmic B per agent-step"}}
+        del out
+
+    # ---- end to end through the host-buffer C-ABI call -----------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        del buf
+        torch.cuda.empty_cache()
+        sess = C.c_void_p()
+        _lib.check(lib.smarl_host_session_create(C.byref(sess), A, K, T, E))
+        assert lib.smarl_host_session_ld(sess) == ld
+        pin = dict(pin_memory=True)
+        actions_h = torch.empty((T, A, ld), dtype=torch.uint8, **pin).copy_(actions)
+        sx_h = torch.empty((A, ld), dtype=torch.uint8, **pin).copy_(env.start_x)
+        sy_h = torch.empty((A, ld), dtype=torch.uint8, **pin).copy_(env.start_y)
+        R_h = torch.empty((A, ld), dtype=torch.float32, **pin)
+        M_h = torch.empty((A, ld), dtype=torch.float32, **pin)
+        C_h = torch.empty((K, ld), dtype=torch.int32, **pin)
+        st_h = torch.zeros(lib.smarl_stats_len(A, K), dtype=torch.float64)
+        lut_h = env._lut.cpu()
+        w_h = torch.tensor(weights, dtype=torch.float32)
+        lam_h = meta.lambdas.cpu()
+        thr_h = thr.cpu()
+        hp = _lib.CoverageParams(S, A, lut_h.numel(), 0, lut_h.data_ptr(), w_h.data_ptr())
+        hacc = _lib.Accounting(a.gamma, T, 0, thr_h.data_ptr())
+
+        def host_call():
+            _lib.check(lib.smarl_host_coverage_rollout(sess, C.byref(hp), C.byref(hacc), sx_h.data_ptr(),
+                                                       sy_h.data_ptr(), actions_h.data_ptr(), lam_h.data_ptr(),
+                                                       R_h.data_ptr(), M_h.data_ptr(), C_h.data_ptr(),
+                                                       st_h.data_ptr()))
+        e2e_steps = max(2, min(a.steps, 5))
+        for _ in range(2):
+            host_call()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_call()                                         # synchronous: returns with host results ready
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        el = float(tt.item())
+        e2e = {"value": world * agent_steps * e2e_steps / el, "unit": UNIT,
+               "h2d_bytes_per_step": int(T * A * ld + 2 * A * ld),
+               "d2h_bytes_per_step": int(3 * A * ld * 4 + 8 * lib.smarl_stats_len(A, K)),
+               "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps,
+               "api": "smarl_host_coverage_rollout (pinned host buffers, fused rollout, chunked 2-stream pipeline)",
+               "check": {"mean_cost_agent0": float(st_h[0] / st_h[-1]), "episodes": float(st_h[-1])}}
+        lib.smarl_host_session_destroy(sess)
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rate, cores = cpu_rate(a, a.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_seconds:.0f}s of whole episodes of the same env config, one env per process on "
+                         f"{cores} processes (oracle/scalar_port.py: env.step + MetaAgent.act + Buffer + reward-to-go)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(a), "mode": "closed-loop step API + returns kernel",
+                       "l2": "inputs larger than L2: each step launch streams 1.3 GB (19 B x 16 x 2^22)",
+                       "agent_steps_per_step": world * agent_steps},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "fused": fused,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
