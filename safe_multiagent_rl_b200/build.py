@@ -27,6 +27,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 # Per-file extras.  collision.cu restates the reference's float64 arithmetic operation by
 # operation, so the compiler must not contract a*b+c into an FMA there.
 EXTRA = {"collision.cu": ["-fmad=false"]}
+# Heavy files (32 agent-count instantiations per kernel) are compiled as several translation units
+# in parallel: the file is built once per value of -DSMARL_TU=k (see the header of each file).
+TU_SPLIT = {"coverage.cu": 3, "congestion.cu": 7, "collision.cu": 3}
 
 
 def _nvcc() -> str:
@@ -54,13 +57,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in sources():
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ_DIR, src[:-3] + ".o")
-        objs.append(o)
-        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hm):
-            cmd = [nvcc, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", s, "-o", o]
-            if verbose:
-                cmd.insert(1, "-Xptxas=-v")
-            jobs.append(cmd)
+        n_tu = TU_SPLIT.get(src, 1)
+        for tu in range(n_tu):
+            o = os.path.join(OBJ_DIR, src[:-3] + (f".tu{tu}" if n_tu > 1 else "") + ".o")
+            objs.append(o)
+            if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hm):
+                cmd = [nvcc, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", s, "-o", o]
+                if n_tu > 1:
+                    cmd.insert(1, f"-DSMARL_TU={tu}")
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                jobs.append(cmd)
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose or r.returncode != 0:
                 sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed for {cmd[-3]}")
+                raise RuntimeError(f"nvcc failed for {cmd[-3]}: " + r.stderr[-2000:])
     if jobs or not os.path.exists(LIB_PATH):
         cmd = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,6 +7,13 @@
 #include "common.cuh"
 #include "stats.cuh"
 
+// Built as three translation units (build.py compiles this file once per SMARL_TU value):
+//   0 step kernel   1 fused rollout kernel   2 reset kernel + C entry points
+#ifndef SMARL_TU
+#define SMARL_TU -1   // single-TU build: everything
+#endif
+#define SMARL_TU_IS(k) (SMARL_TU == -1 || SMARL_TU == (k))
+
 namespace smarl {
 
 struct CollisionStepArgs {
@@ -119,6 +126,42 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
   collisions = n;
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused open-loop episode: positions / done mask / discounted sums in registers for all T
+// steps (main.py:28-57 minus the policy nets, incl. the early break at :51).  The env reward
+// is shared by all agents, so one (S_rew, S_pen) pair per env serves every agent.
+// ---------------------------------------------------------------------------------------
+struct CollisionRolloutArgs {
+  const double* start_x;
+  const double* start_y;
+  const double* landmarks;
+  const float* actions;      // [T][2A][ld]
+  const double* lambdas;
+  double* final_x;
+  double* final_y;
+  uint8_t* final_done;
+  int32_t* n_active;
+  float* R;
+  float* modR;
+  int32_t* C;
+  float* G;
+  float* g_scratch;          // [2][T][ld]
+  double* partials;
+  const double* thresholds;
+  double gamma;
+  int64_t n_envs;
+  int64_t ld;
+  double size;
+  double agents_size;
+  int32_t L;
+  int32_t n_steps;
+  int32_t g_mode;
+};
+
+int launch_collision_step(int A, const CollisionStepArgs& a, unsigned grid, cudaStream_t s);
+int launch_collision_rollout(int A, const CollisionRolloutArgs& a, unsigned grid, cudaStream_t s);
+
+#if SMARL_TU_IS(0)
 template <int A>
 __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const CollisionStepArgs a) {
   const int64_t e = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
@@ -164,6 +207,112 @@ __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const Coll
   if (a.penalty) a.penalty[e] = (float)(__ldg(a.lambdas) * (double)collisions);   // meta_agent.py:21-22
 }
 
+int launch_collision_step(int A, const CollisionStepArgs& a, unsigned grid, cudaStream_t s) {
+  SMARL_DISPATCH_A(A, collision_step_kernel<kA><<<grid, kCollThreads, 0, s>>>(a));
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+#endif
+
+#if SMARL_TU_IS(1)
+template <int A>
+__global__ void __launch_bounds__(kCollThreads) collision_rollout_kernel(const CollisionRolloutArgs a) {
+  __shared__ double s_red[kCollThreads / 32];
+  const int64_t eg = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
+  const bool live = eg < a.n_envs;
+  const int64_t e = live ? eg : 0;
+  const int64_t ld = a.ld;
+  const int T = a.n_steps;
+  double px[A], py[A];
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    px[i] = a.start_x[i * ld + e];
+    py[i] = a.start_y[i * ld + e];
+  }
+  const uint32_t all = A == 32 ? 0xFFFFFFFFu : ((1u << A) - 1u);
+  const double lam = a.lambdas ? __ldg(a.lambdas) : 0.0;
+  uint32_t done_mask = 0u;
+  double s_rew = 0.0, s_pen = 0.0, disc = 1.0;
+  int csum = 0, steps = 0;
+  for (int t = 0; t < T; ++t) {
+    double reward = 0.0;
+    int collisions = 0;
+    if (done_mask != all) {
+      float adx[A], ady[A];
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        adx[i] = a.actions[((int64_t)t * 2 * A + 2 * i) * ld + e];
+        ady[i] = a.actions[((int64_t)t * 2 * A + 2 * i + 1) * ld + e];
+      }
+      collision_env_step<A>(px, py, done_mask, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size,
+                            reward, collisions);
+      ++steps;
+    }
+    const float rf = (float)reward;
+    const float pf = (float)(lam * (double)collisions);
+    s_rew += disc * (double)rf;
+    s_pen += disc * (double)pf;
+    csum += collisions;
+    if (a.g_mode == 1 && live) {
+      a.g_scratch[(int64_t)t * ld + e] = rf;
+      a.g_scratch[((int64_t)T + t) * ld + e] = pf;
+    } else if (a.g_mode == 2 && live) {
+      const float o = (float)(disc * ((double)rf - (double)pf));
+#pragma unroll
+      for (int i = 0; i < A; ++i) a.G[((int64_t)t * A + i) * ld + e] = o;
+    }
+    disc *= a.gamma;
+  }
+  if (live) {
+    const float r = (float)s_rew, m = (float)(s_rew - s_pen);
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      if (a.final_x) a.final_x[i * ld + e] = px[i];
+      if (a.final_y) a.final_y[i * ld + e] = py[i];
+      if (a.final_done) a.final_done[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
+      a.R[i * ld + e] = r;
+      a.modR[i * ld + e] = m;
+    }
+    a.C[e] = csum;
+    if (a.n_active) a.n_active[e] = steps;
+  }
+  if (a.partials) {
+    double* out = a.partials + (int64_t)blockIdx.x * stats_len(A, 1);
+    const double thr = a.thresholds ? __ldg(a.thresholds) : 0.0;
+    const double bc = block_sum<kCollThreads>(live ? (double)csum : 0.0, s_red);
+    const double bv = block_sum<kCollThreads>((live && a.thresholds && (double)csum > thr) ? 1.0 : 0.0, s_red);
+    const double br = block_sum<kCollThreads>(live ? s_rew : 0.0, s_red);
+    const double bm = block_sum<kCollThreads>(live ? s_rew - s_pen : 0.0, s_red);
+    if (threadIdx.x == 0) {
+      out[0] = bc;
+      out[1] = bv;
+      for (int i = 0; i < A; ++i) {
+        out[2 + i] = br;
+        out[2 + A + i] = bm;
+      }
+      out[2 + 2 * A] = 0.0;
+    }
+  }
+  if (a.g_mode == 1 && live) {                            // agent.py:200-206
+    double g_rew = 0.0, g_pen = 0.0;
+    for (int t = T - 1; t >= 0; --t) {
+      g_rew = (double)a.g_scratch[(int64_t)t * ld + e] + a.gamma * g_rew;
+      g_pen = (double)a.g_scratch[((int64_t)T + t) * ld + e] + a.gamma * g_pen;
+      const float o = (float)(g_rew - g_pen);
+#pragma unroll
+      for (int i = 0; i < A; ++i) a.G[((int64_t)t * A + i) * ld + e] = o;
+    }
+  }
+}
+
+int launch_collision_rollout(int A, const CollisionRolloutArgs& a, unsigned grid, cudaStream_t s) {
+  SMARL_DISPATCH_A(A, collision_rollout_kernel<kA><<<grid, kCollThreads, 0, s>>>(a));
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+#endif
+
+#if SMARL_TU_IS(2)
 __global__ void collision_reset_kernel(const double* __restrict__ start_x, const double* __restrict__ start_y,
                                        const double* __restrict__ landmarks, double* __restrict__ pos_x,
                                        double* __restrict__ pos_y, uint8_t* __restrict__ done,
@@ -193,10 +342,13 @@ static int check_collision(const SmarlCollisionParams* p) {
   return SMARL_OK;
 }
 
+#endif
+
 }  // namespace smarl
 
 using namespace smarl;
 
+#if SMARL_TU_IS(2)
 extern "C" int smarl_collision_reset(const SmarlCollisionParams* p, const double* start_x,
                                      const double* start_y, const double* landmarks, double* pos_x,
                                      double* pos_y, uint8_t* done, float* obs, int64_t n_envs, int64_t ld,
@@ -228,9 +380,7 @@ extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x
   a.penalty = penalty; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size;
   a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
   const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
-  SMARL_DISPATCH_A(p->n_agents,
-                   collision_step_kernel<kA><<<grid, kCollThreads, 0, (cudaStream_t)stream>>>(a));
-  SMARL_CUDA(cudaGetLastError());
+  if (int rc = launch_collision_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;
 }
 
@@ -242,6 +392,26 @@ extern "C" int smarl_collision_rollout(const SmarlCollisionParams* p, const Smar
                                        int32_t* C, float* G, float* g_scratch, double* stats,
                                        double* stats_scratch, int64_t n_envs, int64_t ld,
                                        smarl_stream_t stream) {
-  set_error("smarl_collision_rollout: fused Collision rollout not built yet; use the step + returns path");
-  return SMARL_EUNSUPPORTED;
+  if (int rc = check_collision(p)) return rc;
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(acc != nullptr, "accounting params is NULL");
+  SMARL_REQUIRE(acc->n_steps >= 1, "n_steps=%d must be >= 1", acc->n_steps);
+  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 2, "bad g_mode %d", acc->g_mode);
+  SMARL_REQUIRE(start_x && start_y && landmarks && actions && R && modR && C, "null required pointer");
+  SMARL_REQUIRE(acc->g_mode == 0 || G, "g_mode != 0 needs G");
+  SMARL_REQUIRE(acc->g_mode != 1 || g_scratch, "g_mode 1 needs g_scratch [2][T][ld]");
+  SMARL_REQUIRE((stats == nullptr) == (stats_scratch == nullptr), "stats and stats_scratch go together");
+  CollisionRolloutArgs a;
+  a.start_x = start_x; a.start_y = start_y; a.landmarks = landmarks; a.actions = actions;
+  a.lambdas = lambdas; a.final_x = final_x; a.final_y = final_y; a.final_done = final_done;
+  a.n_active = n_active; a.R = R; a.modR = modR; a.C = C; a.G = G; a.g_scratch = g_scratch;
+  a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma; a.n_envs = n_envs;
+  a.ld = ld; a.size = (double)p->size; a.agents_size = p->agents_size; a.L = p->n_landmarks;
+  a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
+  const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
+  if (int rc = launch_collision_rollout(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
+  if (stats)
+    return launch_stats_finalize(stats_scratch, grid, p->n_agents, 1, n_envs, stats, (cudaStream_t)stream);
+  return SMARL_OK;
 }
+#endif

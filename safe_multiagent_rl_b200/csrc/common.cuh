@@ -80,6 +80,15 @@ __device__ __forceinline__ float4 ld_stream_f4(const void* p) {
                : "l"(p));
   return v;
 }
+// Coherent load for data this kernel wrote itself earlier (scratch re-reads): never .nc.
+__device__ __forceinline__ float4 ld_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ double2 ld_stream_d2(const void* p) {
   double2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));

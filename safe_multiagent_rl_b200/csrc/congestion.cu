@@ -3,6 +3,14 @@
 #include "congestion.cuh"
 #include "stats.cuh"
 
+// Built as several translation units (build.py compiles this file once per SMARL_TU value) so the
+// 32 agent-count instantiations of each kernel compile in parallel:
+//   0,1,2 step kernel noise mode 0/1/2   3,4,5 rollout kernel mode 0/1/2   6 C entry points
+#ifndef SMARL_TU
+#define SMARL_TU -1   // single-TU build: everything
+#endif
+#define SMARL_TU_IS(k) (SMARL_TU == -1 || SMARL_TU == (k))
+
 namespace smarl {
 
 struct CongestionStepArgs {
@@ -43,6 +51,50 @@ __device__ __forceinline__ void congestion_transition(uint32_t (&xw)[A], uint32_
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused open-loop episode (main.py:28-57 minus the policy nets, buffer.py:30-39,
+// meta_agent.py:18-30, agent.py:129-132 / :200-206).  Positions stay in registers; the
+// per-agent discounted sums (A x 4 envs, f64) live in shared memory, indexed
+// [agent][env lane][thread] so that every access is conflict-free.
+// ---------------------------------------------------------------------------------------
+struct CongestionRolloutArgs {
+  const uint8_t* start_x;
+  const uint8_t* start_y;
+  const uint8_t* actions;   // [T][A][ld]
+  const uint8_t* moves;     // [T][A][ld] (MODE 1)
+  const double* lambdas;
+  uint8_t* final_x;
+  uint8_t* final_y;
+  float* R;
+  float* modR;
+  int32_t* C;
+  float* G;                 // [T][A][ld]
+  float* g_scratch;         // [T][ld] penalties (g_mode 1)
+  double* partials;
+  const double* thresholds;
+  const double* demand;
+  double gamma;
+  uint64_t keep_threshold;
+  uint64_t seed;
+  int64_t env_offset;
+  int64_t n_groups;
+  int64_t n_envs;
+  int64_t ld;
+  int32_t size;
+  int32_t n_steps;
+  int32_t g_mode;
+};
+
+constexpr int kCongRollThreads = 64;
+
+int launch_congestion_step_m0(int A, const CongestionStepArgs& a, unsigned grid, cudaStream_t s);
+int launch_congestion_step_m1(int A, const CongestionStepArgs& a, unsigned grid, cudaStream_t s);
+int launch_congestion_step_m2(int A, const CongestionStepArgs& a, unsigned grid, cudaStream_t s);
+int launch_congestion_rollout_m0(int A, const CongestionRolloutArgs& a, unsigned grid, cudaStream_t s);
+int launch_congestion_rollout_m1(int A, const CongestionRolloutArgs& a, unsigned grid, cudaStream_t s);
+int launch_congestion_rollout_m2(int A, const CongestionRolloutArgs& a, unsigned grid, cudaStream_t s);
+
+#if SMARL_TU_IS(0) || SMARL_TU_IS(1) || SMARL_TU_IS(2)
 template <int A, int MODE>
 __global__ void __launch_bounds__(kCongThreads) congestion_step_kernel(const CongestionStepArgs a) {
   const int64_t g = (int64_t)blockIdx.x * kCongThreads + threadIdx.x;
@@ -106,6 +158,214 @@ __global__ void __launch_bounds__(kCongThreads) congestion_step_kernel(const Con
   }
 }
 
+#define SMARL_DEFINE_CONG_STEP(M)                                                                       \
+  int launch_congestion_step_m##M(int A, const CongestionStepArgs& a, unsigned grid, cudaStream_t s) {  \
+    SMARL_DISPATCH_A(A, congestion_step_kernel<kA, M><<<grid, kCongThreads, 0, s>>>(a));                \
+    SMARL_CUDA(cudaGetLastError());                                                                     \
+    return SMARL_OK;                                                                                    \
+  }
+#if SMARL_TU_IS(0)
+SMARL_DEFINE_CONG_STEP(0)
+#endif
+#if SMARL_TU_IS(1)
+SMARL_DEFINE_CONG_STEP(1)
+#endif
+#if SMARL_TU_IS(2)
+SMARL_DEFINE_CONG_STEP(2)
+#endif
+#endif
+
+#if SMARL_TU_IS(3) || SMARL_TU_IS(4) || SMARL_TU_IS(5)
+
+template <int A, int MODE>
+__global__ void __launch_bounds__(kCongRollThreads) congestion_rollout_kernel(const CongestionRolloutArgs a) {
+  extern __shared__ double s_acc[];                      // [A][4][kCongRollThreads]
+  __shared__ double s_red[kCongRollThreads / 32];
+  const int tid = threadIdx.x;
+  const int64_t g = (int64_t)blockIdx.x * kCongRollThreads + tid;
+  const bool live = g < a.n_groups;
+  const int64_t e0 = (live ? g : 0) * 4;
+  const int64_t ld = a.ld;
+  const int T = a.n_steps;
+  const int W = a.size + 1;
+  const uint32_t size4 = (uint32_t)a.size * 0x01010101u;
+  const double lam = a.lambdas ? __ldg(a.lambdas) : 0.0;
+
+  uint32_t xw[A], yw[A];
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    xw[i] = ld_stream_u32(a.start_x + i * ld + e0);
+    yw[i] = ld_stream_u32(a.start_y + i * ld + e0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_acc[(i * 4 + k) * kCongRollThreads + tid] = 0.0;
+  }
+  double s_pen[4] = {0, 0, 0, 0};
+  int csum[4] = {0, 0, 0, 0};
+  double disc = 1.0;
+
+  for (int t = 0; t < T; ++t) {
+    uint32_t aw[A], mw[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      aw[i] = ld_stream_u32(a.actions + ((int64_t)t * A + i) * ld + e0);
+      if (MODE == 1) mw[i] = ld_stream_u32(a.moves + ((int64_t)t * A + i) * ld + e0);
+      if (MODE == 0) mw[i] = aw[i];
+    }
+    if (MODE == 2) congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + e0, (uint32_t)t);
+    uint32_t dcw[A], conw[A];
+    congestion_transition<A>(xw, yw, mw, dcw, size4);
+#pragma unroll
+    for (int i = 0; i < A; ++i) conw[i] = 0u;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int c = max(0, A / 3 - congestion_env<A>(xw, yw, dcw, aw, conw, k));
+      c0 = k == 0 ? c : c0;
+      c1 = k == 1 ? c : c1;
+      c2 = k == 2 ? c : c2;
+      c3 = k == 3 ? c : c3;
+    }
+    const int cost[4] = {c0, c1, c2, c3};
+    float pen[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pen[k] = (float)(lam * cost[k]);                  // the step kernel publishes the penalty as f32
+      s_pen[k] += disc * (double)pen[k];
+      csum[k] += cost[k];
+    }
+    if (a.g_mode == 1 && live) st_stream_f4(a.g_scratch + (int64_t)t * ld + e0, make_float4(pen[0], pen[1], pen[2], pen[3]));
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      float r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        r[k] = (float)congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
+                                        (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W);
+        s_acc[(i * 4 + k) * kCongRollThreads + tid] += disc * (double)r[k];
+      }
+      if (a.g_mode == 1 && live) {
+        st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0, make_float4(r[0], r[1], r[2], r[3]));
+      } else if (a.g_mode == 2 && live) {               // agent.py:129-132
+        st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0,
+                     make_float4((float)(disc * ((double)r[0] - (double)pen[0])), (float)(disc * ((double)r[1] - (double)pen[1])),
+                                 (float)(disc * ((double)r[2] - (double)pen[2])), (float)(disc * ((double)r[3] - (double)pen[3]))));
+      }
+    }
+    disc *= a.gamma;
+  }
+
+  bool valid[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) valid[k] = live && (e0 + k < a.n_envs);
+  double* out = a.partials ? a.partials + (int64_t)blockIdx.x * stats_len(A, 1) : nullptr;
+  if (live) {
+    st_stream_i4(a.C + e0, make_int4(csum[0], csum[1], csum[2], csum[3]));
+  }
+#pragma unroll 1
+  for (int i = 0; i < A; ++i) {
+    double raw[4], mod[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      raw[k] = s_acc[(i * 4 + k) * kCongRollThreads + tid];
+      mod[k] = raw[k] - s_pen[k];
+    }
+    if (live) {
+      if (a.final_x) st_stream_u32(a.final_x + i * ld + e0, xw[i]);
+      if (a.final_y) st_stream_u32(a.final_y + i * ld + e0, yw[i]);
+      st_stream_f4(a.R + i * ld + e0, make_float4((float)raw[0], (float)raw[1], (float)raw[2], (float)raw[3]));
+      st_stream_f4(a.modR + i * ld + e0, make_float4((float)mod[0], (float)mod[1], (float)mod[2], (float)mod[3]));
+    }
+    if (out) {
+      double v_raw = 0.0, v_mod = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v_raw += valid[k] ? raw[k] : 0.0;
+        v_mod += valid[k] ? mod[k] : 0.0;
+      }
+      const double b_raw = block_sum<kCongRollThreads>(v_raw, s_red);
+      const double b_mod = block_sum<kCongRollThreads>(v_mod, s_red);
+      if (tid == 0) {
+        out[2 + i] = b_raw;
+        out[2 + A + i] = b_mod;
+      }
+    }
+  }
+  if (out) {
+    const double thr = a.thresholds ? __ldg(a.thresholds) : 0.0;
+    double c = 0.0, viol = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c += valid[k] ? (double)csum[k] : 0.0;
+      viol += (valid[k] && a.thresholds && (double)csum[k] > thr) ? 1.0 : 0.0;
+    }
+    const double bc = block_sum<kCongRollThreads>(c, s_red);
+    const double bv = block_sum<kCongRollThreads>(viol, s_red);
+    if (tid == 0) {
+      out[0] = bc;
+      out[1] = bv;
+      out[2 + 2 * A] = 0.0;
+    }
+  }
+
+  if (a.g_mode == 1 && live) {                          // agent.py:200-206, in place over the stored rewards
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_acc[(i * 4 + k) * kCongRollThreads + tid] = 0.0;
+    for (int t = T - 1; t >= 0; --t) {
+      const float4 q = ld_f4(a.g_scratch + (int64_t)t * ld + e0);
+      const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll 4
+      for (int i = 0; i < A; ++i) {
+        float* gp = a.G + ((int64_t)t * A + i) * ld + e0;
+        const float4 r = ld_f4(gp);
+        const float rr[4] = {r.x, r.y, r.z, r.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double& run = s_acc[(i * 4 + k) * kCongRollThreads + tid];
+          run = ((double)rr[k] - (double)qq[k]) + a.gamma * run;
+          o[k] = (float)run;
+        }
+        st_stream_f4(gp, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+}
+
+#define SMARL_DEFINE_CONG_ROLLOUT(M)                                                                         \
+  int launch_congestion_rollout_m##M(int A, const CongestionRolloutArgs& a, unsigned grid, cudaStream_t s) { \
+    const size_t smem = sizeof(double) * 4 * kCongRollThreads * (size_t)A;                                   \
+    SMARL_DISPATCH_A(A, {                                                                                    \
+      auto kern = congestion_rollout_kernel<kA, M>;                                                          \
+      if (smem > 48 * 1024)                                                                                  \
+        SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+      kern<<<grid, kCongRollThreads, smem, s>>>(a);                                                          \
+    });                                                                                                      \
+    SMARL_CUDA(cudaGetLastError());                                                                          \
+    return SMARL_OK;                                                                                         \
+  }
+#if SMARL_TU_IS(3)
+SMARL_DEFINE_CONG_ROLLOUT(0)
+#endif
+#if SMARL_TU_IS(4)
+SMARL_DEFINE_CONG_ROLLOUT(1)
+#endif
+#if SMARL_TU_IS(5)
+SMARL_DEFINE_CONG_ROLLOUT(2)
+#endif
+#endif
+
+#if SMARL_TU_IS(6)
+static int launch_congestion_step(int mode, int A, const CongestionStepArgs& a, unsigned grid, cudaStream_t s) {
+  return mode == 0 ? launch_congestion_step_m0(A, a, grid, s)
+       : mode == 1 ? launch_congestion_step_m1(A, a, grid, s) : launch_congestion_step_m2(A, a, grid, s);
+}
+static int launch_congestion_rollout(int mode, int A, const CongestionRolloutArgs& a, unsigned grid, cudaStream_t s) {
+  return mode == 0 ? launch_congestion_rollout_m0(A, a, grid, s)
+       : mode == 1 ? launch_congestion_rollout_m1(A, a, grid, s) : launch_congestion_rollout_m2(A, a, grid, s);
+}
+
 static int check_congestion(const SmarlCongestionParams* p) {
   SMARL_REQUIRE(p != nullptr, "params is NULL");
   SMARL_REQUIRE(p->size >= 1 && p->size <= 254, "size=%d outside 1..254", p->size);
@@ -115,10 +375,13 @@ static int check_congestion(const SmarlCongestionParams* p) {
   return SMARL_OK;
 }
 
+#endif
+
 }  // namespace smarl
 
 using namespace smarl;
 
+#if SMARL_TU_IS(6)
 extern "C" int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* pos_x, uint8_t* pos_y,
                                      const uint8_t* actions, uint8_t* moves, float* obs, float* reward,
                                      int32_t* cost, uint8_t* done, const double* lambdas, float* penalty,
@@ -138,12 +401,7 @@ extern "C" int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* po
   a.env_offset = p->env_offset; a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.t = t;
   const unsigned grid = (unsigned)((a.n_groups + kCongThreads - 1) / kCongThreads);
   cudaStream_t s = (cudaStream_t)stream;
-  switch (p->noise_mode) {
-    case 0: SMARL_DISPATCH_A(p->n_agents, congestion_step_kernel<kA, 0><<<grid, kCongThreads, 0, s>>>(a)); break;
-    case 1: SMARL_DISPATCH_A(p->n_agents, congestion_step_kernel<kA, 1><<<grid, kCongThreads, 0, s>>>(a)); break;
-    default: SMARL_DISPATCH_A(p->n_agents, congestion_step_kernel<kA, 2><<<grid, kCongThreads, 0, s>>>(a)); break;
-  }
-  SMARL_CUDA(cudaGetLastError());
+  if (int rc = launch_congestion_step(p->noise_mode, p->n_agents, a, grid, s)) return rc;
   return SMARL_OK;
 }
 
@@ -154,6 +412,31 @@ extern "C" int smarl_congestion_rollout(const SmarlCongestionParams* p, const Sm
                                         float* R, float* modR, int32_t* C, float* G, float* g_scratch,
                                         double* stats, double* stats_scratch, int64_t n_envs,
                                         int64_t ld, smarl_stream_t stream) {
-  set_error("smarl_congestion_rollout: fused Congestion rollout not built yet; use the step + returns path");
-  return SMARL_EUNSUPPORTED;
+  if (int rc = check_congestion(p)) return rc;
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(acc != nullptr, "accounting params is NULL");
+  SMARL_REQUIRE(acc->n_steps >= 1, "n_steps=%d must be >= 1", acc->n_steps);
+  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 2, "bad g_mode %d", acc->g_mode);
+  SMARL_REQUIRE(start_x && start_y && actions && R && modR && C, "null required pointer");
+  SMARL_REQUIRE(p->noise_mode != 1 || moves, "noise_mode 1 needs the recorded moves [T][A][ld]");
+  SMARL_REQUIRE(acc->g_mode == 0 || G, "g_mode != 0 needs G");
+  SMARL_REQUIRE(acc->g_mode != 1 || g_scratch, "g_mode 1 needs g_scratch");
+  SMARL_REQUIRE((stats == nullptr) == (stats_scratch == nullptr), "stats and stats_scratch go together");
+  SMARL_REQUIRE(aligned16(start_x) && aligned16(start_y) && aligned16(actions) && aligned16(moves) &&
+                    aligned16(final_x) && aligned16(final_y) && aligned16(R) && aligned16(modR) &&
+                    aligned16(C) && aligned16(G) && aligned16(g_scratch), "pointers must be 16-byte aligned");
+  CongestionRolloutArgs a;
+  a.start_x = start_x; a.start_y = start_y; a.actions = actions; a.moves = moves; a.lambdas = lambdas;
+  a.final_x = final_x; a.final_y = final_y; a.R = R; a.modR = modR; a.C = C; a.G = G;
+  a.g_scratch = g_scratch; a.partials = stats_scratch; a.thresholds = acc->thresholds;
+  a.demand = p->demand; a.gamma = acc->gamma; a.keep_threshold = p->keep_threshold; a.seed = p->seed;
+  a.env_offset = p->env_offset; a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
+  a.size = p->size; a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
+  const unsigned grid = (unsigned)((a.n_groups + kCongRollThreads - 1) / kCongRollThreads);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = launch_congestion_rollout(p->noise_mode, p->n_agents, a, grid, s)) return rc;
+  if (stats)
+    return launch_stats_finalize(stats_scratch, grid, p->n_agents, 1, n_envs, stats, s);
+  return SMARL_OK;
 }
+#endif

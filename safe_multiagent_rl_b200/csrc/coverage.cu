@@ -9,6 +9,13 @@
 #include "coverage.cuh"
 #include "stats.cuh"
 
+// Built as three translation units (build.py compiles this file once per SMARL_TU value):
+//   0 step kernel   1 fused rollout kernel   2 reset kernel + C entry points
+#ifndef SMARL_TU
+#define SMARL_TU -1   // single-TU build: everything
+#endif
+#define SMARL_TU_IS(k) (SMARL_TU == -1 || SMARL_TU == (k))
+
 namespace smarl {
 
 struct CoverageStepArgs {
@@ -31,6 +38,44 @@ struct CoverageStepArgs {
 
 constexpr int kStepThreads = 128;
 
+// ---------------------------------------------------------------------------------------
+// Fused open-loop episode: positions, cost counters and discounted sums never leave
+// registers for the whole horizon; per step a thread reads A action words (1 B / agent-step).
+// Replaces main.py:28-57 (minus the policy nets) + buffer.py:30-39 + meta_agent.py:18-30 +
+// agent.py:129-132 / :200-206 for four envs per thread.
+// ---------------------------------------------------------------------------------------
+struct CoverageRolloutArgs {
+  const uint8_t* start_x;
+  const uint8_t* start_y;
+  const uint8_t* actions;   // [T][A][ld]
+  const double* lambdas;
+  uint8_t* final_x;
+  uint8_t* final_y;
+  float* R;
+  float* modR;
+  int32_t* C;
+  float* G;                 // [T][A][ld]
+  float* g_scratch;         // [2][T][ld]
+  double* partials;         // [gridDim.x][stats_len]
+  const double* thresholds;
+  const float* lut;
+  const float* weights;
+  double gamma;
+  int64_t n_groups;
+  int64_t n_envs;
+  int64_t ld;
+  int32_t size;
+  int32_t lut_len;
+  int32_t n_steps;
+  int32_t g_mode;
+};
+
+constexpr int kRolloutThreads = 128;
+
+int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaStream_t s);
+int launch_coverage_rollout(int A, const CoverageRolloutArgs& a, unsigned grid, cudaStream_t s);
+
+#if SMARL_TU_IS(0)
 template <int A>
 __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const CoverageStepArgs a) {
   extern __shared__ float s_lut[];
@@ -90,56 +135,15 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
   }
 }
 
-// state <- start and rebuild the float observation (coverage.py:45-52, congestion.py:39-47).
-__global__ void grid_reset_kernel(const uint8_t* __restrict__ start_x, const uint8_t* __restrict__ start_y,
-                                  uint8_t* __restrict__ pos_x, uint8_t* __restrict__ pos_y,
-                                  float* __restrict__ obs, int64_t n_groups, int64_t ld) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
-  const int64_t off = (int64_t)blockIdx.y * ld + g * 4;
-  const uint32_t xw = ld_stream_u32(start_x + off), yw = ld_stream_u32(start_y + off);
-  st_stream_u32(pos_x + off, xw);
-  st_stream_u32(pos_y + off, yw);
-  if (obs) {
-    st_stream_f4(obs + (2 * (int64_t)blockIdx.y) * ld + g * 4, bytes_to_float4(xw));
-    st_stream_f4(obs + (2 * (int64_t)blockIdx.y + 1) * ld + g * 4, bytes_to_float4(yw));
-  }
+int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaStream_t s) {
+  const size_t smem = (size_t)(a.lut_len + 1) * sizeof(float);
+  SMARL_DISPATCH_A(A, coverage_step_kernel<kA><<<grid, kStepThreads, smem, s>>>(a));
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
 }
+#endif
 
-// ---------------------------------------------------------------------------------------
-// Fused open-loop episode: positions, cost counters and discounted sums never leave
-// registers for the whole horizon; per step a thread reads A action words (1 B / agent-step).
-// Replaces main.py:28-57 (minus the policy nets) + buffer.py:30-39 + meta_agent.py:18-30 +
-// agent.py:129-132 / :200-206 for four envs per thread.
-// ---------------------------------------------------------------------------------------
-struct CoverageRolloutArgs {
-  const uint8_t* start_x;
-  const uint8_t* start_y;
-  const uint8_t* actions;   // [T][A][ld]
-  const double* lambdas;
-  uint8_t* final_x;
-  uint8_t* final_y;
-  float* R;
-  float* modR;
-  int32_t* C;
-  float* G;                 // [T][A][ld]
-  float* g_scratch;         // [2][T][ld]
-  double* partials;         // [gridDim.x][stats_len]
-  const double* thresholds;
-  const float* lut;
-  const float* weights;
-  double gamma;
-  int64_t n_groups;
-  int64_t n_envs;
-  int64_t ld;
-  int32_t size;
-  int32_t lut_len;
-  int32_t n_steps;
-  int32_t g_mode;
-};
-
-constexpr int kRolloutThreads = 128;
-
+#if SMARL_TU_IS(1)
 template <int A>
 __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const CoverageRolloutArgs a) {
   extern __shared__ float s_lut[];
@@ -235,8 +239,8 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
     if (a.g_mode == 1) {                               // agent.py:200-206, backward Horner
       double g_rew[4] = {0, 0, 0, 0}, g_pen[4] = {0, 0, 0, 0};
       for (int t = T - 1; t >= 0; --t) {
-        const float4 r = ld_stream_f4(a.g_scratch + (int64_t)t * ld + e0);
-        const float4 q = ld_stream_f4(a.g_scratch + ((int64_t)T + t) * ld + e0);
+        const float4 r = ld_f4(a.g_scratch + (int64_t)t * ld + e0);
+        const float4 q = ld_f4(a.g_scratch + ((int64_t)T + t) * ld + e0);
         const float rr[4] = {r.x, r.y, r.z, r.w}, qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -293,6 +297,31 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
   }
 }
 
+int launch_coverage_rollout(int A, const CoverageRolloutArgs& a, unsigned grid, cudaStream_t s) {
+  const size_t smem = (size_t)(a.lut_len + 1) * sizeof(float);
+  SMARL_DISPATCH_A(A, coverage_rollout_kernel<kA><<<grid, kRolloutThreads, smem, s>>>(a));
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+#endif
+
+#if SMARL_TU_IS(2)
+// state <- start and rebuild the float observation (coverage.py:45-52, congestion.py:39-47).
+__global__ void grid_reset_kernel(const uint8_t* __restrict__ start_x, const uint8_t* __restrict__ start_y,
+                                  uint8_t* __restrict__ pos_x, uint8_t* __restrict__ pos_y,
+                                  float* __restrict__ obs, int64_t n_groups, int64_t ld) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const int64_t off = (int64_t)blockIdx.y * ld + g * 4;
+  const uint32_t xw = ld_stream_u32(start_x + off), yw = ld_stream_u32(start_y + off);
+  st_stream_u32(pos_x + off, xw);
+  st_stream_u32(pos_y + off, yw);
+  if (obs) {
+    st_stream_f4(obs + (2 * (int64_t)blockIdx.y) * ld + g * 4, bytes_to_float4(xw));
+    st_stream_f4(obs + (2 * (int64_t)blockIdx.y + 1) * ld + g * 4, bytes_to_float4(yw));
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------
@@ -307,10 +336,13 @@ static int check_coverage(const SmarlCoverageParams* p) {
   return SMARL_OK;
 }
 
+#endif
+
 }  // namespace smarl
 
 using namespace smarl;
 
+#if SMARL_TU_IS(2)
 extern "C" int smarl_grid_reset(const uint8_t* start_x, const uint8_t* start_y, uint8_t* pos_x,
                                 uint8_t* pos_y, float* obs, int32_t n_agents, int64_t n_envs,
                                 int64_t ld, smarl_stream_t stream) {
@@ -344,10 +376,7 @@ extern "C" int smarl_coverage_step(const SmarlCoverageParams* p, uint8_t* pos_x,
   a.lut = p->lut; a.weights = p->weights;
   a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.lut_len = p->lut_len;
   const unsigned grid = (unsigned)((a.n_groups + kStepThreads - 1) / kStepThreads);
-  const size_t smem = (size_t)(p->lut_len + 1) * sizeof(float);
-  SMARL_DISPATCH_A(p->n_agents,
-                   coverage_step_kernel<kA><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(a));
-  SMARL_CUDA(cudaGetLastError());
+  if (int rc = launch_coverage_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;
 }
 
@@ -379,12 +408,10 @@ extern "C" int smarl_coverage_rollout(const SmarlCoverageParams* p, const SmarlA
   a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld; a.size = p->size;
   a.lut_len = p->lut_len; a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
   const unsigned grid = (unsigned)((a.n_groups + kRolloutThreads - 1) / kRolloutThreads);
-  const size_t smem = (size_t)(p->lut_len + 1) * sizeof(float);
-  SMARL_DISPATCH_A(p->n_agents,
-                   coverage_rollout_kernel<kA><<<grid, kRolloutThreads, smem, (cudaStream_t)stream>>>(a));
-  SMARL_CUDA(cudaGetLastError());
+  if (int rc = launch_coverage_rollout(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   if (stats)
     return launch_stats_finalize(stats_scratch, grid, p->n_agents, p->n_agents, n_envs, stats,
                                  (cudaStream_t)stream);
   return SMARL_OK;
 }
+#endif

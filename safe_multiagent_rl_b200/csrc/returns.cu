@@ -256,8 +256,8 @@ extern "C" int32_t smarl_stats_len(int32_t n_agents, int32_t n_constraints) {
 }
 
 extern "C" int64_t smarl_stats_scratch_len(int32_t n_agents, int32_t n_constraints, int64_t n_envs) {
-  const int64_t n_groups = (n_envs + 3) / 4;
-  const int64_t n_chunks = (n_groups + kAccThreads - 1) / kAccThreads;
+  // one row of block partials per CTA; the smallest CTA any producer uses covers 64 envs
+  const int64_t n_chunks = (n_envs + 63) / 64;
   return n_chunks * stats_len(n_agents, n_constraints);
 }
 

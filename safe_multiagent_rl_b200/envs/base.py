@@ -81,6 +81,32 @@ class BatchedEnv:
         self.t += 1
         return self._views(reward, cost, done)
 
+    def _rollout_outputs(self, T, g_mode, out, g_scratch_rows):
+        """Allocate (or reuse from ``out``) the product buffers of a fused rollout."""
+        from ..rollout import G_NONE
+        A, K, E, dev = self.n_agents, self.n_constraints, self.n_envs, self.device
+        o = out if out is not None else {}
+
+        def buf(name, rows, dtype, lead=()):
+            if name not in o:
+                o[name] = self._alloc(rows, dtype, lead)
+            return o[name]
+        buf("R_", A, torch.float32), buf("modR_", A, torch.float32), buf("C_", K, torch.int32)
+        o["G_"] = buf("G_buf", A, torch.float32, (T,)) if g_mode != G_NONE else None
+        o["gs_"] = buf("g_scratch", 1, torch.float32, (g_scratch_rows,)) if g_mode == G_REWARD_TO_GO else None
+        if "stats_vec" not in o:
+            o["stats_vec"] = torch.zeros(self.lib.smarl_stats_len(A, K), dtype=torch.float64, device=dev)
+            o["stats_scratch"] = torch.zeros(self.lib.smarl_stats_scratch_len(A, K, E), dtype=torch.float64,
+                                             device=dev)
+        return o
+
+    def _rollout_result(self, o):
+        from ..rollout import Stats
+        A, K, E = self.n_agents, self.n_constraints, self.n_envs
+        o.update(R=env_major(o["R_"], E), modR=env_major(o["modR_"], E), C=env_major(o["C_"], E),
+                 G=None if o["G_"] is None else env_major(o["G_"], E), stats=Stats(o["stats_vec"], A, K))
+        return o
+
     def new_rollout_buffer(self, n_steps, g_mode=G_REWARD_TO_GO):
         return RolloutBuffer(n_steps, self.n_agents, self.n_constraints, self.n_envs, self.cost_dtype,
                              self.device, g_mode)

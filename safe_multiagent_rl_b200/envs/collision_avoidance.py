@@ -9,6 +9,8 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..layout import env_major
+from ..rollout import G_NONE, make_accounting
 from .base import BatchedEnv
 
 
@@ -85,3 +87,23 @@ class BatchedCollisionAvoidance(BatchedEnv):
             C.byref(self._params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done),
             _lib.ptr(act), _lib.ptr(self.landmarks), _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost),
             _lib.ptr(done), _lib.ptr(lambdas), _lib.ptr(penalty), self.n_envs, self.ld, _lib.stream_ptr()))
+
+    def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None):
+        """Open-loop fused episode (one launch).  actions ``[T, 2*n_agents, ld]`` float32 (kernel layout,
+        rows dx0, dy0, dx1, ...).  Adds ``n_active`` [E]: the episode length T' (main.py:51)."""
+        T = int(actions.shape[0])
+        A, E, dev = self.n_agents, self.n_envs, self.device
+        assert actions.dtype == torch.float32 and tuple(actions.shape) == (T, 2 * A, self.ld) and actions.is_contiguous()
+        o = self._rollout_outputs(T, g_mode, out, 2 * T)
+        if "n_active_" not in o:
+            o["n_active_"] = self._alloc(1, torch.int32)
+        thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
+        acc = make_accounting(gamma, T, g_mode, thr)
+        _lib.check(self.lib.smarl_collision_rollout(
+            C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),
+            _lib.ptr(self.landmarks), _lib.ptr(actions), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y),
+            _lib.ptr(self.agent_done), _lib.ptr(o["n_active_"]), _lib.ptr(o["R_"]), _lib.ptr(o["modR_"]),
+            _lib.ptr(o["C_"]), _lib.ptr(o["G_"]), _lib.ptr(o["gs_"]), _lib.ptr(o["stats_vec"]),
+            _lib.ptr(o["stats_scratch"]), E, self.ld, _lib.stream_ptr()))
+        o["n_active"] = o["n_active_"][0, :E]
+        return self._rollout_result(o)

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..rollout import G_NONE, make_accounting
 from .base import BatchedEnv
 
 # congestion.py:28 -- the reference's hard-coded table (only valid for size <= 3)
@@ -120,3 +121,25 @@ class BatchedCongestion(BatchedEnv):
             C.byref(p), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(act), _lib.ptr(self.moves),
             _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
             _lib.ptr(penalty), self.t, self.n_envs, self.ld, _lib.stream_ptr()))
+
+    def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None, moves=None):
+        """Open-loop fused episode (one launch).  actions ``[T, n_agents, ld]`` uint8 (kernel layout);
+        ``moves`` of the same shape replays recorded effective moves, otherwise noise comes from the
+        Philox stream (same stream as T calls of ``step``)."""
+        T = int(actions.shape[0])
+        A, E, dev = self.n_agents, self.n_envs, self.device
+        assert actions.dtype == torch.uint8 and tuple(actions.shape) == (T, A, self.ld) and actions.is_contiguous()
+        if moves is not None:
+            assert moves.dtype == torch.uint8 and tuple(moves.shape) == (T, A, self.ld) and moves.is_contiguous()
+        mode = NOISE_RECORDED if moves is not None else (NOISE_PHILOX if self.noise > 0 else NOISE_NONE)
+        o = self._rollout_outputs(T, g_mode, out, T)
+        thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
+        acc = make_accounting(gamma, T, g_mode, thr)
+        p = self._params(mode)
+        _lib.check(self.lib.smarl_congestion_rollout(
+            C.byref(p), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y), _lib.ptr(actions),
+            _lib.ptr(moves), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(o["R_"]),
+            _lib.ptr(o["modR_"]), _lib.ptr(o["C_"]), _lib.ptr(o["G_"]), _lib.ptr(o["gs_"]),
+            _lib.ptr(o["stats_vec"]), _lib.ptr(o["stats_scratch"]), E, self.ld, _lib.stream_ptr()))
+        self.t = T
+        return self._rollout_result(o)

@@ -8,8 +8,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..layout import env_major
-from ..rollout import G_NONE, G_REWARD_TO_GO, Stats, make_accounting
+from ..rollout import G_NONE, make_accounting
 from .base import BatchedEnv
 
 
@@ -118,26 +117,12 @@ class BatchedCoverageDiscrete(BatchedEnv):
         T = int(actions.shape[0])
         A, E, dev = self.n_agents, self.n_envs, self.device
         assert actions.dtype == torch.uint8 and tuple(actions.shape) == (T, A, self.ld) and actions.is_contiguous()
-        o = out if out is not None else {}
-        def buf(name, rows, dtype, lead=()):
-            if name not in o:
-                o[name] = self._alloc(rows, dtype, lead)
-            return o[name]
-        R, modR = buf("R_", A, torch.float32), buf("modR_", A, torch.float32)
-        Csum = buf("C_", A, torch.int32)
-        G = buf("G_", A, torch.float32, (T,)) if g_mode != G_NONE else None
-        gs = buf("g_scratch", 1, torch.float32, (2 * T,)) if g_mode == G_REWARD_TO_GO else None
-        if "stats_vec" not in o:
-            o["stats_vec"] = torch.zeros(self.lib.smarl_stats_len(A, A), dtype=torch.float64, device=dev)
-            o["stats_scratch"] = torch.zeros(self.lib.smarl_stats_scratch_len(A, A, E), dtype=torch.float64,
-                                             device=dev)
+        o = self._rollout_outputs(T, g_mode, out, 2 * T)
         thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
         acc = make_accounting(gamma, T, g_mode, thr)
         _lib.check(self.lib.smarl_coverage_rollout(
             C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),
-            _lib.ptr(actions), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(R),
-            _lib.ptr(modR), _lib.ptr(Csum), _lib.ptr(G), _lib.ptr(gs), _lib.ptr(o["stats_vec"]),
-            _lib.ptr(o["stats_scratch"]), E, self.ld, _lib.stream_ptr()))
-        o.update(R=env_major(R, E), modR=env_major(modR, E), C=env_major(Csum, E),
-                 G=None if G is None else env_major(G, E), stats=Stats(o["stats_vec"], A, A))
-        return o
+            _lib.ptr(actions), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(o["R_"]),
+            _lib.ptr(o["modR_"]), _lib.ptr(o["C_"]), _lib.ptr(o["G_"]), _lib.ptr(o["gs_"]),
+            _lib.ptr(o["stats_vec"]), _lib.ptr(o["stats_scratch"]), E, self.ld, _lib.stream_ptr()))
+        return self._rollout_result(o)

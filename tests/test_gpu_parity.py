@@ -297,3 +297,85 @@ def test_lambda_update_and_meta_agent():
     want = no.lambda_update([0.2] * 3, np.array([30.0, 20.0, 1.0]), [25, 25, 25], 0.05)
     np.testing.assert_allclose(meta.lambdas.cpu().numpy(), want, rtol=1e-15)
     assert meta.learning_cycle == 0
+
+
+# ----------------------------------------------------------------------------- fused rollouts (Congestion, Collision)
+def kernel_layout(a, ld):
+    """[T, E, rows] numpy -> [T, rows, ld] device tensor."""
+    T, E, R = a.shape
+    out = torch.zeros(T, R, ld, dtype=torch.as_tensor(a).dtype, device="cuda")
+    out[:, :, :E] = torch.as_tensor(a, device="cuda").permute(0, 2, 1)
+    return out
+
+
+def check_products(out, want, want_G, thr, E, scale, exact_C=True):
+    assert np.array_equal(out["C"].cpu().numpy(), want["C"].astype(np.int64))
+    close(out["R"].cpu().numpy(), want["R"], scale)
+    close(out["modR"].cpu().numpy(), want["modR"], scale)
+    if want_G is not None:
+        close(out["G"].cpu().numpy(), want_G, scale)
+    st = out["stats"]
+    assert np.array_equal(st.cost_sum.cpu().numpy(), want["C"].sum(0))
+    assert np.array_equal(st.violations.cpu().numpy(), (want["C"] > np.asarray(thr)[None]).sum(0))
+    close(st.return_sum.cpu().numpy(), want["R"].sum(0), scale * E)
+    close(st.modified_return_sum.cpu().numpy(), want["modR"].sum(0), scale * E)
+    assert float(st.count) == E
+
+
+@pytest.mark.parametrize("size,A,E,T,noise,seed", CONGESTION_CASES + [(10, 8, 700, 100, 0.1, 6), (4, 16, 90, 12, 0.2, 7)])
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", ["philox", "recorded"])
+def test_congestion_fused_rollout(size, A, E, T, noise, seed, g_mode, mode):
+    s = smarl()
+    demand, starts, actions = congestion_setup(size, A, E, T, seed)
+    gamma, lam_np, thr = 0.9, np.array([0.35]), np.array([0.3 * T])
+    offset = 77 + seed
+    env = s.BatchedCongestion(size, A, n_envs=E, noise=noise, starts=starts, demand_rate=demand, seed=5 + seed,
+                              env_offset=offset)
+    ids = np.arange(offset, offset + E)
+    pos = starts.copy()
+    all_moves = []
+
+    def step_fn(t):
+        nonlocal pos
+        u1, u2 = philox.congestion_uniforms(5 + seed, ids, t, A)
+        moves = no.congestion_noise_moves(actions[t], u1, u2, noise)
+        all_moves.append(moves)
+        pos, r, c, _, _ = no.congestion_step(pos, actions[t], moves, size, demand)
+        return r.astype(np.float32).astype(np.float64), c          # rewards are published as f32
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    want_G = {0: None, 1: want["G"], 2: no.discounted_terms(want["mod_reward"], gamma)}[g_mode]
+    scale = np.max(np.abs(want["modR"]))
+    lam = torch.as_tensor(lam_np, device="cuda")
+    act_k = kernel_layout(actions.astype(np.uint8), env.ld)
+    mv_k = kernel_layout(np.stack(all_moves).astype(np.uint8), env.ld) if mode == "recorded" else None
+    out = env.rollout(act_k, lambdas=lam, gamma=gamma, thresholds=thr, g_mode=g_mode, moves=mv_k)
+    assert np.array_equal(env.state().cpu().numpy(), pos)
+    check_products(out, want, want_G, thr, E, scale)
+
+
+@pytest.mark.parametrize("size,A,L,E,T,seed", COLLISION_CASES)
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+def test_collision_fused_rollout(size, A, L, E, T, seed, g_mode):
+    s = smarl()
+    starts, landmarks, actions = collision_setup(size, A, L, E, T, seed)
+    gamma, lam_np, thr = 0.99, np.array([0.5]), np.array([1.0])
+    env = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=L, starts=starts, landmarks=landmarks)
+    pos, done = starts.copy(), np.zeros((E, A), dtype=bool)
+    n_active = np.zeros(E, dtype=np.int64)
+
+    def step_fn(t):
+        nonlocal pos, done, n_active
+        pos, r, c, done, active = no.collision_step(pos, done, actions[t].astype(np.float64), landmarks, size)
+        n_active += active
+        return r.astype(np.float32).astype(np.float64), c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    want_G = {0: None, 1: want["G"], 2: no.discounted_terms(want["mod_reward"], gamma)}[g_mode]
+    scale = np.max(np.abs(want["modR"]))
+    lam = torch.as_tensor(lam_np, device="cuda")
+    act_k = kernel_layout(actions.reshape(T, E, 2 * A), env.ld)
+    out = env.rollout(act_k, lambdas=lam, gamma=gamma, thresholds=thr, g_mode=g_mode)
+    assert np.array_equal(env.state().cpu().numpy(), pos)                           # bit-exact f64 final positions
+    assert np.array_equal(env.agent_done[:, :E].t().cpu().numpy().astype(bool), done)
+    assert np.array_equal(out["n_active"].cpu().numpy(), n_active)
+    check_products(out, want, want_G, thr, E, scale)
