@@ -23,7 +23,8 @@
  *    from different host threads / streams.
  *  - Return value: SMARL_OK or a negative error; smarl_last_error() gives a
  *    thread-local message.  There is no CPU fallback.
- *  - n_agents is limited to 1..32, grid size to 1..254 (coordinates are uint8).
+ *  - n_agents is limited to 1..32; grid size to 1..127 (Coverage: doubled uint8 coordinates
+ *    index the penalty table) and 1..254 (Congestion); per call (2*n_agents+1)*ld < 2^32.
  */
 #ifndef SMARL_H_
 #define SMARL_H_

@@ -82,56 +82,68 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
   coverage_load_lut(s_lut, a.lut, a.lut_len);
   const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
   if (g >= a.n_groups) return;
-  const int64_t e0 = g * 4;
-  const int64_t ld = a.ld;
+  // 32-bit element offsets (host checks (2A+1) * ld < 2^32): one add per row, one wide add per access
+  const uint32_t ld = (uint32_t)a.ld;
+  const uint32_t e0 = (uint32_t)g * 4u;
 
   uint32_t xw[A], yw[A], aw[A];
+  {
+    uint32_t off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i) {
-    xw[i] = ld_stream_u32(a.pos_x + i * ld + e0);
-    yw[i] = ld_stream_u32(a.pos_y + i * ld + e0);
-    aw[i] = ld_stream_u32(a.actions + i * ld + e0);
+    for (int i = 0; i < A; ++i, off += ld) {
+      xw[i] = ld_stream_u32(a.pos_x + off);
+      yw[i] = ld_stream_u32(a.pos_y + off);
+      aw[i] = ld_stream_u32(a.actions + off);
+    }
   }
   const uint32_t size4 = (uint32_t)a.size * 0x01010101u;
   double pen[4] = {0.0, 0.0, 0.0, 0.0};
+  {
+    uint32_t off = e0, obs_off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i) {
-    grid_move4(xw[i], yw[i], aw[i], size4);              // coverage.py:174-189
-    const uint32_t cw = move_cost4(aw[i]);               // coverage.py:191-196
-    st_stream_u32(a.pos_x + i * ld + e0, xw[i]);
-    st_stream_u32(a.pos_y + i * ld + e0, yw[i]);
-    st_stream_u32(a.cost + i * ld + e0, cw);
-    if (a.done) st_stream_u32(a.done + i * ld + e0, 0u);  // coverage.py:97-98
-    if (a.obs) {
-      st_stream_f4(a.obs + (2 * i) * ld + e0, bytes_to_float4(xw[i]));
-      st_stream_f4(a.obs + (2 * i + 1) * ld + e0, bytes_to_float4(yw[i]));
-    }
-    if (a.penalty) {                                       // meta_agent.py:21-22
-      const double lam = __ldg(a.lambdas + i);
+    for (int i = 0; i < A; ++i, off += ld, obs_off += 2u * ld) {
+      grid_move4(xw[i], yw[i], aw[i], size4);              // coverage.py:174-189
+      const uint32_t cw = move_cost4(aw[i]);               // coverage.py:191-196
+      st_stream_u32(a.pos_x + off, xw[i]);
+      st_stream_u32(a.pos_y + off, yw[i]);
+      st_stream_u32(a.cost + off, cw);
+      if (a.done) st_stream_u32(a.done + off, 0u);         // coverage.py:97-98
+      if (a.obs) {
+        st_stream_f4(a.obs + obs_off, bytes_to_float4(xw[i]));
+        st_stream_f4(a.obs + (obs_off + ld), bytes_to_float4(yw[i]));
+      }
+      if (a.penalty) {                                      // meta_agent.py:21-22
+        const double lam = __ldg(a.lambdas + i);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pen[k] += ((cw >> (8 * k)) & 1u) ? lam : 0.0;
+        for (int k = 0; k < 4; ++k)
+          if ((cw >> (8 * k)) & 1u) pen[k] += lam;
+      }
     }
   }
   if (a.penalty)
     st_stream_f4(a.penalty + e0, make_float4((float)pen[0], (float)pen[1], (float)pen[2], (float)pen[3]));
 
   float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+  const uint32_t lut_bytes = (uint32_t)a.lut_len * 4u;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const uint32_t sel = (uint32_t)k | ((uint32_t)(k + 4) << 4);
+    const uint32_t sel = coverage_pack_sel(k);
     uint32_t p[A];
 #pragma unroll
-    for (int i = 0; i < A; ++i) p[i] = __byte_perm(xw[i], yw[i], sel) & 0xFFFFu;
-    const float r = -coverage_pair_penalty<A>(p, s_lut, (uint32_t)a.lut_len);   // coverage.py:79-83
+    for (int i = 0; i < A; ++i) p[i] = coverage_pack2(xw[i], yw[i], sel);
+    const float r = -coverage_pair_penalty<A>(p, s_lut, lut_bytes);              // coverage.py:79-83
     r0 = k == 0 ? r : r0;
     r1 = k == 1 ? r : r1;
     r2 = k == 2 ? r : r2;
     r3 = k == 3 ? r : r3;
   }
+  {
+    uint32_t off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i) {
-    const float w = a.weights ? __ldg(a.weights + i) : 1.0f;                     // coverage.py:86-87
-    st_stream_f4(a.reward + i * ld + e0, make_float4(r0 * w, r1 * w, r2 * w, r3 * w));
+    for (int i = 0; i < A; ++i, off += ld) {
+      const float w = a.weights ? __ldg(a.weights + i) : 1.0f;                   // coverage.py:86-87
+      st_stream_f4(a.reward + off, make_float4(r0 * w, r1 * w, r2 * w, r3 * w));
+    }
   }
 }
 
@@ -168,10 +180,13 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
   double disc = 1.0;
 
   for (int t = 0; t < T; ++t) {
-    const uint8_t* act_t = a.actions + (int64_t)t * A * ld + e0;
+    const uint8_t* act_t = a.actions + (int64_t)t * A * ld;          // uniform; per-thread offsets stay 32-bit
     uint32_t aw[A];
+    {
+      uint32_t off = (uint32_t)e0;
 #pragma unroll
-    for (int i = 0; i < A; ++i) aw[i] = ld_stream_u32(act_t + i * ld);
+      for (int i = 0; i < A; ++i, off += (uint32_t)ld) aw[i] = ld_stream_u32(act_t + off);
+    }
     double pen[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < A; ++i) {
@@ -179,16 +194,17 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
       const uint32_t cw = move_cost4(aw[i]);
       cnt[i] += cw;                                   // four byte counters, T <= 255
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pen[k] += ((cw >> (8 * k)) & 1u) ? lam[i] : 0.0;
+      for (int k = 0; k < 4; ++k)
+        if ((cw >> (8 * k)) & 1u) pen[k] += lam[i];
     }
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-      const uint32_t sel = (uint32_t)k | ((uint32_t)(k + 4) << 4);
+      const uint32_t sel = coverage_pack_sel(k);
       uint32_t p[A];
 #pragma unroll
-      for (int i = 0; i < A; ++i) p[i] = __byte_perm(xw[i], yw[i], sel) & 0xFFFFu;
-      const float r = -coverage_pair_penalty<A>(p, s_lut, (uint32_t)a.lut_len);
+      for (int i = 0; i < A; ++i) p[i] = coverage_pack2(xw[i], yw[i], sel);
+      const float r = -coverage_pair_penalty<A>(p, s_lut, (uint32_t)a.lut_len * 4u);
       r0 = k == 0 ? r : r0;
       r1 = k == 1 ? r : r1;
       r2 = k == 2 ? r : r2;
@@ -327,7 +343,7 @@ __global__ void grid_reset_kernel(const uint8_t* __restrict__ start_x, const uin
 // ---------------------------------------------------------------------------------------
 static int check_coverage(const SmarlCoverageParams* p) {
   SMARL_REQUIRE(p != nullptr, "params is NULL");
-  SMARL_REQUIRE(p->size >= 1 && p->size <= 254, "size=%d outside 1..254", p->size);
+  SMARL_REQUIRE(p->size >= 1 && p->size <= 127, "size=%d outside 1..127", p->size);
   SMARL_REQUIRE(p->lut_len >= 0 && (p->lut_len == 0 || p->lut != nullptr), "bad penalty table");
   if (p->lut_len > kCoverageMaxLut) {
     set_error("lut_len=%d exceeds the shared-memory table limit %d", p->lut_len, kCoverageMaxLut);
@@ -375,6 +391,10 @@ extern "C" int smarl_coverage_step(const SmarlCoverageParams* p, uint8_t* pos_x,
   a.cost = cost; a.done = done; a.lambdas = lambdas; a.penalty = penalty;
   a.lut = p->lut; a.weights = p->weights;
   a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.lut_len = p->lut_len;
+  if ((int64_t)(2 * p->n_agents + 1) * ld >= (1ll << 32)) {
+    set_error("(2A+1)*ld = %lld exceeds 32-bit element offsets; split the env batch", (long long)((2 * p->n_agents + 1) * ld));
+    return SMARL_EUNSUPPORTED;
+  }
   const unsigned grid = (unsigned)((a.n_groups + kStepThreads - 1) / kStepThreads);
   if (int rc = launch_coverage_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;

@@ -4,31 +4,47 @@
 
 namespace smarl {
 
-// Largest penalty table kept in shared memory (entries).  fv^2 <= this, i.e. fieldview <= 110.
+// Coverage grids are limited to size <= 127 so that doubled coordinates fit a byte (see
+// coverage_pack2).  Largest penalty table kept in shared memory (entries): fv^2 <= this.
 constexpr int kCoverageMaxLut = 12287;
 
-// Sum of pair penalties of ONE env whose agents are packed as p[a] = x | y << 8.
+// Agents of env lane k packed for the pair loop: p[a] = (2x | 2y << 8), upper bytes zero.
+// One PRMT gathers (x_k, y_k) and zero-fills bytes 2,3 by replicating the (clear) sign bit of
+// x_k -- coordinates are <= 127 -- and one add doubles both bytes without carry.
+__device__ __forceinline__ uint32_t coverage_pack2(uint32_t xw, uint32_t yw, uint32_t sel) {
+  uint32_t p;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(p) : "r"(xw), "r"(yw), "r"(sel));
+  return p + p;
+}
+// selector for env lane k: byte0 = x.b[k], byte1 = y.b[k], byte2 = byte3 = sign(x.b[k]) = 0
+__device__ __forceinline__ uint32_t coverage_pack_sel(int k) {
+  return (uint32_t)k | ((uint32_t)(k + 4) << 4) | ((uint32_t)(8 + k) << 8) | ((uint32_t)(8 + k) << 12);
+}
+
+// Sum of pair penalties of ONE env whose agents are packed by coverage_pack2.
 //
 // Replaces the i<j double loop over scipy's distance_matrix in CoverageContinuous.reward
 // (envs/coverage.py:76-83).  For integer coordinates the distance is sqrt(q) with
-// q = dx^2 + dy^2 an integer, so the penalty is a table lookup: |dx|,|dy| for the pair come
-// from one SIMD byte abs-diff, q from one dp4a, and q is clamped to lut_len, whose entry is 0.
+// q = dx^2 + dy^2 an integer, so the penalty is a table lookup: 2|dx|, 2|dy| for the pair come
+// from one SIMD byte abs-diff (VABSDIFF4), 4q -- already the byte offset into the f32 table --
+// from one dp4a (IDP.4A), clamped (VIMNMX) to the table's trailing zero entry, then LDS + FADD.
 // Canonical summation order (every kernel that produces rewards uses this function, so
 // step-mode and fused-mode rewards are bit-identical): pair n in the reference's i-major
 // order goes to accumulator n % 4, result = (acc0 + acc1) + (acc2 + acc3), all f32.
 template <int A>
 __device__ __forceinline__ float coverage_pair_penalty(const uint32_t (&p)[A],
                                                        const float* __restrict__ s_lut,
-                                                       uint32_t lut_len) {
+                                                       uint32_t lut_bytes) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int n = 0;
+  const char* base = reinterpret_cast<const char*>(s_lut);
 #pragma unroll
   for (int i = 0; i < A; ++i) {
 #pragma unroll
     for (int j = i + 1; j < A; ++j) {
       const uint32_t v = __vabsdiffu4(p[i], p[j]);
-      const uint32_t q = min(__dp4a(v, v, 0u), lut_len);
-      acc[n & 3] += s_lut[q];
+      const uint32_t off = min(__dp4a(v, v, 0u), lut_bytes);
+      acc[n & 3] += *reinterpret_cast<const float*>(base + off);
       ++n;
     }
   }

@@ -47,8 +47,8 @@ class BatchedCoverageDiscrete(BatchedEnv):
     def __init__(self, size, n_agents, n_envs=1, shuffle=False, agents_size=0.5, fieldview_size=None,
                  weights=None, device="cuda", starts=None, env_offset=0):
         self._init_common(size, n_agents, n_envs, device, env_offset)
-        if not (1 <= self.size <= 254):
-            raise ValueError("size must be in 1..254 (uint8 coordinates)")
+        if not (1 <= self.size <= 127):
+            raise ValueError("size must be in 1..127 (doubled uint8 coordinates index the penalty table)")
         if shuffle:
             raise NotImplementedError("shuffle=True (per-episode re-randomised starts) is not built yet")
         self.shuffle = False

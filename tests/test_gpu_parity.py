@@ -36,7 +36,7 @@ COVERAGE_CASES = [
     (64, 32, 130, 4, None, 3),        # maximum agents
     (3, 2, 17, 30, 10.0, 4),          # field of view larger than the grid: every pair overlaps
     (5, 1, 40, 5, None, 5),           # single agent: no pairs
-    (254, 4, 64, 6, 40.0, 6),         # maximum grid size
+    (127, 4, 64, 6, 40.0, 6),         # maximum grid size
 ]
 
 
