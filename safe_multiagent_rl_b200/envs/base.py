@@ -22,6 +22,10 @@ class BatchedEnv:
             raise ValueError("n_agents must be in 1..32")
         self.size, self.n_agents, self.n_envs = int(size), int(n_agents), int(n_envs)
         self.device = require_cuda(device)
+        if self.device.index != torch.cuda.current_device():
+            # libsmarl launches on the current device; one process drives one GPU (torchrun model)
+            raise ValueError(f"env device {self.device} is not the current CUDA device; call "
+                             "torch.cuda.set_device() first")
         self.ld = pad_ld(self.n_envs)
         self.env_offset = int(env_offset)       # global id of env 0 when sharded over GPUs
         self.lib = _lib.load()
@@ -35,10 +39,13 @@ class BatchedEnv:
         """Return an ``[action_rows, ld]`` device tensor in the kernel layout (zero-copy when the
         caller already hands one over, e.g. ``env.action_buffer`` filled by the policies)."""
         rows = self.action_rows
-        if isinstance(actions, torch.Tensor) and actions.device == self.device and \
-                actions.dtype == self.action_dtype and tuple(actions.shape) == (rows, self.ld) and \
-                actions.is_contiguous():
-            return actions
+        kernel_shape = isinstance(actions, torch.Tensor) and tuple(actions.shape) == (rows, self.ld)
+        if kernel_shape and (agent_major or (rows, self.ld) != (self.n_envs, rows)):
+            # already in the kernel layout (unambiguous shape, or the caller said so): zero-copy
+            if actions.device == self.device and actions.dtype == self.action_dtype and actions.is_contiguous():
+                return actions
+            self.action_buffer.copy_(actions)
+            return self.action_buffer
         a = torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
         a = a.to(self.device)
         if not agent_major:                                   # reference orientation: [E, A(, 2)]

@@ -28,4 +28,6 @@ def require_cuda(device) -> torch.device:
         raise RuntimeError("safe_multiagent_rl_b200 runs on CUDA devices only (there is no CPU fallback)")
     if not torch.cuda.is_available():
         raise RuntimeError("no CUDA device available (there is no CPU fallback)")
+    if device.index is None:                      # normalise "cuda" -> "cuda:<current>" so tensor.device compares equal
+        device = torch.device("cuda", torch.cuda.current_device())
     return device

@@ -379,3 +379,26 @@ def test_collision_fused_rollout(size, A, L, E, T, seed, g_mode):
     assert np.array_equal(env.agent_done[:, :E].t().cpu().numpy().astype(bool), done)
     assert np.array_equal(out["n_active"].cpu().numpy(), n_active)
     check_products(out, want, want_G, thr, E, scale)
+
+
+def test_step_accepts_kernel_layout_and_env_major_actions():
+    """env.step takes actions as [E, A] (reference orientation) or as the [A, ld] kernel layout
+    (zero-copy); both must give the same transition."""
+    s = smarl()
+    rng = np.random.default_rng(0)
+    E, A, S = 100, 5, 9
+    starts = rng.integers(0, S, size=(E, A, 2))
+    act = rng.integers(0, 5, size=(E, A)).astype(np.uint8)
+    e1 = s.BatchedCoverageDiscrete(S, A, n_envs=E, starts=starts)
+    e2 = s.BatchedCoverageDiscrete(S, A, n_envs=E, starts=starts)
+    e3 = s.BatchedCoverageDiscrete(S, A, n_envs=E, starts=starts)
+    for e in (e1, e2, e3):
+        e.reset()
+    e1.step(act)
+    k = torch.zeros(A, e2.ld, dtype=torch.uint8, device="cuda")
+    k[:, :E] = torch.as_tensor(act, device="cuda").t()
+    e2.step(k)                                           # auto-detected kernel layout
+    e3.action_buffer.copy_(k)
+    e3.step(e3.action_buffer, agent_major=True)          # policies writing the env's own buffer
+    assert torch.equal(e1.state(), e2.state()) and torch.equal(e1.state(), e3.state())
+    assert torch.equal(e1.reward, e2.reward) and torch.equal(e1.reward, e3.reward)
