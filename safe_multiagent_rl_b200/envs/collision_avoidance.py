@@ -10,7 +10,7 @@ import torch
 
 from .. import _lib
 from ..layout import env_major
-from ..rollout import G_NONE, make_accounting
+from ..rollout import G_NONE, device_thresholds, make_accounting
 from .base import BatchedEnv
 
 
@@ -97,7 +97,7 @@ class BatchedCollisionAvoidance(BatchedEnv):
         o = self._rollout_outputs(T, g_mode, out, 2 * T)
         if "n_active_" not in o:
             o["n_active_"] = self._alloc(1, torch.int32)
-        thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
+        thr = device_thresholds(thresholds, dev)
         acc = make_accounting(gamma, T, g_mode, thr)
         _lib.check(self.lib.smarl_collision_rollout(
             C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..rollout import G_NONE, make_accounting
+from ..rollout import G_NONE, device_thresholds, make_accounting
 from .base import BatchedEnv
 
 # congestion.py:28 -- the reference's hard-coded table (only valid for size <= 3)
@@ -133,7 +133,7 @@ class BatchedCongestion(BatchedEnv):
             assert moves.dtype == torch.uint8 and tuple(moves.shape) == (T, A, self.ld) and moves.is_contiguous()
         mode = NOISE_RECORDED if moves is not None else (NOISE_PHILOX if self.noise > 0 else NOISE_NONE)
         o = self._rollout_outputs(T, g_mode, out, T)
-        thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
+        thr = device_thresholds(thresholds, dev)
         acc = make_accounting(gamma, T, g_mode, thr)
         p = self._params(mode)
         _lib.check(self.lib.smarl_congestion_rollout(

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..rollout import G_NONE, make_accounting
+from ..rollout import G_NONE, device_thresholds, make_accounting
 from .base import BatchedEnv
 
 
@@ -118,7 +118,7 @@ class BatchedCoverageDiscrete(BatchedEnv):
         A, E, dev = self.n_agents, self.n_envs, self.device
         assert actions.dtype == torch.uint8 and tuple(actions.shape) == (T, A, self.ld) and actions.is_contiguous()
         o = self._rollout_outputs(T, g_mode, out, 2 * T)
-        thr = None if thresholds is None else torch.as_tensor(thresholds, dtype=torch.float64, device=dev)
+        thr = device_thresholds(thresholds, dev)
         acc = make_accounting(gamma, T, g_mode, thr)
         _lib.check(self.lib.smarl_coverage_rollout(
             C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),

@@ -45,6 +45,23 @@ class Stats:
         return self.vec[2 * self.K + 2 * self.A]
 
 
+_THR_CACHE = {}
+
+
+def device_thresholds(thresholds, device):
+    """f64 device tensor for a thresholds list; cached by value so repeated calls (and calls made
+    while a CUDA graph is being captured, after one warm-up call) do no host->device copy."""
+    if thresholds is None:
+        return None
+    if isinstance(thresholds, torch.Tensor) and thresholds.is_cuda and thresholds.dtype == torch.float64:
+        return thresholds
+    key = (str(device), tuple(float(x) for x in np.asarray(
+        thresholds.detach().cpu() if isinstance(thresholds, torch.Tensor) else thresholds, dtype=np.float64).ravel()))
+    if key not in _THR_CACHE:
+        _THR_CACHE[key] = torch.tensor(key[1], dtype=torch.float64, device=device)
+    return _THR_CACHE[key]
+
+
 def make_accounting(gamma, n_steps, g_mode, thresholds_dev):
     return _lib.Accounting(float(gamma), int(n_steps), int(g_mode), _lib.ptr(thresholds_dev))
 
@@ -91,9 +108,7 @@ class RolloutBuffer:
         g_mode = self.g_mode if g_mode is None else g_mode
         if g_mode != G_NONE and self.G is None:
             raise ValueError("buffer was created without G storage")
-        thr = None
-        if thresholds is not None:
-            thr = torch.as_tensor(thresholds, dtype=torch.float64, device=self.device).contiguous()
+        thr = device_thresholds(thresholds, self.device)
         acc = make_accounting(gamma, self.T, g_mode, thr)
         _lib.check(lib.smarl_rollout_returns(
             C.byref(acc), _lib.ptr(self.reward), _lib.ptr(self.cost), self.cost_code, _lib.ptr(self.penalty),

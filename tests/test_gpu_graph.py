@@ -1,0 +1,56 @@
+"""The step / returns / rollout calls are CUDA-graph capturable (no syncs, no allocations once the
+buffers exist): a whole closed-loop batch of episodes replays from one graph with identical results.
+This is how launch-bound small batches (BASELINE config 1: 50 envs) are driven."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("env_name", ["coverage", "congestion", "collision"])
+def test_closed_loop_in_one_cuda_graph(env_name):
+    import safe_multiagent_rl_b200 as s
+    rng = np.random.default_rng(0)
+    E, T = 50, 50
+    if env_name == "coverage":
+        A = 3
+        env = s.BatchedCoverageDiscrete(5, A, n_envs=E, weights=[1.0, 2.0, 3.0], starts=rng.integers(0, 5, (E, A, 2)))
+        actions = torch.as_tensor(rng.integers(0, 5, (T, A, env.ld)).astype(np.uint8), device="cuda")
+        K = A
+    elif env_name == "congestion":
+        A = 8
+        st = rng.integers(0, 10, (E, A, 2)); st[:, 0] = 0
+        env = s.BatchedCongestion(10, A, n_envs=E, noise=0.1, starts=st, demand_rate=rng.random((11, 11)) * 8 + 2, seed=4)
+        actions = torch.as_tensor(rng.integers(0, 5, (T, A, env.ld)).astype(np.uint8), device="cuda")
+        K = 1
+    else:
+        A = 3
+        env = s.BatchedCollisionAvoidance(5, A, n_envs=E, starts=rng.random((E, A, 2)) * 5, landmarks=rng.random((E, 1, 2)) * 5)
+        actions = torch.as_tensor(rng.normal(0, 0.5, (T, 2 * A, env.ld)).astype(np.float32), device="cuda")
+        K = 1
+    lam = torch.full((K,), 0.2, dtype=torch.float64, device="cuda")
+    buf = env.new_rollout_buffer(T)
+    thr = [20.0] * K
+
+    def closed():
+        env.reset()
+        for t in range(T):
+            env.step(actions[t], lambdas=lam, out=(buf, t), agent_major=True)
+        return buf.finish(0.99, thr)
+    eager = closed()
+    want = {k: eager[k].clone() for k in ("R", "modR", "C", "G")}
+    want_pos = env.state().clone()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        closed()
+    for buf_t in (buf.R, buf.modR, buf.Csum, buf.G, env.pos_x, env.pos_y):
+        buf_t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    got = dict(R=buf.R, modR=buf.modR, C=buf.Csum, G=buf.G)
+    for k in want:
+        g = got[k][..., :E].transpose(-1, -2)
+        assert torch.equal(g, want[k]), k
+    assert torch.equal(env.state(), want_pos)

@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Throughput sweep over BASELINE.json configs[0..4] shapes (all three envs, grid 5-64, agents 3-32,
+envs 1K-4M) on one GPU: closed-loop (T step launches + returns kernel, captured in ONE CUDA graph so
+small batches are not launch-bound) and fused open-loop rollout.  Prints a markdown table.
+
+    python tools/sweep.py [--quick] > profiles/rNN/sweep.md
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import safe_multiagent_rl_b200 as s  # noqa: E402
+
+PEAK = 6551.0
+
+
+def make(env_name, S, A, E, g):
+    dev = "cuda"
+    if env_name == "coverage":
+        env = s.BatchedCoverageDiscrete(S, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)],
+                                        starts=np.zeros((E, A, 2), np.uint8))
+        env.start_x[:, :E] = torch.randint(0, S, (A, E), generator=g, device=dev, dtype=torch.uint8)
+        env.start_y[:, :E] = torch.randint(0, S, (A, E), generator=g, device=dev, dtype=torch.uint8)
+        K, bytes_step = A, 19.0 + 4.0 / A
+    elif env_name == "congestion":
+        rng = np.random.default_rng(0)
+        env = s.BatchedCongestion(S, A, n_envs=E, noise=0.1, starts=np.zeros((E, A, 2), np.uint8),
+                                  demand_rate=rng.random((S + 1, S + 1)) * 8 + 2, seed=1)
+        env.start_x[1:, :E] = torch.randint(0, S, (A - 1, E), generator=g, device=dev, dtype=torch.uint8)
+        env.start_y[1:, :E] = torch.randint(0, S, (A - 1, E), generator=g, device=dev, dtype=torch.uint8)
+        K, bytes_step = 1, 19.0 + 8.0 / A            # incl. the effective-move row the step kernel publishes
+    else:
+        rng = np.random.default_rng(0)
+        env = s.BatchedCollisionAvoidance(S, A, n_envs=E, starts=np.zeros((E, A, 2)), landmarks=np.zeros((E, 1, 2)))
+        env.start_x[:, :E] = torch.rand((A, E), generator=g, device=dev, dtype=torch.float64) * S
+        env.start_y[:, :E] = torch.rand((A, E), generator=g, device=dev, dtype=torch.float64) * S
+        env.landmarks[:, :E] = torch.rand((2, E), generator=g, device=dev, dtype=torch.float64) * S
+        K, bytes_step = 1, 55.0 + 24.0 / A
+    return env, K, bytes_step
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def run(env_name, S, A, E, T):
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    env, K, bytes_step = make(env_name, S, A, E, g)
+    if env_name == "collision":
+        actions = torch.randn((T, 2 * A, env.ld), generator=g, device="cuda") * 0.5
+    else:
+        actions = torch.randint(0, 5, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
+    lam = torch.full((K,), 0.1, dtype=torch.float64, device="cuda")
+    buf = env.new_rollout_buffer(T)
+    gamma, thr = 0.99, [25.0] * K
+
+    def closed():
+        env.reset()
+        for t in range(T):
+            env.step(actions[t], lambdas=lam, out=(buf, t), agent_major=True)
+        buf.finish(gamma, thr)
+    closed()                                     # warm-up outside capture (allocations, module load)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        closed()
+    iters = max(3, min(50, int(2e9 / (E * A * T)) + 3))
+    ms_closed = timed(graph.replay, iters)
+    out = {}
+    ms_fused = timed(lambda: env.rollout(actions, lambdas=lam, gamma=gamma, thresholds=thr, out=out), iters)
+    n = float(E) * A * T
+    return dict(env=env_name, S=S, A=A, E=E, T=T, closed=n / ms_closed * 1e3, fused=n / ms_fused * 1e3,
+                ms_closed=ms_closed, ms_fused=ms_fused,
+                closed_gbs=(bytes_step + 9.3) * n / ms_closed / 1e6)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    cfgs = [("coverage", 5, 3, 50, 50),            # configs[0]
+            ("collision", 5, 3, 65536, 50),        # configs[1]
+            ("congestion", 10, 8, 1 << 20, 100),   # configs[2]
+            ("coverage", 32, 16, 1 << 22, 50)]     # configs[3] per GPU
+    if not a.quick:                                  # configs[4]: sweep
+        for env_name in ("coverage", "congestion", "collision"):
+            for S, A in [(5, 3), (8, 4), (16, 8), (32, 16), (64, 32)]:
+                for E in [1 << 10, 1 << 13, 1 << 16, 1 << 20, 1 << 22]:
+                    if env_name == "collision" and E * A > (1 << 25):
+                        continue
+                    if E * A * 50 > 4e9:
+                        continue
+                    cfgs.append((env_name, S, A, E, 50))
+    print("| env | size | agents | envs | T | closed-loop agent-steps/s (CUDA graph) | ms | fused agent-steps/s | ms |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for c in cfgs:
+        r = run(*c)
+        print(f"| {r['env']} | {r['S']} | {r['A']} | {r['E']} | {r['T']} | {r['closed']:.3g} | {r['ms_closed']:.3f} | "
+              f"{r['fused']:.3g} | {r['ms_fused']:.3f} |", flush=True)
+        torch.cuda.empty_cache()
