@@ -96,14 +96,18 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
     const double lx = lm[(2 * l) * ld], ly = lm[(2 * l + 1) * ld];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
+      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2); (lx-px) == -(px-lx) exactly
       const double ax = __dadd_rn(px[i], -lx), ay = __dadd_rn(py[i], -ly);
-      // np.linalg.norm(state - land) = sqrt(ddot) = sqrt(fma(ay, ay, ax*ax))   [probed, OpenBLAS]
-      const double nrm = __dsqrt_rn(__fma_rn(ay, ay, __dmul_rn(ax, ax)));
-      reach |= (nrm < agents_size) ? (1u << i) : 0u;
-      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2)
-      const double bx = __dadd_rn(lx, -px[i]), by = __dadd_rn(ly, -py[i]);
-      const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)));
+      const double ax2 = __dmul_rn(ax, ax);
+      const double d = __dsqrt_rn(__dadd_rn(ax2, __dmul_rn(ay, ay)));
       mind[i] = fmin(mind[i], d);
+      // landmark reach uses np.linalg.norm(state - land) = sqrt(ddot) = sqrt(fma(ay, ay, ax*ax))
+      // [probed, OpenBLAS]: it differs from d by at most an ulp or two, so the fused form is only
+      // evaluated when d is within 1e-9 (relative) of the radius.
+      bool hit = d < agents_size;
+      if (fabs(d - agents_size) <= 1e-9 * agents_size)
+        hit = __dsqrt_rn(__fma_rn(ay, ay, ax2)) < agents_size;
+      reach |= hit ? (1u << i) : 0u;
     }
   }
   done_mask |= reach & ~done_mask;   // only agents that moved this step are tested; done ones stay done
