@@ -123,6 +123,40 @@ int smarl_coverage_rollout(const SmarlCoverageParams* p, const SmarlAccounting* 
                            int64_t n_envs, int64_t ld, smarl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * CoverageContinuous / CoverageDiscretized (float64 positions; the "ExploreContinuous" family the
+ * paper's launchers use, experiments_run/AC_explore_constr_1.bat)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t size;           /* positions clamp to [0,size]                       coverage.py:70-71    */
+  int32_t n_agents;       /* A; K = A float costs                              coverage.py:22       */
+  int32_t mode;           /* 0 CoverageContinuous (:54-74,:91-95), 1 CoverageDiscretized (:219-241) */
+  int32_t has_coarseness; /* mode 0: rescale long moves (:64-69)                                    */
+  double fieldview;       /* fv = size / sqrt(A) unless overridden             coverage.py:15-18    */
+  double max_norm;        /* mode 0: sqrt(2)*size/coarseness                   coverage.py:66       */
+  double zoom;            /* mode 1: coarseness/size                           coverage.py:215      */
+  double hi;              /* mode 1: size*zoom                                 coverage.py:230      */
+  double cost_axis;       /* mode 1: 1*(size/coarseness)                       coverage.py:237      */
+  double cost_diag;       /* mode 1: sqrt(2)*(size/coarseness)                                      */
+  const float* weights;   /* [A] or NULL                                       coverage.py:86-87    */
+} SmarlCoverageFloatParams;
+
+/* state <- start (f64 [A][ld]) and obs rebuild, for the float-position Coverage envs
+ * (CoverageContinuous.reset/_restart, coverage.py:28-52). */
+int smarl_coverage_float_reset(const double* start_x, const double* start_y, double* pos_x,
+                               double* pos_y, float* obs, int32_t n_agents, int64_t n_envs,
+                               int64_t ld, smarl_stream_t stream);
+
+/* One CoverageContinuous.step / CoverageDiscretized.step (coverage.py:100-106) + MetaAgent.act.
+ *   pos_x,pos_y f64 [A][ld] in/out
+ *   actions: mode 0 f32 [2A][ld] rows dx0,dy0,dx1,...; mode 1 u8 [A][ld] in 0..8
+ *   obs f32 [2A][ld], reward f32 [A][ld], cost f32 [A][ld] (norm of the action / lattice step length),
+ *   done u8 [A][ld] (NULL ok, always 0), lambdas f64 [A] + penalty f32 [ld] (both NULL to skip) */
+int smarl_coverage_float_step(const SmarlCoverageFloatParams* p, double* pos_x, double* pos_y,
+                              const void* actions, float* obs, float* reward, float* cost,
+                              uint8_t* done, const double* lambdas, float* penalty, int64_t n_envs,
+                              int64_t ld, smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Congestion
  * ---------------------------------------------------------------------------------- */
 typedef struct {
@@ -205,11 +239,11 @@ int smarl_collision_rollout(const SmarlCollisionParams* p, const SmarlAccounting
  * Rollout accounting over a device rollout buffer filled by the *_step calls
  * (closed-loop mode: a policy chooses actions between steps).
  * ---------------------------------------------------------------------------------- */
-enum { SMARL_COST_U8 = 0, SMARL_COST_I32 = 1 };
+enum { SMARL_COST_U8 = 0, SMARL_COST_I32 = 1, SMARL_COST_F32 = 2 };   /* F32: C is written as f32 */
 
 /* MetaAgent.act's penalty for rewards/costs that did not come from a *_step call
  * (meta_agent.py:21-22): penalty[t][e] = sum_k lambda_k cost[t][k][e].
- *   cost [T][K][ld] u8 or i32, lambdas f64 [K], penalty f32 [T][ld] */
+ *   cost [T][K][ld] u8, i32 or f32, lambdas f64 [K], penalty f32 [T][ld] */
 int smarl_rollout_penalty(const void* cost, int32_t cost_dtype, const double* lambdas,
                           float* penalty, int32_t n_constraints, int32_t n_steps, int64_t n_envs,
                           int64_t ld, smarl_stream_t stream);

@@ -109,6 +109,88 @@ def coverage_discrete_step(pos, actions, size, lut, weights=None):
 
 
 # --------------------------------------------------------------------------------------
+# Coverage on float positions -- CoverageContinuous / CoverageDiscretized
+# --------------------------------------------------------------------------------------
+_POW_UFUNC = None
+
+
+def _pow2(v):
+    """libm pow(v, 2.0) element-wise: what numpy's *scalar* ``x ** 2`` evaluates (coverage.py:83);
+    it differs from x*x by one ulp on ~0.08 % of inputs."""
+    global _POW_UFUNC
+    if _POW_UFUNC is None:
+        import ctypes
+        import ctypes.util
+        f = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6").pow
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_double, ctypes.c_double]
+        _POW_UFUNC = np.frompyfunc(lambda a: f(a, 2.0), 1, 1)
+    return _POW_UFUNC(np.asarray(v, dtype=np.float64)).astype(np.float64)
+
+
+def coverage_float_reward(pos, fv, weights=None, exact_pow=True):
+    """CoverageContinuous.reward (envs/coverage.py:76-89) on float64 positions [E, A, 2].
+
+    D_ij = sqrt(dx*dx + dy*dy) (scipy distance_matrix, array ops); i-major sequential sum of
+    (fv - D_ij)**2 over pairs with fv - D_ij > 0.  ``exact_pow`` uses libm pow like the reference's
+    numpy scalar power; False uses a multiply (what the CUDA kernel does; <= 1 ulp per term)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    E, A, _ = pos.shape
+    rew = np.zeros(E, dtype=np.float64)
+    for i in range(A):
+        for j in range(i + 1, A):
+            dx = np.abs(pos[:, j, 0] - pos[:, i, 0])
+            dy = np.abs(pos[:, j, 1] - pos[:, i, 1])
+            gap = fv - np.sqrt(dx * dx + dy * dy)
+            pen = _pow2(gap) if exact_pow else gap * gap
+            rew = np.where(gap > 0, rew - pen, rew)
+    reward = np.repeat(rew[:, None], A, axis=1)
+    if weights is not None:
+        reward = reward * np.asarray(weights, dtype=np.float64)[None, :A]
+    return reward
+
+
+def coverage_continuous_step(pos, actions, size, fv, weights=None, coarseness=None, exact_pow=True):
+    """One CoverageContinuous.step (coverage.py:54-74 transition, :76-89 reward, :91-95 constraint).
+
+    pos [E,A,2] f64, actions [E,A,2] f64 (fp32-origin).  With ``coarseness`` the move is rescaled to
+    max_norm = sqrt(2)*size/coarseness when sqrt(norm) > max_norm (sic: the reference compares the
+    square root of the norm, :67).  cost_a = np.linalg.norm(action_a) of the ORIGINAL action."""
+    pos = np.asarray(pos, dtype=np.float64)
+    actions = np.asarray(actions, dtype=np.float64)
+    dx, dy = actions[:, :, 0].copy(), actions[:, :, 1].copy()
+    if coarseness is not None:
+        norm = np.sqrt(dx * dx + dy * dy)
+        max_norm = np.sqrt(2) * size / coarseness
+        big = np.sqrt(norm) > max_norm
+        with np.errstate(invalid="ignore", divide="ignore"):
+            dx = np.where(big, (dx / norm) * max_norm, dx)
+            dy = np.where(big, (dy / norm) * max_norm, dy)
+    new = np.empty_like(pos)
+    new[:, :, 0] = np.maximum(0.0, np.minimum(float(size), pos[:, :, 0] + dx))
+    new[:, :, 1] = np.maximum(0.0, np.minimum(float(size), pos[:, :, 1] + dy))
+    reward = coverage_float_reward(new, fv, weights, exact_pow)
+    ax, ay = actions[:, :, 0], actions[:, :, 1]
+    cost = np.sqrt(_fma(ay, ay, ax * ax))                   # np.linalg.norm of the 2-vector
+    return new, reward, cost, np.zeros(pos.shape[:2], dtype=bool)
+
+
+def coverage_discretized_step(pos, actions, size, coarseness, fv, weights=None, exact_pow=True):
+    """One CoverageDiscretized.step (coverage.py:219-241): 9 lattice moves on a 1/zoom grid,
+    zoom = coarseness/size; state stays float: x' = max(0, min(size*zoom, x*zoom + dx)) / zoom."""
+    pos = np.asarray(pos, dtype=np.float64)
+    actions = np.asarray(actions, dtype=np.int64)
+    zoom = coarseness / size
+    hi = size * zoom
+    new = np.empty_like(pos)
+    new[:, :, 0] = np.maximum(0.0, np.minimum(hi, pos[:, :, 0] * zoom + DIR9_X[actions])) / zoom
+    new[:, :, 1] = np.maximum(0.0, np.minimum(hi, pos[:, :, 1] * zoom + DIR9_Y[actions])) / zoom
+    reward = coverage_float_reward(new, fv, weights, exact_pow)
+    table = np.array([1, 1, 1, 1, np.sqrt(2), np.sqrt(2), np.sqrt(2), np.sqrt(2), 0]) * (size / coarseness)
+    return new, reward, table[actions], np.zeros(pos.shape[:2], dtype=bool)
+
+
+# --------------------------------------------------------------------------------------
 # Congestion
 # --------------------------------------------------------------------------------------
 def congestion_noise_moves(actions, u1, u2, noise):

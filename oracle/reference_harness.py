@@ -76,6 +76,33 @@ def run_coverage_discrete(size, n_agents, starts, actions, weights=None, fieldvi
                 fieldview=float(env.fieldview_size))
 
 
+def run_coverage_float(kind, size, n_agents, starts, actions, weights=None, fieldview_size=None, coarseness=None):
+    """kind 'continuous' (actions [T,A,2] floats) or 'discretized' (actions [T,A] ints 0..8)."""
+    ref = load()
+    np_state = np.random.get_state()
+    if kind == "continuous":
+        env = ref.coverage.CoverageContinuous(size, n_agents, shuffle=False, weights=weights,
+                                              fieldview_size=fieldview_size, coarseness=coarseness)
+    else:
+        env = ref.coverage.CoverageDiscretized(size, n_agents, coarseness=coarseness, shuffle=False, weights=weights,
+                                               fieldview_size=fieldview_size)
+    np.random.set_state(np_state)
+    for ag, s in zip(env.agents, starts):
+        ag.start = [float(s[0]), float(s[1])]
+    s0 = env.reset()
+    T = len(actions)
+    pos = np.zeros((T, n_agents, 2)); rew = np.zeros((T, n_agents)); cost = np.zeros((T, n_agents))
+    for t in range(T):
+        if kind == "continuous":
+            act = [[[float(a[0]), float(a[1])]] for a in actions[t]]
+        else:
+            act = [int(a) for a in actions[t]]
+        st, r, c, d = env.step(act)
+        pos[t] = _f64(st); rew[t] = _f64(r); cost[t] = _f64(c)
+        assert not any(d)
+    return dict(state0=_f64(s0), pos=pos, reward=rew, cost=cost, fieldview=float(env.fieldview_size))
+
+
 def run_congestion(size, n_agents, starts, actions, demand, noise=0.0, uniforms=None):
     """starts [A,2] ints (agent 0 is forced to (0,0) by the reference ctor; we inject all),
     actions [T,A] intended, uniforms [T,A,2] in [0,1) replayed through the env's

@@ -20,6 +20,12 @@ class Accounting(C.Structure):
                 ("thresholds", c_ptr)]
 
 
+class CoverageFloatParams(C.Structure):
+    _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("mode", C.c_int32), ("has_coarseness", C.c_int32),
+                ("fieldview", C.c_double), ("max_norm", C.c_double), ("zoom", C.c_double), ("hi", C.c_double),
+                ("cost_axis", C.c_double), ("cost_diag", C.c_double), ("weights", c_ptr)]
+
+
 class CongestionParams(C.Structure):
     _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("demand", c_ptr),
                 ("noise_mode", C.c_int32), ("reserved", C.c_int32),
@@ -47,6 +53,9 @@ PROTOTYPES = {
     "smarl_coverage_rollout": (C.c_int, [P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
                                          c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                          i64, i64, c_ptr]),
+    "smarl_coverage_float_reset": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
+    "smarl_coverage_float_step": (C.c_int, [P(CoverageFloatParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                            c_ptr, c_ptr, i64, i64, c_ptr]),
     "smarl_congestion_step": (C.c_int, [P(CongestionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_congestion_rollout": (C.c_int, [P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
@@ -70,7 +79,7 @@ PROTOTYPES = {
                                               c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
-COST_U8, COST_I32 = 0, 1
+COST_U8, COST_I32, COST_F32 = 0, 1, 2
 _lib = None
 
 

@@ -1,0 +1,174 @@
+// CoverageContinuous / CoverageDiscretized on sm_100a (float64 positions).  One thread owns one
+// env; all arrays agent-major SoA.  Compiled with -fmad=false: positions follow the reference's
+// float64 operations one by one (bit-exact); the pair penalty uses a multiply where the reference's
+// numpy scalar power calls libm pow (<= 1 ulp per term, invisible after the f32 rounding of rewards).
+#include "common.cuh"
+
+#ifndef SMARL_TU
+#define SMARL_TU -1
+#endif
+#define SMARL_TU_IS(k) (SMARL_TU == -1 || SMARL_TU == (k))
+
+namespace smarl {
+
+struct CoverageFloatArgs {
+  double* pos_x;
+  double* pos_y;
+  const void* actions;
+  float* obs;
+  float* reward;
+  float* cost;
+  uint8_t* done;
+  const double* lambdas;
+  float* penalty;
+  const float* weights;
+  int64_t n_envs;
+  int64_t ld;
+  double size, fieldview, max_norm, zoom, hi, cost_axis, cost_diag;
+  int32_t has_coarseness;
+};
+
+constexpr int kCovFThreads = 128;
+
+int launch_coverage_float_step(int mode, int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s);
+
+#if SMARL_TU_IS(0) || SMARL_TU_IS(1)
+template <int A, int MODE>
+__global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const CoverageFloatArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
+  if (e >= a.n_envs) return;
+  const int64_t ld = a.ld;
+  double px[A], py[A];
+  double pen = 0.0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    px[i] = a.pos_x[i * ld + e];
+    py[i] = a.pos_y[i * ld + e];
+  }
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    double cost;
+    if (MODE == 0) {                                   // CoverageContinuous.transition, coverage.py:54-74
+      const float* act = static_cast<const float*>(a.actions);
+      double dx = (double)act[(2 * i) * ld + e], dy = (double)act[(2 * i + 1) * ld + e];
+      cost = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));          // :94 np.linalg.norm(action)
+      if (a.has_coarseness) {
+        const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // :65
+        if (__dsqrt_rn(norm) > a.max_norm) {                           // :67 (sic: sqrt of the norm)
+          dx = __dmul_rn(__ddiv_rn(dx, norm), a.max_norm);
+          dy = __dmul_rn(__ddiv_rn(dy, norm), a.max_norm);
+        }
+      }
+      px[i] = fmax(0.0, fmin(a.size, __dadd_rn(px[i], dx)));            // :70
+      py[i] = fmax(0.0, fmin(a.size, __dadd_rn(py[i], dy)));
+    } else {                                           // CoverageDiscretized.transition, coverage.py:219-234
+      const uint32_t m = static_cast<const uint8_t*>(a.actions)[i * ld + e];
+      // directions (:221): x +1,-1,0,0,+1,+1,-1,-1,0 ; y 0,0,-1,+1,+1,-1,+1,-1,0
+      const int dxi = (m == 0 || m == 4 || m == 5) ? 1 : ((m == 1 || m == 6 || m == 7) ? -1 : 0);
+      const int dyi = (m == 3 || m == 4 || m == 6) ? 1 : ((m == 2 || m == 5 || m == 7) ? -1 : 0);
+      px[i] = __ddiv_rn(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(px[i], a.zoom), (double)dxi))), a.zoom);   // :230
+      py[i] = __ddiv_rn(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(py[i], a.zoom), (double)dyi))), a.zoom);
+      cost = m < 4 ? a.cost_axis : (m < 8 ? a.cost_diag : 0.0);        // :237
+    }
+    a.pos_x[i * ld + e] = px[i];
+    a.pos_y[i * ld + e] = py[i];
+    a.cost[i * ld + e] = (float)cost;
+    if (a.done) a.done[i * ld + e] = 0;                                 // :97-98
+    if (a.obs) {
+      a.obs[(2 * i) * ld + e] = (float)px[i];
+      a.obs[(2 * i + 1) * ld + e] = (float)py[i];
+    }
+    if (a.penalty) pen += __ldg(a.lambdas + i) * cost;                  // meta_agent.py:21-22
+  }
+  if (a.penalty) a.penalty[e] = (float)pen;
+  // reward, coverage.py:76-89: i-major sequential f64 sum over overlapping pairs
+  double rew = 0.0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+#pragma unroll
+    for (int j = i + 1; j < A; ++j) {
+      const double dx = __dadd_rn(px[j], -px[i]), dy = __dadd_rn(py[j], -py[i]);
+      const double gap = __dadd_rn(a.fieldview, -__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+      if (gap > 0.0) rew = __dadd_rn(rew, -__dmul_rn(gap, gap));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    const double w = a.weights ? (double)__ldg(a.weights + i) : 1.0;
+    a.reward[i * ld + e] = (float)__dmul_rn(rew, w);
+  }
+}
+
+#define SMARL_DEFINE_COVF_STEP(M)                                                                        \
+  int launch_coverage_float_step_m##M(int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s) { \
+    SMARL_DISPATCH_A(A, coverage_float_step_kernel<kA, M><<<grid, kCovFThreads, 0, s>>>(a));             \
+    SMARL_CUDA(cudaGetLastError());                                                                      \
+    return SMARL_OK;                                                                                     \
+  }
+#endif
+int launch_coverage_float_step_m0(int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s);
+int launch_coverage_float_step_m1(int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s);
+#if SMARL_TU_IS(0)
+SMARL_DEFINE_COVF_STEP(0)
+#endif
+#if SMARL_TU_IS(1)
+SMARL_DEFINE_COVF_STEP(1)
+#endif
+
+#if SMARL_TU_IS(2)
+__global__ void coverage_float_reset_kernel(const double* __restrict__ start_x, const double* __restrict__ start_y,
+                                            double* __restrict__ pos_x, double* __restrict__ pos_y,
+                                            float* __restrict__ obs, int A, int64_t n_envs, int64_t ld) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  for (int i = 0; i < A; ++i) {
+    const double x = start_x[i * ld + e], y = start_y[i * ld + e];
+    pos_x[i * ld + e] = x;
+    pos_y[i * ld + e] = y;
+    if (obs) {
+      obs[(2 * i) * ld + e] = (float)x;
+      obs[(2 * i + 1) * ld + e] = (float)y;
+    }
+  }
+}
+#endif
+
+}  // namespace smarl
+
+using namespace smarl;
+
+#if SMARL_TU_IS(2)
+extern "C" int smarl_coverage_float_reset(const double* start_x, const double* start_y, double* pos_x,
+                                          double* pos_y, float* obs, int32_t n_agents, int64_t n_envs,
+                                          int64_t ld, smarl_stream_t stream) {
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(start_x && start_y && pos_x && pos_y, "null state pointer");
+  SMARL_REQUIRE(n_agents >= 1 && n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", n_agents);
+  coverage_float_reset_kernel<<<(unsigned)((n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      start_x, start_y, pos_x, pos_y, obs, n_agents, n_envs, ld);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
+extern "C" int smarl_coverage_float_step(const SmarlCoverageFloatParams* p, double* pos_x, double* pos_y,
+                                         const void* actions, float* obs, float* reward, float* cost,
+                                         uint8_t* done, const double* lambdas, float* penalty,
+                                         int64_t n_envs, int64_t ld, smarl_stream_t stream) {
+  SMARL_REQUIRE(p != nullptr, "params is NULL");
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(p->size >= 1, "size=%d must be >= 1", p->size);
+  SMARL_REQUIRE(p->mode == 0 || p->mode == 1, "bad mode %d", p->mode);
+  SMARL_REQUIRE(p->mode == 0 || p->zoom > 0.0, "mode 1 needs zoom > 0");
+  SMARL_REQUIRE(pos_x && pos_y && actions && reward && cost, "null required pointer");
+  SMARL_REQUIRE((lambdas == nullptr) == (penalty == nullptr), "lambdas and penalty go together");
+  CoverageFloatArgs a;
+  a.pos_x = pos_x; a.pos_y = pos_y; a.actions = actions; a.obs = obs; a.reward = reward; a.cost = cost;
+  a.done = done; a.lambdas = lambdas; a.penalty = penalty; a.weights = p->weights; a.n_envs = n_envs;
+  a.ld = ld; a.size = (double)p->size; a.fieldview = p->fieldview; a.max_norm = p->max_norm;
+  a.zoom = p->zoom; a.hi = p->hi; a.cost_axis = p->cost_axis; a.cost_diag = p->cost_diag;
+  a.has_coarseness = p->has_coarseness;
+  const unsigned grid = (unsigned)((n_envs + kCovFThreads - 1) / kCovFThreads);
+  return p->mode == 0 ? launch_coverage_float_step_m0(p->n_agents, a, grid, (cudaStream_t)stream)
+                      : launch_coverage_float_step_m1(p->n_agents, a, grid, (cudaStream_t)stream);
+}
+#endif

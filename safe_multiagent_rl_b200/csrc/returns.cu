@@ -40,13 +40,28 @@ int sm_count() {
 constexpr int kAccThreads = 128;
 
 template <typename CT> struct CostVec;
+template <> struct CostVec<float> {   // float costs are summed in f64 like the reference and stored as f32
+  typedef double acc_t;
+  static __device__ __forceinline__ void load(const float* p, double (&c)[4]) {
+    const float4 f = ld_stream_f4(p);
+    c[0] = f.x; c[1] = f.y; c[2] = f.z; c[3] = f.w;
+  }
+  static __device__ __forceinline__ int4 pack(const double (&s)[4]) {
+    return make_int4(__float_as_int((float)s[0]), __float_as_int((float)s[1]), __float_as_int((float)s[2]),
+                     __float_as_int((float)s[3]));
+  }
+};
 template <> struct CostVec<uint8_t> {
+  typedef int acc_t;
+  static __device__ __forceinline__ int4 pack(const int (&s)[4]) { return make_int4(s[0], s[1], s[2], s[3]); }
   static __device__ __forceinline__ void load(const uint8_t* p, int (&c)[4]) {
     const uint32_t w = ld_stream_u32(p);
     c[0] = w & 0xFF; c[1] = (w >> 8) & 0xFF; c[2] = (w >> 16) & 0xFF; c[3] = w >> 24;
   }
 };
 template <> struct CostVec<int32_t> {
+  typedef int acc_t;
+  static __device__ __forceinline__ int4 pack(const int (&s)[4]) { return make_int4(s[0], s[1], s[2], s[3]); }
   static __device__ __forceinline__ void load(const int32_t* p, int (&c)[4]) {
     const float4 f = ld_stream_f4(p);
     c[0] = __float_as_int(f.x); c[1] = __float_as_int(f.y); c[2] = __float_as_int(f.z); c[3] = __float_as_int(f.w);
@@ -64,7 +79,7 @@ penalty_kernel(const CT* __restrict__ cost, const double* __restrict__ lambdas, 
   const int64_t t = blockIdx.y;
   double pen[4] = {0, 0, 0, 0};
   for (int k = 0; k < K; ++k) {
-    int c[4];
+    typename CostVec<CT>::acc_t c[4];
     CostVec<CT>::load(cost + (t * K + k) * ld + e0, c);
     const double lam = __ldg(lambdas + k);
 #pragma unroll
@@ -174,15 +189,15 @@ __global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs 
     // C_k = sum_t c[t,k]  (buffer.py:39, meta_agent.py:28)
     const int k = row - a.A;
     const CT* cost = static_cast<const CT*>(a.cost);
-    int sum[4] = {0, 0, 0, 0};
+    typename CostVec<CT>::acc_t sum[4] = {0, 0, 0, 0};
 #pragma unroll 4
     for (int t = 0; t < T; ++t) {
-      int c[4];
+      typename CostVec<CT>::acc_t c[4];
       CostVec<CT>::load(cost + ((int64_t)t * a.K + k) * ld + e0, c);
 #pragma unroll
       for (int j = 0; j < 4; ++j) sum[j] += c[j];
     }
-    if (live) st_stream_i4(a.C + (int64_t)k * ld + e0, make_int4(sum[0], sum[1], sum[2], sum[3]));
+    if (live) st_stream_i4(a.C + (int64_t)k * ld + e0, CostVec<CT>::pack(sum));
     if (out) {
       const double thr = a.thresholds ? __ldg(a.thresholds + k) : 0.0;
       double c = 0.0, viol = 0.0;
@@ -276,6 +291,9 @@ extern "C" int smarl_rollout_penalty(const void* cost, int32_t cost_dtype, const
   else if (cost_dtype == SMARL_COST_I32)
     penalty_kernel<int32_t><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
         static_cast<const int32_t*>(cost), lambdas, penalty, K, n_groups, ld);
+  else if (cost_dtype == SMARL_COST_F32)
+    penalty_kernel<float><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<const float*>(cost), lambdas, penalty, K, n_groups, ld);
   else
     SMARL_REQUIRE(false, "bad cost_dtype %d", cost_dtype);
   SMARL_CUDA(cudaGetLastError());
@@ -311,6 +329,8 @@ extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* re
     returns_kernel<uint8_t><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
   else if (cost_dtype == SMARL_COST_I32)
     returns_kernel<int32_t><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
+  else if (cost_dtype == SMARL_COST_F32)
+    returns_kernel<float><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
   else
     SMARL_REQUIRE(false, "bad cost_dtype %d", cost_dtype);
   SMARL_CUDA(cudaGetLastError());

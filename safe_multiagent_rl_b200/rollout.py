@@ -75,9 +75,9 @@ class RolloutBuffer:
         self.ld = pad_ld(n_envs)
         self.device = torch.device(device)
         self.g_mode = g_mode
-        assert cost_dtype in (torch.uint8, torch.int32)
+        assert cost_dtype in (torch.uint8, torch.int32, torch.float32)
         self.cost_dtype = cost_dtype
-        self.cost_code = _lib.COST_U8 if cost_dtype == torch.uint8 else _lib.COST_I32
+        self.cost_code = {torch.uint8: _lib.COST_U8, torch.int32: _lib.COST_I32, torch.float32: _lib.COST_F32}[cost_dtype]
         T, A, K, E = self.T, self.A, self.K, self.E
         self.reward = alloc(A, E, torch.float32, device, (T,))
         self.cost = alloc(K, E, cost_dtype, device, (T,))
@@ -85,7 +85,7 @@ class RolloutBuffer:
         self.penalty = alloc(1, E, torch.float32, device, (T,))[:, 0]
         self.R = alloc(A, E, torch.float32, device)
         self.modR = alloc(A, E, torch.float32, device)
-        self.Csum = alloc(K, E, torch.int32, device)
+        self.Csum = alloc(K, E, torch.float32 if cost_dtype == torch.float32 else torch.int32, device)
         self.G = alloc(A, E, torch.float32, device, (T,)) if g_mode != G_NONE else None
         lib = _lib.load()
         self.stats_vec = torch.zeros(lib.smarl_stats_len(A, K), dtype=torch.float64, device=device)

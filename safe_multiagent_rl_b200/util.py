@@ -4,6 +4,7 @@ from __future__ import annotations
 from .envs.collision_avoidance import BatchedCollisionAvoidance
 from .envs.congestion import BatchedCongestion
 from .envs.coverage import BatchedCoverageDiscrete
+from .envs.coverage_float import BatchedCoverageContinuous, BatchedCoverageDiscretized
 
 
 def make_env(params, n_envs=1, device="cuda", **kw):
@@ -19,7 +20,11 @@ def make_env(params, n_envs=1, device="cuda", **kw):
     if name == "Congestion":
         return BatchedCongestion(params.size, params.n_agents, n_envs=n_envs, noise=params.noise,
                                  shuffle=params.shuffle, device=device, **kw), False
-    if name in ("CoverageDiscretized", "CoverageContinuous"):
-        raise NotImplementedError(f"{name} is not built yet (DESIGN.md: next rows)")
+    if name == "CoverageDiscretized":
+        return BatchedCoverageDiscretized(params.size, params.n_agents, n_envs=n_envs, coarseness=params.coarseness,
+                                          shuffle=params.shuffle, weights=params.weights, device=device, **kw), False
+    if name == "CoverageContinuous":
+        return BatchedCoverageContinuous(params.size, params.n_agents, n_envs=n_envs, shuffle=params.shuffle,
+                                         weights=params.weights, coarseness=params.coarseness, device=device, **kw), True
     raise ValueError("params.environment must be CoverageDiscrete, CoverageDiscretized, CoverageContinuous, "
                      "Collision or Congestion")

@@ -50,6 +50,26 @@ def coverage(name, size, A, E, T, weights, lam, gamma, thr, seed, fv=None):
                         starts=starts, actions=actions, pos=pos, reward=rew, cost=cost, **acc)
 
 
+def coverage_float(name, kind, size, A, E, T, coarse, weights, lam, gamma, thr, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "continuous":
+        starts = rng.random((E, A, 2)) * size
+        actions = rng.normal(0, 0.8, size=(T, E, A, 2)).astype(np.float32)
+    else:
+        zoom = coarse / size
+        starts = np.floor(rng.random((E, A, 2)) * size * zoom) / zoom
+        actions = rng.integers(0, 9, size=(T, E, A)).astype(np.int16)
+    pos = np.zeros((T, E, A, 2)); rew = np.zeros((T, E, A)); cost = np.zeros((T, E, A))
+    for e in range(E):
+        tr = rh.run_coverage_float(kind, size, A, starts[e], actions[:, e].astype(np.float64) if kind == "continuous"
+                                   else actions[:, e], weights=weights, coarseness=coarse)
+        pos[:, e], rew[:, e], cost[:, e] = tr["pos"], tr["reward"], tr["cost"]
+    acc = accounting(rew, cost, lam, gamma, thr, 0.05)
+    np.savez_compressed(os.path.join(HERE, name), env=kind, size=size, n_agents=A, coarseness=coarse, weights=weights,
+                        fieldview=tr["fieldview"], lambdas=lam, gamma=gamma, thresholds=thr, meta_lr=0.05,
+                        starts=starts, actions=actions, pos=pos, reward=rew, cost=cost, **acc)
+
+
 def congestion(name, size, A, E, T, noise, lam, gamma, thr, seed, philox_seed, env_offset):
     rng = np.random.default_rng(seed)
     demand = rng.random((size + 1, size + 1)) * 8 + 2
@@ -109,6 +129,11 @@ if __name__ == "__main__":
     # config 2 shape and the paper's Collision config
     collision("collision_c2.npz", 5, 3, 1, 64, 50, [0.5], 0.99, [1.0], 4)
     collision("collision_paper.npz", 2, 5, 1, 32, 20, [0.8], 0.99, [1.0], 5)
+    # the paper's "ExploreContinuous" launcher config (coarseness 6, CLI defaults size 3 / 3 agents / max_t 8)
+    coverage_float("coverage_continuous_paper.npz", "continuous", 3, 3, 32, 8, 6, [1.0, 1.0, 1.0], [0.2, 0.2, 0.2], 0.99,
+                   [15.0] * 3, 6)
+    coverage_float("coverage_discretized.npz", "discretized", 5, 3, 16, 30, 20, [1.0, 2.0, 3.0], [0.1, 0.2, 0.3], 0.999,
+                   [5.0] * 3, 7)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

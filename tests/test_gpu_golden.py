@@ -113,3 +113,32 @@ def test_collision_vs_reference_outputs(name):
     check_accounting(g, fused, scale)
     assert np.array_equal(fused["n_active"].cpu().numpy(), g["active"].sum(0))
     assert np.array_equal(env.state().cpu().numpy(), g["pos"][-1])
+
+
+@pytest.mark.parametrize("name", ["coverage_continuous_paper.npz", "coverage_discretized.npz"])
+def test_coverage_float_vs_reference_outputs(name):
+    import safe_multiagent_rl_b200 as s
+    g = np.load(os.path.join(GOLD, name))
+    size, A, coarse = int(g["size"]), int(g["n_agents"]), int(g["coarseness"])
+    T, E = g["actions"].shape[:2]
+    if str(g["env"]) == "continuous":
+        env = s.BatchedCoverageContinuous(size, A, n_envs=E, weights=g["weights"].tolist(), coarseness=coarse,
+                                          starts=g["starts"])
+    else:
+        env = s.BatchedCoverageDiscretized(size, A, n_envs=E, coarseness=coarse, weights=g["weights"].tolist(),
+                                           starts=g["starts"])
+    lam = torch.as_tensor(g["lambdas"], dtype=torch.float64, device="cuda")
+    buf = env.new_rollout_buffer(T)
+    env.reset()
+    for t in range(T):
+        a = g["actions"][t] if str(g["env"]) == "continuous" else g["actions"][t].astype(np.uint8)
+        obs, r, c, d = env.step(a, lambdas=lam, out=(buf, t))
+        assert np.array_equal(env.state().cpu().numpy(), g["pos"][t])                      # bit-exact float64
+        assert np.array_equal(c.cpu().numpy(), g["cost"][t].astype(np.float32))
+        close(r.cpu().numpy(), g["reward"][t], np.abs(g["reward"][t]).max() + 1e-9, rtol=2e-7)
+    out = buf.finish(float(g["gamma"]), g["thresholds"])
+    scale = np.abs(g["modR"]).max()
+    close(out["R"].cpu().numpy(), g["R"], scale)
+    close(out["modR"].cpu().numpy(), g["modR"], scale)
+    close(out["G"].cpu().numpy(), g["G"], scale)
+    close(out["C"].cpu().numpy(), g["C"], np.abs(g["C"]).max())

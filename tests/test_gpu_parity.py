@@ -402,3 +402,63 @@ def test_step_accepts_kernel_layout_and_env_major_actions():
     e3.step(e3.action_buffer, agent_major=True)          # policies writing the env's own buffer
     assert torch.equal(e1.state(), e2.state()) and torch.equal(e1.state(), e3.state())
     assert torch.equal(e1.reward, e2.reward) and torch.equal(e1.reward, e3.reward)
+
+
+# ----------------------------------------------------------------------------- float-position Coverage variants
+@pytest.mark.parametrize("size,A,E,T,coarse,seed", [(5, 3, 300, 40, None, 0), (5, 3, 300, 40, 6, 1), (10, 8, 130, 15, 20, 2),
+                                                     (3, 32, 33, 6, 2, 3)])
+def test_coverage_continuous_matches_oracle(size, A, E, T, coarse, seed):
+    s = smarl()
+    rng = np.random.default_rng(seed)
+    w = (1.0 + (np.arange(A) % 3)).tolist()
+    starts = rng.random((E, A, 2)) * size
+    actions = rng.normal(0, 0.8, size=(T, E, A, 2)).astype(np.float32)
+    env = s.BatchedCoverageContinuous(size, A, n_envs=E, weights=w, coarseness=coarse, starts=starts)
+    fv = no.coverage_fieldview(size, A)
+    assert env.fieldview_size == fv
+    lam_np = np.linspace(0.1, 0.3, A)
+    lam = torch.as_tensor(lam_np, device="cuda")
+    gamma = 0.99
+    buf = env.new_rollout_buffer(T)
+    env.reset()
+    pos = starts.copy()
+    rs, cs = [], []
+    for t in range(T):
+        obs, r, c, d = env.step(actions[t], lambdas=lam, out=(buf, t))
+        pos, r_o, c_o, _ = no.coverage_continuous_step(pos, actions[t].astype(np.float64), size, fv, w, coarse, exact_pow=False)
+        assert np.array_equal(env.state().cpu().numpy(), pos)                        # bit-exact float64
+        assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))               # f64-exact, rounded once
+        assert np.array_equal(c.cpu().numpy(), c_o.astype(np.float32))
+        assert not d.any()
+        close(env.obs[:, :E].t().cpu().numpy().reshape(E, A, 2), pos)
+        rs.append(r_o.astype(np.float32).astype(np.float64)); cs.append(c_o)
+    want = no.rollout(lambda t: (rs[t], cs[t]), T, gamma, lam_np)
+    out = buf.finish(gamma, thresholds=[0.5 * T] * A)
+    scale = np.abs(want["modR"]).max()
+    close(out["R"].cpu().numpy(), want["R"], scale)
+    close(out["modR"].cpu().numpy(), want["modR"], scale)
+    close(out["G"].cpu().numpy(), want["G"], scale)
+    close(out["C"].cpu().numpy(), want["C"], np.abs(want["C"]).max())
+    close(out["stats"].cost_sum.cpu().numpy(), want["C"].sum(0), np.abs(want["C"].sum(0)).max())
+    assert np.array_equal(out["stats"].violations.cpu().numpy(), (out["C"].cpu().numpy() > 0.5 * T).sum(0))
+
+
+@pytest.mark.parametrize("size,A,E,T,coarse,seed", [(5, 3, 300, 40, 20, 0), (5, 3, 100, 40, 6, 1), (10, 8, 130, 15, 7, 2),
+                                                     (3, 32, 33, 6, 3, 3)])
+def test_coverage_discretized_matches_oracle(size, A, E, T, coarse, seed):
+    s = smarl()
+    rng = np.random.default_rng(seed)
+    w = (1.0 + (np.arange(A) % 3)).tolist()
+    zoom = coarse / size
+    starts = np.floor(rng.random((E, A, 2)) * size * zoom) / zoom
+    actions = rng.integers(0, 9, size=(T, E, A))
+    env = s.BatchedCoverageDiscretized(size, A, n_envs=E, coarseness=coarse, weights=w, starts=starts)
+    fv = no.coverage_fieldview(size, A)
+    env.reset()
+    pos = starts.copy()
+    for t in range(T):
+        obs, r, c, d = env.step(actions[t].astype(np.uint8))
+        pos, r_o, c_o, _ = no.coverage_discretized_step(pos, actions[t], size, coarse, fv, w, exact_pow=False)
+        assert np.array_equal(env.state().cpu().numpy(), pos)
+        assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))
+        assert np.array_equal(c.cpu().numpy(), c_o.astype(np.float32))

@@ -107,3 +107,29 @@ def test_keep_threshold_is_exact():
         thr = philox.keep_threshold(noise)
         w = np.concatenate([rng.integers(0, 2 ** 32, 1000), [0, 2 ** 32 - 1, max(thr - 1, 0), min(thr, 2 ** 32 - 1)]])
         assert np.array_equal(w * 2.0 ** -32 < 1 - noise, w < thr)
+
+
+@pytest.mark.parametrize("name", ["coverage_continuous_paper.npz", "coverage_discretized.npz"])
+def test_coverage_float_golden(name):
+    g = load(name)
+    size, A, coarse = int(g["size"]), int(g["n_agents"]), int(g["coarseness"])
+    fv = no.coverage_fieldview(size, A)
+    assert fv == float(g["fieldview"])
+    pos = g["starts"].copy()
+    T = g["actions"].shape[0]
+    rew, cost = [], []
+    for t in range(T):
+        if str(g["env"]) == "continuous":
+            pos, r, c, _ = no.coverage_continuous_step(pos, g["actions"][t].astype(np.float64), size, fv, g["weights"], coarse)
+        else:
+            pos, r, c, _ = no.coverage_discretized_step(pos, g["actions"][t], size, coarse, fv, g["weights"])
+        np.testing.assert_array_equal(pos, g["pos"][t])
+        np.testing.assert_array_equal(r, g["reward"][t])
+        np.testing.assert_array_equal(c, g["cost"][t])
+        rew.append(r); cost.append(c)
+    lam, gamma = g["lambdas"], float(g["gamma"])
+    mod = no.modified_reward(np.stack(rew), np.stack(cost), lam)
+    np.testing.assert_array_equal(no.episode_returns(np.stack(rew), gamma), g["R"])
+    np.testing.assert_allclose(no.episode_returns(mod, gamma), g["modR"], rtol=1e-12)
+    np.testing.assert_allclose(no.episode_cost_sums(np.stack(cost)), g["C"], rtol=1e-14)
+    np.testing.assert_allclose(no.reward_to_go(mod, gamma), g["G"], rtol=1e-12, atol=1e-12)

@@ -168,3 +168,41 @@ def test_accounting_matches_reference(A, K, T, gamma, seed):
     lam2 = no.lambda_update(lam, out["C"], thr, 0.05)
     np.testing.assert_allclose(lam2, out["lambdas_after"], rtol=1e-14)
     np.testing.assert_allclose(out["C"] - thr, out["mean_violation"], rtol=1e-14)
+
+
+# ------------------------------------------------------------------ differential: float Coverage variants
+@pytest.mark.parametrize("size,A,T,coarse,seed", [(5, 3, 40, None, 0), (5, 3, 40, 6, 1), (10, 8, 15, 20, 2), (3, 5, 30, 2, 3)])
+def test_coverage_continuous_matches_reference(size, A, T, coarse, seed):
+    rng = np.random.default_rng(seed)
+    w = (1.0 + (np.arange(A) % 3)).tolist()
+    fv = no.coverage_fieldview(size, A)
+    for e in range(4):
+        starts = rng.random((A, 2)) * size
+        actions = rng.normal(0, 0.8, size=(T, A, 2)).astype(np.float32).astype(np.float64)
+        tr = rh.run_coverage_float("continuous", size, A, starts, actions, weights=w, coarseness=coarse)
+        pos = starts[None].copy()
+        for t in range(T):
+            pos, r, c, d = no.coverage_continuous_step(pos, actions[t][None], size, fv, w, coarse)
+            assert np.array_equal(pos[0], tr["pos"][t])                   # bit-exact f64
+            assert np.array_equal(r[0], tr["reward"][t])                  # bit-exact f64 (libm pow path)
+            assert np.array_equal(c[0], tr["cost"][t])
+            fast = no.coverage_float_reward(pos, fv, w, exact_pow=False)  # the multiply the CUDA kernel uses
+            np.testing.assert_allclose(fast[0], tr["reward"][t], rtol=1e-14)
+
+
+@pytest.mark.parametrize("size,A,T,coarse,seed", [(5, 3, 40, 20, 0), (5, 3, 40, 6, 1), (10, 8, 15, 7, 2), (3, 4, 30, 3, 3)])
+def test_coverage_discretized_matches_reference(size, A, T, coarse, seed):
+    rng = np.random.default_rng(seed)
+    w = (1.0 + (np.arange(A) % 3)).tolist()
+    fv = no.coverage_fieldview(size, A)
+    zoom = coarse / size
+    for e in range(4):
+        starts = np.floor(rng.random((A, 2)) * size * zoom) / zoom        # coverage.py:270-272
+        actions = rng.integers(0, 9, size=(T, A))
+        tr = rh.run_coverage_float("discretized", size, A, starts, actions, weights=w, coarseness=coarse)
+        pos = starts[None].copy()
+        for t in range(T):
+            pos, r, c, d = no.coverage_discretized_step(pos, actions[t][None], size, coarse, fv, w)
+            assert np.array_equal(pos[0], tr["pos"][t])
+            assert np.array_equal(r[0], tr["reward"][t])
+            assert np.array_equal(c[0], tr["cost"][t])
