@@ -64,6 +64,24 @@ int smarl_grid_reset(const uint8_t* start_x, const uint8_t* start_y, uint8_t* po
                      smarl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * shuffle=True: per-episode re-randomised starts / landmarks (Agent.reset: envs/coverage.py:266-273,
+ * envs/congestion.py:211-217, envs/collision_avoidance.py:178-179; landmarks :100-101).  The reference
+ * draws from numpy's global MT19937 stream; here each (x,y) pair comes from Philox4x32-10 with counter
+ * (global env id, episode, row) and key seed, as 53-bit uniforms u (numpy's random_sample formula),
+ * so draws do not depend on sharding.  Fill the start arrays, then call the env's reset.
+ *   kind 0: floor(u*size) u8           kind 1: same, row 0 pinned to (0,0) (Congestion agent 0)
+ *   kind 2: u*size f64                 kind 3: floor((u*size)*zoom)/zoom f64 (CoverageDiscretized)
+ * The f64 variant addresses row r at x[r*row_stride + e] (row_stride = ld for starts, 2*ld with
+ * y = x + ld for Collision's interleaved landmark rows); row_offset separates counter domains.
+ * ---------------------------------------------------------------------------------- */
+int smarl_random_starts_u8(int32_t kind, int32_t size, uint64_t seed, int64_t episode, int64_t env_offset,
+                           uint8_t* start_x, uint8_t* start_y, int32_t n_agents, int64_t n_envs, int64_t ld,
+                           smarl_stream_t stream);
+int smarl_random_starts_f64(int32_t kind, int32_t size, double zoom, uint64_t seed, int64_t episode,
+                            int64_t env_offset, int32_t row_offset, double* x, double* y, int64_t row_stride,
+                            int32_t n_rows, int64_t n_envs, smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * CoverageDiscrete ("Explore")
  * ---------------------------------------------------------------------------------- */
 typedef struct {

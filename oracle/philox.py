@@ -71,3 +71,32 @@ def keep_threshold(noise):
     from fractions import Fraction
     lim = Fraction(1 - noise) * (1 << 32)        # exact value of the f64 ``1 - noise`` times 2**32
     return min(1 << 32, max(0, math.ceil(lim)))
+
+
+def start_uniforms(seed, env_ids, episode, rows):
+    """53-bit uniforms (ux, uy), each [E, len(rows)], of the shuffle=True start draws: counter
+    (env id, episode, row), key (seed lo, seed hi ^ "RSET"), numpy's random_sample bit recipe."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    rows = np.asarray(rows, dtype=np.uint64)
+    o = philox4x32_10((env_ids & MASK)[:, None], (env_ids >> np.uint64(32))[:, None],
+                      np.full((1, 1), episode, dtype=np.uint64), rows[None, :],
+                      seed & 0xFFFFFFFF, ((seed >> 32) & 0xFFFFFFFF) ^ 0x52534554)
+
+    def u53(a, b):
+        return ((a >> np.uint32(5)).astype(np.float64) * 67108864.0 + (b >> np.uint32(6)).astype(np.float64)) \
+            * (1.0 / 9007199254740992.0)
+    return u53(o[0], o[1]), u53(o[2], o[3])
+
+
+def random_starts(kind, size, seed, env_ids, episode, n_rows, zoom=None, row_offset=0):
+    """[E, n_rows, 2] starts: kind 0 floor(u*size); 1 same with row 0 at (0,0); 2 u*size;
+    3 floor((u*size)*zoom)/zoom  (Agent.reset in the reference envs)."""
+    ux, uy = start_uniforms(seed, env_ids, episode, np.arange(n_rows) + row_offset)
+    xy = np.stack([ux * size, uy * size], axis=-1)
+    if kind in (0, 1):
+        xy = np.floor(xy)
+        if kind == 1:
+            xy[:, 0] = 0
+    elif kind == 3:
+        xy = np.floor(xy * zoom) / zoom
+    return xy

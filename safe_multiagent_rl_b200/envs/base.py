@@ -30,6 +30,9 @@ class BatchedEnv:
         self.env_offset = int(env_offset)       # global id of env 0 when sharded over GPUs
         self.lib = _lib.load()
         self.t = 0
+        self.shuffle = False
+        self.seed = 0
+        self._episode = 0          # shuffle=True: index of the next episode's start draw
 
     # ---- buffers --------------------------------------------------------------------------------
     def _alloc(self, rows, dtype, lead=()):
@@ -64,8 +67,26 @@ class BatchedEnv:
         """``env.reset()`` for every env: returns the observation ``[n_envs, state_space]`` (a view;
         row e is ``np.array(state).flatten()`` of env e, main.py:33)."""
         self.t = 0
+        self._maybe_shuffle()
         self._reset_impl()
         return env_major(self.obs, self.n_envs)
+
+    def _maybe_shuffle(self):
+        """shuffle=True (coverage.py:31-43, congestion.py:42-43, collision_avoidance.py:75-89): draw
+        this episode's starts on the device before the reset / fused rollout reads them."""
+        if self.shuffle:
+            self._draw_starts(self._episode)
+            self._episode += 1
+
+    def _draw_grid_starts(self, episode, kind):
+        _lib.check(self.lib.smarl_random_starts_u8(kind, self.size, self.seed & (2 ** 64 - 1), episode, self.env_offset,
+                                                   _lib.ptr(self.start_x), _lib.ptr(self.start_y), self.n_agents,
+                                                   self.n_envs, self.ld, _lib.stream_ptr()))
+
+    def _draw_float_starts(self, episode, kind, zoom=0.0):
+        _lib.check(self.lib.smarl_random_starts_f64(kind, self.size, float(zoom), self.seed & (2 ** 64 - 1), episode,
+                                                    self.env_offset, 0, _lib.ptr(self.start_x), _lib.ptr(self.start_y),
+                                                    self.ld, self.n_agents, self.n_envs, _lib.stream_ptr()))
 
     def step(self, actions, lambdas=None, out=None, agent_major=False):
         """``env.step(actions)`` for every env.

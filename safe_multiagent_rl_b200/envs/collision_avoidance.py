@@ -28,15 +28,13 @@ class BatchedCollisionAvoidance(BatchedEnv):
     action_dtype = torch.float32
 
     def __init__(self, size, n_agents, n_envs=1, n_landmarks=1, shuffle=False, agents_size=0.25,
-                 normalize_state=False, device="cuda", starts=None, landmarks=None, env_offset=0):
+                 normalize_state=False, device="cuda", starts=None, landmarks=None, env_offset=0, seed=0):
         assert type(size) == int and type(n_agents) == int and type(n_landmarks) == int   # :51-53
         assert type(agents_size) in (float, int)
         self._init_common(size, n_agents, n_envs, device, env_offset)
-        if shuffle:
-            raise NotImplementedError("shuffle=True (re-randomised starts/landmarks per episode) is not built yet")
         if normalize_state:
             raise NotImplementedError("normalize_state=True is not built yet")
-        self.shuffle, self.normalize_state = False, False
+        self.shuffle, self.normalize_state, self.seed = bool(shuffle), False, int(seed)
         self.agents_size = float(agents_size)
         A, E, dev = self.n_agents, self.n_envs, self.device
         self.n_landmarks = int(n_landmarks)
@@ -45,7 +43,8 @@ class BatchedCollisionAvoidance(BatchedEnv):
         self.n_constraints = 1
         self.action_rows = 2 * A
         if starts is None or landmarks is None:
-            L0 = 1                                              # the ctor draws a single landmark (:62)
+            # the ctor draws a single landmark (:62); with shuffle every reset redraws n_landmarks (:100-101)
+            L0 = self.n_landmarks if self.shuffle else 1
             draws = np.random.rand(E, A + L0, 2) * self.size
             if starts is None:
                 starts = draws[:, :A]
@@ -64,12 +63,21 @@ class BatchedCollisionAvoidance(BatchedEnv):
         self.pos_x, self.pos_y = self.start_x.clone(), self.start_y.clone()
         self.agent_done = self._alloc(A, torch.uint8)
         self.action_buffer = self._alloc(2 * A, torch.float32)  # rows dx0, dy0, dx1, ...
-        self.obs = self._alloc(2 * A, torch.float32)
+        if self.shuffle:
+            self.state_space += 2 * self.L                       # landmarks are part of the state (:65-68)
+        self.obs = self._alloc(2 * A + (2 * self.L if self.shuffle else 0), torch.float32)
         self.reward = self._alloc(A, torch.float32)
         self.cost = self._alloc(1, torch.int32)
         self.done = self._alloc(A, torch.uint8)
         self.penalty = self._alloc(1, torch.float32)[0]
-        self._params = _lib.CollisionParams(self.size, A, self.L, 0, self.agents_size)
+        self._params = _lib.CollisionParams(self.size, A, self.L, int(self.shuffle), self.agents_size)
+
+    def _draw_starts(self, episode):
+        self._draw_float_starts(episode, 2)                      # agents (:82-84) ...
+        _lib.check(self.lib.smarl_random_starts_f64(               # ... then the landmarks (:85, :100-101)
+            2, self.size, 0.0, self.seed & (2 ** 64 - 1), episode, self.env_offset, self.n_agents,
+            _lib.ptr(self.landmarks), self.landmarks.data_ptr() + 8 * self.ld, 2 * self.ld, self.L, self.n_envs,
+            _lib.stream_ptr()))
 
     def state(self):
         """[n_envs, n_agents, 2] float64 positions (a copy)."""
@@ -99,6 +107,7 @@ class BatchedCollisionAvoidance(BatchedEnv):
             o["n_active_"] = self._alloc(1, torch.int32)
         thr = device_thresholds(thresholds, dev)
         acc = make_accounting(gamma, T, g_mode, thr)
+        self._maybe_shuffle()
         _lib.check(self.lib.smarl_collision_rollout(
             C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),
             _lib.ptr(self.landmarks), _lib.ptr(actions), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y),

@@ -51,9 +51,7 @@ class BatchedCongestion(BatchedEnv):
         if not (1 <= self.size <= 254):
             raise ValueError("size must be in 1..254 (uint8 coordinates)")
         assert 0 <= noise <= 1                                    # congestion.py:30
-        if shuffle:
-            raise NotImplementedError("shuffle=True is not built yet")
-        self.shuffle, self.noise, self.seed = False, float(noise), int(seed)
+        self.shuffle, self.noise, self.seed = bool(shuffle), float(noise), int(seed)
         A, E, dev = self.n_agents, self.n_envs, self.device
         self.state_space = 2 * A
         self.constraint_space = [1]
@@ -93,6 +91,9 @@ class BatchedCongestion(BatchedEnv):
     def _params(self, mode):
         return _lib.CongestionParams(self.size, self.n_agents, _lib.ptr(self._demand), mode, 0,
                                      keep_threshold(self.noise), self.seed & (2 ** 64 - 1), self.env_offset)
+
+    def _draw_starts(self, episode):
+        self._draw_grid_starts(episode, 1)        # agent 0 restarts at (0,0), congestion.py:215-216
 
     def state(self):
         E = self.n_envs
@@ -136,6 +137,7 @@ class BatchedCongestion(BatchedEnv):
         thr = device_thresholds(thresholds, dev)
         acc = make_accounting(gamma, T, g_mode, thr)
         p = self._params(mode)
+        self._maybe_shuffle()
         _lib.check(self.lib.smarl_congestion_rollout(
             C.byref(p), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y), _lib.ptr(actions),
             _lib.ptr(moves), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(o["R_"]),

@@ -45,13 +45,11 @@ class BatchedCoverageDiscrete(BatchedEnv):
     action_dtype = torch.uint8
 
     def __init__(self, size, n_agents, n_envs=1, shuffle=False, agents_size=0.5, fieldview_size=None,
-                 weights=None, device="cuda", starts=None, env_offset=0):
+                 weights=None, device="cuda", starts=None, env_offset=0, seed=0):
         self._init_common(size, n_agents, n_envs, device, env_offset)
         if not (1 <= self.size <= 127):
             raise ValueError("size must be in 1..127 (doubled uint8 coordinates index the penalty table)")
-        if shuffle:
-            raise NotImplementedError("shuffle=True (per-episode re-randomised starts) is not built yet")
-        self.shuffle = False
+        self.shuffle, self.seed = bool(shuffle), int(seed)
         self.agents_size = agents_size
         A, E = self.n_agents, self.n_envs
         self.state_space = 2 * A
@@ -92,6 +90,9 @@ class BatchedCoverageDiscrete(BatchedEnv):
         self.done = self._alloc(A, torch.uint8)
         self.penalty = self._alloc(1, torch.float32)[0]
 
+    def _draw_starts(self, episode):
+        self._draw_grid_starts(episode, 0)
+
     def state(self):
         """[n_envs, n_agents, 2] integer positions (a copy)."""
         E = self.n_envs
@@ -120,6 +121,7 @@ class BatchedCoverageDiscrete(BatchedEnv):
         o = self._rollout_outputs(T, g_mode, out, 2 * T)
         thr = device_thresholds(thresholds, dev)
         acc = make_accounting(gamma, T, g_mode, thr)
+        self._maybe_shuffle()
         _lib.check(self.lib.smarl_coverage_rollout(
             C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y),
             _lib.ptr(actions), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(o["R_"]),

@@ -15,11 +15,10 @@ class _CoverageFloat(BatchedEnv):
     cost_dtype = torch.float32
     never_done = True
 
-    def _setup(self, size, n_agents, n_envs, device, env_offset, shuffle, agents_size, fieldview_size, weights, starts):
+    def _setup(self, size, n_agents, n_envs, device, env_offset, shuffle, agents_size, fieldview_size, weights, starts,
+               seed=0):
         self._init_common(size, n_agents, n_envs, device, env_offset)
-        if shuffle:
-            raise NotImplementedError("shuffle=True (per-episode re-randomised starts) is not built yet")
-        self.shuffle, self.agents_size = False, agents_size
+        self.shuffle, self.agents_size, self.seed = bool(shuffle), agents_size, int(seed)
         A, E, dev = self.n_agents, self.n_envs, self.device
         self.fieldview_size = self.size / (np.sqrt(A)) if fieldview_size is None else fieldview_size   # coverage.py:15-18
         self.state_space = 2 * A
@@ -60,6 +59,11 @@ class _CoverageFloat(BatchedEnv):
             self.ld, _lib.stream_ptr()))
 
 
+    def _draw_starts(self, episode):
+        zoom = getattr(self, "zoom_fac", None)
+        self._draw_float_starts(episode, 3 if zoom is not None else 2, zoom or 0.0)
+
+
 class BatchedCoverageContinuous(_CoverageFloat):
     """``CoverageContinuous(size, n_agents, shuffle, agents_size, fieldview_size, weights, coarseness)``
     (coverage.py:11) + ``n_envs``/``device``.  Actions are ``[n_envs, n_agents, 2]`` float32."""
@@ -68,11 +72,12 @@ class BatchedCoverageContinuous(_CoverageFloat):
     action_dtype = torch.float32
 
     def __init__(self, size, n_agents, n_envs=1, shuffle=False, agents_size=0.5, fieldview_size=None, weights=None,
-                 coarseness=None, device="cuda", starts=None, env_offset=0):
+                 coarseness=None, device="cuda", starts=None, env_offset=0, seed=0):
         self.action_rows = 2 * int(n_agents)
         if starts is None:
             starts = np.random.rand(int(n_envs), int(n_agents), 2) * size          # coverage.py:267
-        self._setup(size, n_agents, n_envs, device, env_offset, shuffle, agents_size, fieldview_size, weights, starts)
+        self._setup(size, n_agents, n_envs, device, env_offset, shuffle, agents_size, fieldview_size, weights, starts,
+                    seed)
         self.coarseness = coarseness
         max_norm = float(np.sqrt(2) * self.size / coarseness) if coarseness is not None else 0.0   # coverage.py:66
         self._params = _lib.CoverageFloatParams(self.size, self.n_agents, 0, int(coarseness is not None),
@@ -88,7 +93,7 @@ class BatchedCoverageDiscretized(_CoverageFloat):
     action_dtype = torch.uint8
 
     def __init__(self, size, n_agents, n_envs=1, coarseness=20, shuffle=False, agents_size=0.5, fieldview_size=None,
-                 weights=None, device="cuda", starts=None, env_offset=0):
+                 weights=None, device="cuda", starts=None, env_offset=0, seed=0):
         self.action_rows = int(n_agents)
         self.coarseness = coarseness
         self.zoom_fac = coarseness / size                                           # coverage.py:215
@@ -96,7 +101,8 @@ class BatchedCoverageDiscretized(_CoverageFloat):
             # the ctor builds (and discards) n_agents continuous agents first, coverage.py:19,:216
             draws = np.random.rand(int(n_envs), 2 * int(n_agents), 2)[:, int(n_agents):] * size
             starts = np.floor(draws * self.zoom_fac) / self.zoom_fac                # coverage.py:270-272
-        self._setup(size, n_agents, n_envs, device, env_offset, shuffle, agents_size, fieldview_size, weights, starts)
+        self._setup(size, n_agents, n_envs, device, env_offset, shuffle, agents_size, fieldview_size, weights, starts,
+                    seed)
         table = np.array([1, np.sqrt(2)]) * (self.size / coarseness)                # coverage.py:237
         self._params = _lib.CoverageFloatParams(self.size, self.n_agents, 1, 0, float(self.fieldview_size), 0.0,
                                                 float(self.zoom_fac), float(self.size * self.zoom_fac),
