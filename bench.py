@@ -220,7 +220,7 @@ def run_ours(a):
         if ev_b is not None:
             ev_b.record()
         _lib.check(lib.smarl_rollout_returns(C.byref(acc), P(buf.reward), P(buf.cost), buf.cost_code,
-                                             P(buf.penalty), P(buf.R), P(buf.modR), P(buf.Csum), P(buf.G),
+                                             P(buf.penalty), None, P(buf.R), P(buf.modR), P(buf.Csum), P(buf.G),
                                              P(buf.stats_vec), P(buf.stats_scratch), A, K, E, ld, stream))
         sd.allreduce_stats(buf.stats_vec)                       # the only inter-GPU traffic
         _lib.check(lib.smarl_lambda_update(P(meta.lambdas), P(buf.stats_vec), P(thr), 0.002, A, K, stream))

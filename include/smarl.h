@@ -115,7 +115,10 @@ typedef struct {
   int32_t n_steps;        /* T = max_t                             main.py:29               */
   int32_t g_mode;         /* what G holds: 0 none, 1 reward-to-go G_t = m_t + gamma G_{t+1}
                              (ACAgent.compute_returns agent.py:200-206), 2 gamma^t m_t
-                             (AbstractAgent.compute_returns agent.py:129-132)               */
+                             (AbstractAgent.compute_returns agent.py:129-132), 3 (returns kernel
+                             only) PPO's per-episode standardisation of mode 1,
+                             (G - mean) / (std_unbiased + 1e-7) over the episode's steps
+                             (PPOAgent.step agent.py:276-281; PPOAgent extends ACAgent)     */
   const double* thresholds; /* [K] device, for violation counts; NULL = skip  buffer.py:47  */
 } SmarlAccounting;
 
@@ -227,8 +230,8 @@ typedef struct {
  *   lx0,ly0,lx1,...   obs f32 [2A(+2L)][ld] (NULL ok) */
 int smarl_collision_reset(const SmarlCollisionParams* p, const double* start_x,
                           const double* start_y, const double* landmarks, double* pos_x,
-                          double* pos_y, uint8_t* done, float* obs, int64_t n_envs, int64_t ld,
-                          smarl_stream_t stream);
+                          double* pos_y, uint8_t* done, int32_t* episode_len, float* obs, int64_t n_envs,
+                          int64_t ld, smarl_stream_t stream);
 
 /* One CollisionAvoidance.step (:139-148 = transition :103-125 + reward :127-130/:158-162 +
  * constraint :132-133/:150-156 + check_done :135-136) with MetaAgent.act fused.  Envs whose
@@ -237,11 +240,13 @@ int smarl_collision_reset(const SmarlCollisionParams* p, const double* start_x,
  *   pos_x,pos_y f64 [A][ld] in/out   done u8 [A][ld] in/out
  *   actions f32 [2A][ld] rows dx0,dy0,dx1,... (the reference's policies emit fp32, agent.py:124-125)
  *   landmarks f64 [2L][ld]   obs f32 [2A(+2L)][ld]   reward f32 [A][ld]   cost i32 [ld]
- *   done_out u8 [A][ld]: this step's done flags for a rollout buffer (NULL ok) */
+ *   done_out u8 [A][ld]: this step's done flags for a rollout buffer (NULL ok)
+ *   episode_len i32 [ld] in/out (NULL ok): incremented for envs that were still running (reset zeroes it) */
 int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x, double* pos_y,
                          uint8_t* done, const float* actions, const double* landmarks, float* obs,
-                         float* reward, int32_t* cost, uint8_t* done_out, const double* lambdas,
-                         float* penalty, int64_t n_envs, int64_t ld, smarl_stream_t stream);
+                         float* reward, int32_t* cost, uint8_t* done_out, int32_t* episode_len,
+                         const double* lambdas, float* penalty, int64_t n_envs, int64_t ld,
+                         smarl_stream_t stream);
 
 /* Fused open-loop episode.  actions f32 [T][2A][ld].  n_active i32 [ld] out = episode length
  * T' (steps until all agents done, NULL ok).  C i32 [1][ld]. */
@@ -270,11 +275,12 @@ int smarl_rollout_penalty(const void* cost, int32_t cost_dtype, const double* la
  * and compute_returns (agent.py:129-132, :200-206) for n_envs episodes at once:
  *   R_a = sum_t gamma^t r[t,a]   modR_a = sum_t gamma^t (r[t,a] - pen[t])   C_k = sum_t c[t,k]
  *   reward f32 [T][A][ld]   cost [T][K][ld]   penalty f32 [T][ld] (NULL = 0)
+ *   n_active i32 [ld]: episode lengths T' (NULL = T); only g_mode 3 needs them (steps >= T' get 0)
  *   R, modR f32 [A][ld]     C i32 [K][ld]     G f32 [T][A][ld] per acc->g_mode
  *   stats/stats_scratch as above (NULL to skip). */
 int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const void* cost,
-                          int32_t cost_dtype, const float* penalty, float* R, float* modR,
-                          int32_t* C, float* G, double* stats, double* stats_scratch,
+                          int32_t cost_dtype, const float* penalty, const int32_t* n_active, float* R,
+                          float* modR, int32_t* C, float* G, double* stats, double* stats_scratch,
                           int32_t n_agents, int32_t n_constraints, int64_t n_envs, int64_t ld,
                           smarl_stream_t stream);
 

@@ -418,6 +418,24 @@ def discounted_terms(mod_rewards, gamma):
     return disc[:, None, None] * mod_rewards
 
 
+def ppo_standardised_returns(mod_rewards, gamma, n_active=None):
+    """PPOAgent.step (agent.py:276-281; PPOAgent extends ACAgent, so compute_returns is the
+    reward-to-go of :200-206): x_t = G_t over the episode's T' steps, then
+    (x - mean) / (std_unbiased + 1e-7); steps past T' are 0.  The reference does this in torch
+    float32; here float64.  mod_rewards [T, E, A] (zero past T'), n_active [E] or None -> [T, E, A]."""
+    x = reward_to_go(mod_rewards, gamma)
+    T, E, A = x.shape
+    n = np.full(E, T) if n_active is None else np.asarray(n_active)
+    live = (np.arange(T)[:, None] < n[None, :])[:, :, None]
+    xs = np.where(live, x, 0.0)
+    cnt = n[None, :, None].astype(np.float64)
+    mean = xs.sum(0, keepdims=True) / cnt
+    with np.errstate(invalid="ignore", divide="ignore"):
+        var = np.where(live, (x - mean) ** 2, 0.0).sum(0, keepdims=True) / (cnt - 1)
+        out = (x - mean) / (np.sqrt(var) + 1e-7)
+    return np.where(live, out, 0.0)
+
+
 def lambda_update(lambdas, mean_cost, thresholds, lr):
     """meta_agent.py:32-36 (leq=True): lambda <- max(0, lambda + lr * (mean C - thr))."""
     lam = np.asarray(lambdas, dtype=np.float64) + lr * (

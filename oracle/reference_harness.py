@@ -47,10 +47,10 @@ def load():
     import envs.collision_avoidance as collision
     from safe_multi_agent_RL.meta_agent import MetaAgent
     from safe_multi_agent_RL.buffer import Buffer
-    from safe_multi_agent_RL.agent import ACAgent, AbstractAgent
+    from safe_multi_agent_RL.agent import ACAgent, AbstractAgent, PPOAgent
     _ns = types.SimpleNamespace(coverage=coverage, congestion=congestion, collision=collision,
                                 MetaAgent=MetaAgent, Buffer=Buffer, ACAgent=ACAgent,
-                                AbstractAgent=AbstractAgent)
+                                AbstractAgent=AbstractAgent, PPOAgent=PPOAgent)
     return _ns
 
 
@@ -212,3 +212,16 @@ def run_accounting(rewards, costs, lambdas0, gamma, thresholds, meta_lr, n_steps
     return dict(mod_reward=_f64(mods), R=_f64(buf.scores[-1]), modR=_f64(buf.modified_scores[-1]),
                 C=_f64(buf.constraints[-1]), G=G, disc=disc, lambdas_after=_f64(meta.lambdas),
                 mean_violation=_f64(mean_sc[2]))
+
+
+def run_ppo_returns(mod_rewards, gamma):
+    """The reference's PPOAgent.step (agent.py:276-281) on one agent's modified rewards [T'] ->
+    standardised discounted terms [T'] (torch float32).  The agent object is created without
+    __init__ (no networks needed): step() only touches rewards / gamma / returns."""
+    ref = load()
+    agent = object.__new__(ref.PPOAgent)
+    agent.rewards = [float(v) for v in mod_rewards]
+    agent.gamma = gamma
+    agent.returns = []
+    agent.step()
+    return np.asarray([float(v) for v in agent.returns], dtype=np.float64)

@@ -64,14 +64,14 @@ PROTOTYPES = {
                                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                            c_ptr, i64, i64, c_ptr]),
     "smarl_collision_reset": (C.c_int, [P(CollisionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                        c_ptr, i64, i64, c_ptr]),
+                                        c_ptr, c_ptr, i64, i64, c_ptr]),
     "smarl_collision_step": (C.c_int, [P(CollisionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                       c_ptr, c_ptr, c_ptr, c_ptr, i64, i64, c_ptr]),
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i64, i64, c_ptr]),
     "smarl_collision_rollout": (C.c_int, [P(CollisionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
                                           c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                           c_ptr, c_ptr, c_ptr, i64, i64, c_ptr]),
     "smarl_rollout_penalty": (C.c_int, [c_ptr, i32, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
-    "smarl_rollout_returns": (C.c_int, [P(Accounting), c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr,
+    "smarl_rollout_returns": (C.c_int, [P(Accounting), c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
     "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64]),

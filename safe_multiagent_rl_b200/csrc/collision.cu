@@ -26,6 +26,7 @@ struct CollisionStepArgs {
   float* reward;
   int32_t* cost;
   uint8_t* done_out;
+  int32_t* episode_len;
   const double* lambdas;
   float* penalty;
   int64_t n_envs;
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const Coll
     for (int l = 0; l < 2 * a.L; ++l) a.obs[(2 * A + l) * ld + e] = (float)a.landmarks[l * ld + e];
   }
   a.cost[e] = collisions;
+  if (a.episode_len && active) a.episode_len[e] += 1;
   if (a.penalty) a.penalty[e] = (float)(__ldg(a.lambdas) * (double)collisions);   // meta_agent.py:21-22
 }
 
@@ -320,10 +322,11 @@ int launch_collision_rollout(int A, const CollisionRolloutArgs& a, unsigned grid
 __global__ void collision_reset_kernel(const double* __restrict__ start_x, const double* __restrict__ start_y,
                                        const double* __restrict__ landmarks, double* __restrict__ pos_x,
                                        double* __restrict__ pos_y, uint8_t* __restrict__ done,
-                                       float* __restrict__ obs, int A, int L, int obs_landmarks,
-                                       int64_t n_envs, int64_t ld) {
+                                       int32_t* __restrict__ episode_len, float* __restrict__ obs, int A, int L,
+                                       int obs_landmarks, int64_t n_envs, int64_t ld) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_envs) return;
+  if (episode_len) episode_len[e] = 0;
   for (int i = 0; i < A; ++i) {
     const double x = start_x[i * ld + e], y = start_y[i * ld + e];
     pos_x[i * ld + e] = x;
@@ -355,15 +358,15 @@ using namespace smarl;
 #if SMARL_TU_IS(2)
 extern "C" int smarl_collision_reset(const SmarlCollisionParams* p, const double* start_x,
                                      const double* start_y, const double* landmarks, double* pos_x,
-                                     double* pos_y, uint8_t* done, float* obs, int64_t n_envs, int64_t ld,
-                                     smarl_stream_t stream) {
+                                     double* pos_y, uint8_t* done, int32_t* episode_len, float* obs,
+                                     int64_t n_envs, int64_t ld, smarl_stream_t stream) {
   if (int rc = check_collision(p)) return rc;
   if (int rc = check_layout(n_envs, ld)) return rc;
   SMARL_REQUIRE(start_x && start_y && landmarks && pos_x && pos_y && done, "null required pointer");
   SMARL_REQUIRE(p->n_agents >= 1 && p->n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", p->n_agents);
   const unsigned grid = (unsigned)((n_envs + 255) / 256);
   collision_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(start_x, start_y, landmarks, pos_x, pos_y,
-                                                                 done, obs, p->n_agents, p->n_landmarks,
+                                                                 done, episode_len, obs, p->n_agents, p->n_landmarks,
                                                                  p->obs_landmarks, n_envs, ld);
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;
@@ -372,15 +375,16 @@ extern "C" int smarl_collision_reset(const SmarlCollisionParams* p, const double
 extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x, double* pos_y,
                                     uint8_t* done, const float* actions, const double* landmarks,
                                     float* obs, float* reward, int32_t* cost, uint8_t* done_out,
-                                    const double* lambdas, float* penalty, int64_t n_envs, int64_t ld,
-                                    smarl_stream_t stream) {
+                                    int32_t* episode_len, const double* lambdas, float* penalty,
+                                    int64_t n_envs, int64_t ld, smarl_stream_t stream) {
   if (int rc = check_collision(p)) return rc;
   if (int rc = check_layout(n_envs, ld)) return rc;
   SMARL_REQUIRE(pos_x && pos_y && done && actions && landmarks && reward && cost, "null required pointer");
   SMARL_REQUIRE((lambdas == nullptr) == (penalty == nullptr), "lambdas and penalty go together");
   CollisionStepArgs a;
   a.pos_x = pos_x; a.pos_y = pos_y; a.done = done; a.actions = actions; a.landmarks = landmarks;
-  a.obs = obs; a.reward = reward; a.cost = cost; a.done_out = done_out; a.lambdas = lambdas;
+  a.obs = obs; a.reward = reward; a.cost = cost; a.done_out = done_out; a.episode_len = episode_len;
+  a.lambdas = lambdas;
   a.penalty = penalty; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size;
   a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
   const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);

@@ -92,6 +92,7 @@ struct ReturnsArgs {
   const float* reward;     // [T][A][ld]
   const void* cost;        // [T][K][ld]
   const float* penalty;    // [T][ld] or NULL
+  const int32_t* n_active; // [ld] or NULL
   float* R;
   float* modR;
   int32_t* C;
@@ -126,7 +127,56 @@ __global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs 
   if (row < a.A) {
     double raw[4] = {0, 0, 0, 0}, mod[4] = {0, 0, 0, 0};
     const double gamma = a.gamma;
-    if (a.g_mode != 2) {
+    if (a.g_mode == 3) {
+      // PPO (agent.py:276-281; PPOAgent extends ACAgent, so compute_returns is the reward-to-go of
+      // :200-206): x_t = G_t over the episode's T' steps, then (x - mean) / (std_unbiased + 1e-7).
+      // Sweep 1 (backward Horner): G_t, their sum and sum of squares (G_0 = modR); sweep 2: write.
+      int n_act[4] = {T, T, T, T};
+      if (a.n_active) {
+        int c[4];
+        CostVec<int32_t>::load(a.n_active + e0, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n_act[k] = min(max(c[k], 0), T);
+      }
+      double sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+      for (int t = T - 1; t >= 0; --t) {
+        const float4 r = ld_stream_f4(a.reward + ((int64_t)t * a.A + row) * ld + e0);
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+        const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          raw[k] = (double)rr[k] + gamma * raw[k];
+          mod[k] = ((double)rr[k] - (double)pp[k]) + gamma * mod[k];
+          if (t < n_act[k]) {
+            sum[k] += mod[k];
+            sq[k] += mod[k] * mod[k];
+          }
+        }
+      }
+      double mean[4], inv[4], run[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double n = (double)n_act[k];
+        mean[k] = sum[k] / n;
+        const double var = (sq[k] - n * mean[k] * mean[k]) / (n - 1.0);
+        inv[k] = 1.0 / (sqrt(fmax(var, 0.0)) + 1e-7);
+        if (n_act[k] < 2) inv[k] = __longlong_as_double(0x7ff8000000000000ll);   // torch: std of one sample is nan
+      }
+      for (int t = T - 1; t >= 0; --t) {
+        const float4 r = ld_stream_f4(a.reward + ((int64_t)t * a.A + row) * ld + e0);
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+        const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          run[k] = ((double)rr[k] - (double)pp[k]) + gamma * run[k];
+          o[k] = t < n_act[k] ? (float)((run[k] - mean[k]) * inv[k]) : 0.f;
+        }
+        if (live) st_stream_f4(a.G + ((int64_t)t * a.A + row) * ld + e0, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    } else if (a.g_mode != 2) {
       // Backward Horner: G_t = m_t + gamma G_{t+1} (agent.py:200-206); G_0 is the discounted
       // episode return of buffer.py:31-35.
 #pragma unroll 4
@@ -301,14 +351,15 @@ extern "C" int smarl_rollout_penalty(const void* cost, int32_t cost_dtype, const
 }
 
 extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const void* cost,
-                                     int32_t cost_dtype, const float* penalty, float* R, float* modR,
-                                     int32_t* C, float* G, double* stats, double* stats_scratch,
+                                     int32_t cost_dtype, const float* penalty, const int32_t* n_active,
+                                     float* R, float* modR, int32_t* C, float* G, double* stats,
+                                     double* stats_scratch,
                                      int32_t n_agents, int32_t n_constraints, int64_t n_envs,
                                      int64_t ld, smarl_stream_t stream) {
   if (int rc = check_layout(n_envs, ld)) return rc;
   SMARL_REQUIRE(acc != nullptr, "accounting params is NULL");
   SMARL_REQUIRE(acc->n_steps >= 1, "n_steps=%d must be >= 1", acc->n_steps);
-  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 2, "bad g_mode %d", acc->g_mode);
+  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 3, "bad g_mode %d", acc->g_mode);
   SMARL_REQUIRE(n_agents >= 1 && n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", n_agents);
   SMARL_REQUIRE(n_constraints >= 1 && n_constraints <= SMARL_MAX_AGENTS, "n_constraints=%d outside 1..32",
                 n_constraints);
@@ -318,7 +369,7 @@ extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* re
   SMARL_REQUIRE(aligned16(reward) && aligned16(cost) && aligned16(penalty) && aligned16(R) &&
                     aligned16(modR) && aligned16(C) && aligned16(G), "pointers must be 16-byte aligned");
   ReturnsArgs a;
-  a.reward = reward; a.cost = cost; a.penalty = penalty; a.R = R; a.modR = modR; a.C = C; a.G = G;
+  a.reward = reward; a.cost = cost; a.penalty = penalty; a.n_active = n_active; a.R = R; a.modR = modR; a.C = C; a.G = G;
   a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma;
   a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
   a.A = n_agents; a.K = n_constraints; a.T = acc->n_steps; a.g_mode = acc->g_mode;

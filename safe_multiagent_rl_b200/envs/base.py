@@ -149,7 +149,7 @@ class BatchedEnv:
             actions = policy(obs, t)
             agent_major = isinstance(actions, torch.Tensor) and actions.data_ptr() == self.action_buffer.data_ptr()
             obs, _, _, _ = self.step(actions, lambdas=lambdas, out=(buf, t), agent_major=agent_major)
-        out = buf.finish(gamma, thresholds, g_mode)
+        out = buf.finish(gamma, thresholds, g_mode, n_active=getattr(self, "episode_len", None))
         out["buffer"] = buf
         return out
 

@@ -62,6 +62,7 @@ class BatchedCollisionAvoidance(BatchedEnv):
         self.landmarks[:, :E] = torch.as_tensor(landmarks.reshape(E, 2 * self.L).T.copy()).to(dev)
         self.pos_x, self.pos_y = self.start_x.clone(), self.start_y.clone()
         self.agent_done = self._alloc(A, torch.uint8)
+        self.episode_len = self._alloc(1, torch.int32)[0]          # steps taken before all agents were done
         self.action_buffer = self._alloc(2 * A, torch.float32)  # rows dx0, dy0, dx1, ...
         if self.shuffle:
             self.state_space += 2 * self.L                       # landmarks are part of the state (:65-68)
@@ -87,14 +88,15 @@ class BatchedCollisionAvoidance(BatchedEnv):
     def _reset_impl(self):
         _lib.check(self.lib.smarl_collision_reset(
             C.byref(self._params), _lib.ptr(self.start_x), _lib.ptr(self.start_y), _lib.ptr(self.landmarks),
-            _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done), _lib.ptr(self.obs),
-            self.n_envs, self.ld, _lib.stream_ptr()))
+            _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done), _lib.ptr(self.episode_len),
+            _lib.ptr(self.obs), self.n_envs, self.ld, _lib.stream_ptr()))
 
     def _step_impl(self, act, reward, cost, done, lambdas, penalty):
         _lib.check(self.lib.smarl_collision_step(
             C.byref(self._params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done),
             _lib.ptr(act), _lib.ptr(self.landmarks), _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost),
-            _lib.ptr(done), _lib.ptr(lambdas), _lib.ptr(penalty), self.n_envs, self.ld, _lib.stream_ptr()))
+            _lib.ptr(done), _lib.ptr(self.episode_len), _lib.ptr(lambdas), _lib.ptr(penalty), self.n_envs, self.ld,
+            _lib.stream_ptr()))
 
     def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None):
         """Open-loop fused episode (one launch).  actions ``[T, 2*n_agents, ld]`` float32 (kernel layout,

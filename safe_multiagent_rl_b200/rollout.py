@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .layout import alloc, env_major, pad_ld
 
-G_NONE, G_REWARD_TO_GO, G_DISCOUNTED_TERMS = 0, 1, 2
+G_NONE, G_REWARD_TO_GO, G_DISCOUNTED_TERMS, G_PPO_STANDARDISED = 0, 1, 2, 3
 
 
 class Stats:
@@ -102,8 +102,10 @@ class RolloutBuffer:
     def costs(self):
         return env_major(self.cost, self.E)                  # [T, E, K]
 
-    def finish(self, gamma, thresholds=None, g_mode=None):
-        """Buffer.step for all envs: returns dict(R [E,A], modR [E,A], C [E,K], G [T,E,A] | None, stats)."""
+    def finish(self, gamma, thresholds=None, g_mode=None, n_active=None):
+        """Buffer.step for all envs: returns dict(R [E,A], modR [E,A], C [E,K], G [T,E,A] | None, stats).
+        ``n_active`` (i32 [ld] episode lengths, e.g. the Collision env's ``episode_len``) is only needed by
+        ``G_PPO_STANDARDISED`` when episodes can end early."""
         lib = _lib.load()
         g_mode = self.g_mode if g_mode is None else g_mode
         if g_mode != G_NONE and self.G is None:
@@ -112,7 +114,7 @@ class RolloutBuffer:
         acc = make_accounting(gamma, self.T, g_mode, thr)
         _lib.check(lib.smarl_rollout_returns(
             C.byref(acc), _lib.ptr(self.reward), _lib.ptr(self.cost), self.cost_code, _lib.ptr(self.penalty),
-            _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum), _lib.ptr(self.G if g_mode else None),
+            _lib.ptr(n_active), _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum), _lib.ptr(self.G if g_mode else None),
             _lib.ptr(self.stats_vec), _lib.ptr(self.stats_scratch), self.A, self.K, self.E, self.ld,
             _lib.stream_ptr()))
         return dict(R=env_major(self.R, self.E), modR=env_major(self.modR, self.E),

@@ -462,3 +462,47 @@ def test_coverage_discretized_matches_oracle(size, A, E, T, coarse, seed):
         assert np.array_equal(env.state().cpu().numpy(), pos)
         assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))
         assert np.array_equal(c.cpu().numpy(), c_o.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- PPO standardised returns
+def test_ppo_standardised_returns_coverage_and_collision():
+    """g_mode 3 of the returns kernel (PPOAgent.step, agent.py:276-281), incl. early-ending
+    Collision episodes whose length comes from the env's episode_len counter."""
+    s = smarl()
+    # Coverage: every episode runs T steps
+    size, A, E, T, fv, seed = COVERAGE_CASES[0]
+    starts, actions, weights, lut = coverage_setup(size, A, E, T, fv, seed)
+    env = s.BatchedCoverageDiscrete(size, A, n_envs=E, weights=weights, starts=starts)
+    lam_np = np.array([0.1, 0.2, 0.3])
+    pos = starts.copy()
+    def step_fn(t):
+        nonlocal pos
+        pos, r, c, _ = no.coverage_discrete_step(pos, actions[t], size, lut, weights)
+        return r, c
+    want = no.rollout(step_fn, T, 0.999, lam_np)
+    act = torch.as_tensor(actions.astype(np.uint8), device="cuda")
+    out = env.rollout_closed_loop(lambda obs, t: act[t], T, torch.as_tensor(lam_np, device="cuda"), 0.999,
+                                  g_mode=s.G_PPO_STANDARDISED)
+    close(out["G"].cpu().numpy(), no.ppo_standardised_returns(want["mod_reward"], 0.999), 1.0, rtol=2e-5)
+    close(out["modR"].cpu().numpy(), want["modR"], np.abs(want["modR"]).max())
+    # Collision: a quarter of the episodes end early
+    size, A, L, E, T, seed = COLLISION_CASES[0]
+    starts, landmarks, actions = collision_setup(size, A, L, E, T, seed)
+    env = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=L, starts=starts, landmarks=landmarks)
+    pos, done = starts.copy(), np.zeros((E, A), dtype=bool)
+    n_active = np.zeros(E, dtype=np.int64)
+    def step_fn2(t):
+        nonlocal pos, done, n_active
+        pos, r, c, done, active = no.collision_step(pos, done, actions[t].astype(np.float64), landmarks, size)
+        n_active += active
+        return r.astype(np.float32).astype(np.float64), c
+    want = no.rollout(step_fn2, T, 0.99, [0.5])
+    act = torch.as_tensor(actions, device="cuda")
+    out = env.rollout_closed_loop(lambda obs, t: act[t], T, torch.as_tensor([0.5], dtype=torch.float64, device="cuda"),
+                                  0.99, g_mode=s.G_PPO_STANDARDISED)
+    assert np.array_equal(env.episode_len[:E].cpu().numpy(), n_active) and (n_active < T).any()
+    ok = n_active >= 2
+    got = out["G"].cpu().numpy()
+    ref = no.ppo_standardised_returns(want["mod_reward"], 0.99, n_active)
+    close(got[:, ok], ref[:, ok], 1.0, rtol=2e-5)
+    assert np.isnan(got[0, n_active == 1]).all()            # torch: the std of a single sample is nan

@@ -206,3 +206,12 @@ def test_coverage_discretized_matches_reference(size, A, T, coarse, seed):
             assert np.array_equal(pos[0], tr["pos"][t])
             assert np.array_equal(r[0], tr["reward"][t])
             assert np.array_equal(c[0], tr["cost"][t])
+
+
+def test_ppo_standardised_returns_match_reference():
+    rng = np.random.default_rng(0)
+    for T, gamma in [(50, 0.999), (8, 0.99), (100, 0.9), (2, 0.5)]:
+        m = rng.normal(-3, 4, size=T)
+        want = rh.run_ppo_returns(m, gamma)                          # torch float32
+        got = no.ppo_standardised_returns(m[:, None, None], gamma)[:, 0, 0]
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
