@@ -38,7 +38,7 @@ UNIT = "agent-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n_envs", type=int, default=1 << 22, help="envs per GPU")
@@ -108,7 +108,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -344,6 +344,19 @@ def run_ours(a):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{a.cpu_seconds:.0f}s of whole episodes of the same env config, one env per process on "
                          f"{cores} processes (oracle/scalar_port.py: env.step + MetaAgent.act + Buffer + reward-to-go)"}
+        try:                                       # extra: the plain-C oracle (pthreads) on a 2^16-env slice
+            from oracle import c_oracle as co
+            from oracle import numpy_oracle as no
+            n = 1 << 16
+            lut64 = no.coverage_penalty_lut(S, no.coverage_fieldview(S, A))
+            sx, sy = env.start_x[:, :n].cpu().numpy(), env.start_y[:, :n].cpu().numpy()
+            act = actions[:, :, :n].cpu().numpy()
+            t0 = time.perf_counter()
+            co.coverage_rollout(S, sx, sy, act, lut64, np.asarray(weights), np.full(A, 0.1), a.gamma, n)
+            cpu["c_oracle"] = {"value": n * A * T / (time.perf_counter() - t0), "unit": UNIT, "threads": co.num_threads(),
+                               "sample": "oracle/c/oracle.c fused rollout of 65536 envs (batched C, not the reference's execution model)"}
+        except Exception as ex:                    # the C oracle is optional test infrastructure
+            cpu["c_oracle"] = {"error": str(ex)[:200]}
 
     if rank == 0:
         print(json.dumps({

@@ -138,6 +138,26 @@ __device__ __forceinline__ void grid_move4(uint32_t& xw, uint32_t& yw, uint32_t 
   xw = __vsubus4(__vminu4(xw + inc_x, size4), dec_x);
   yw = __vsubus4(__vminu4(yw + inc_y, size4), dec_y);
 }
+// Same move for grids with size <= 127 (Coverage): with the top bit of every byte free, per-byte
+// comparisons are carry-free adds -- bit 7 of (x + 128 - S) is [x >= S], bit 7 of (x + 127) is
+// [x >= 1] -- so the clamp costs 7 plain integer ops per coordinate word instead of the emulated
+// SIMD min / saturating-subtract intrinsics.  ge_bias = (128 - S) * 0x01010101.
+__device__ __forceinline__ void grid_move4_s127(uint32_t& xw, uint32_t& yw, uint32_t aw, uint32_t ge_bias) {
+  const uint32_t k1 = 0x01010101u, k7f = 0x7F7F7F7Fu;
+  const uint32_t b0 = aw & k1, b1 = (aw >> 1) & k1, b2 = (aw >> 2) & k1;
+  const uint32_t inc_x = (b0 | b1 | b2) ^ k1;   // a == 0
+  const uint32_t dec_x = b0 & ~b1;              // a == 1
+  const uint32_t dec_y = b1 & ~b0;              // a == 2
+  const uint32_t inc_y = b0 & b1;               // a == 3
+  xw = xw + (inc_x & ~((xw + ge_bias) >> 7)) - (dec_x & ((xw + k7f) >> 7));
+  yw = yw + (inc_y & ~((yw + ge_bias) >> 7)) - (dec_y & ((yw + k7f) >> 7));
+}
+// p += lam where bit (mask) of w is set: one predicate-producing LOP3 + one predicated DADD.
+__device__ __forceinline__ void add_if_bit(double& p, double lam, uint32_t w, uint32_t mask) {
+  asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}"
+      : "+d"(p)
+      : "d"(lam), "r"(w), "r"(mask));
+}
 // cost byte = 1 for a non-stay action (coverage.py:191-196: [1,1,1,1,0][a]).
 __device__ __forceinline__ uint32_t move_cost4(uint32_t aw) { return ((aw >> 2) & 0x01010101u) ^ 0x01010101u; }
 

@@ -96,13 +96,13 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
       aw[i] = ld_stream_u32(a.actions + off);
     }
   }
-  const uint32_t size4 = (uint32_t)a.size * 0x01010101u;
+  const uint32_t ge_bias = (uint32_t)(128 - a.size) * 0x01010101u;
   double pen[4] = {0.0, 0.0, 0.0, 0.0};
   {
     uint32_t off = e0, obs_off = e0;
 #pragma unroll
     for (int i = 0; i < A; ++i, off += ld, obs_off += 2u * ld) {
-      grid_move4(xw[i], yw[i], aw[i], size4);              // coverage.py:174-189
+      grid_move4_s127(xw[i], yw[i], aw[i], ge_bias);       // coverage.py:174-189
       const uint32_t cw = move_cost4(aw[i]);               // coverage.py:191-196
       st_stream_u32(a.pos_x + off, xw[i]);
       st_stream_u32(a.pos_y + off, yw[i]);
@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
       if (a.penalty) {                                      // meta_agent.py:21-22
         const double lam = __ldg(a.lambdas + i);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if ((cw >> (8 * k)) & 1u) pen[k] += lam;
+        for (int k = 0; k < 4; ++k) add_if_bit(pen[k], lam, cw, 1u << (8 * k));
       }
     }
   }
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
     cnt[i] = 0u;
     lam[i] = a.lambdas ? __ldg(a.lambdas + i) : 0.0;
   }
-  const uint32_t size4 = (uint32_t)a.size * 0x01010101u;
+  const uint32_t ge_bias = (uint32_t)(128 - a.size) * 0x01010101u;
   double s_rew[4] = {0, 0, 0, 0}, s_pen[4] = {0, 0, 0, 0};
   double disc = 1.0;
 
@@ -190,12 +189,11 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
     double pen[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      grid_move4(xw[i], yw[i], aw[i], size4);
+      grid_move4_s127(xw[i], yw[i], aw[i], ge_bias);
       const uint32_t cw = move_cost4(aw[i]);
       cnt[i] += cw;                                   // four byte counters, T <= 255
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if ((cw >> (8 * k)) & 1u) pen[k] += lam[i];
+      for (int k = 0; k < 4; ++k) add_if_bit(pen[k], lam[i], cw, 1u << (8 * k));
     }
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll 1
@@ -289,7 +287,7 @@ __global__ void __launch_bounds__(kRolloutThreads) coverage_rollout_kernel(const
     }
     const double b_rew = block_sum<kRolloutThreads>(v_rew, s_red);
     const double b_pen = block_sum<kRolloutThreads>(v_pen, s_red);
-#pragma unroll 1
+#pragma unroll      // keep cnt[] statically indexed: a rolled loop would push the counters into local memory
     for (int i = 0; i < A; ++i) {
       double c = 0.0, viol = 0.0;
       const double thr = a.thresholds ? __ldg(a.thresholds + i) : 0.0;

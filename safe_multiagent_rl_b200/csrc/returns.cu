@@ -5,6 +5,7 @@
 // compute_returns (agent.py:129-132, :200-206).  All sums are carried in f64 like the
 // reference; only the stored products are f32.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "stats.cuh"
 
@@ -38,6 +39,7 @@ int sm_count() {
 }
 
 constexpr int kAccThreads = 128;
+constexpr int kReturnsThreads = 128;   // default CTA size of returns_kernel (>= 64: stats scratch rows are sized for 64)
 
 template <typename CT> struct CostVec;
 template <> struct CostVec<float> {   // float costs are summed in f64 like the reference and stored as f32
@@ -108,13 +110,15 @@ struct ReturnsArgs {
 
 // One CTA = one row (agent a, or constraint k) x 512 envs.  Rows of the same env chunk get
 // consecutive block ids so that they run together and share the chunk's penalty rows in L2.
-template <typename CT>
-__global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs a) {
-  __shared__ double s_red[kAccThreads / 32];
+// GM = 1 serves g_mode 0 and 1 (backward Horner, G written iff g_mode == 1), 2 and 3 their own paths;
+// a template parameter so that the PPO path's extra registers do not cut the occupancy of the others.
+template <typename CT, int THREADS, int GM>
+__global__ void __launch_bounds__(THREADS) returns_kernel(const ReturnsArgs a) {
+  __shared__ double s_red[THREADS / 32];
   const int rows = a.A + a.K;
   const int row = blockIdx.x % rows;
   const int64_t chunk = blockIdx.x / rows;
-  const int64_t g = chunk * kAccThreads + threadIdx.x;
+  const int64_t g = chunk * THREADS + threadIdx.x;
   const bool live = g < a.n_groups;
   const int64_t e0 = (live ? g : 0) * 4;
   const int64_t ld = a.ld;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs 
   if (row < a.A) {
     double raw[4] = {0, 0, 0, 0}, mod[4] = {0, 0, 0, 0};
     const double gamma = a.gamma;
-    if (a.g_mode == 3) {
+    if (GM == 3) {
       // PPO (agent.py:276-281; PPOAgent extends ACAgent, so compute_returns is the reward-to-go of
       // :200-206): x_t = G_t over the episode's T' steps, then (x - mean) / (std_unbiased + 1e-7).
       // Sweep 1 (backward Horner): G_t, their sum and sum of squares (G_0 = modR); sweep 2: write.
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs 
         }
         if (live) st_stream_f4(a.G + ((int64_t)t * a.A + row) * ld + e0, make_float4(o[0], o[1], o[2], o[3]));
       }
-    } else if (a.g_mode != 2) {
+    } else if (GM != 2) {
       // Backward Horner: G_t = m_t + gamma G_{t+1} (agent.py:200-206); G_0 is the discounted
       // episode return of buffer.py:31-35.
 #pragma unroll 4
@@ -227,8 +231,8 @@ __global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs 
         v_raw += valid[k] ? raw[k] : 0.0;
         v_mod += valid[k] ? mod[k] : 0.0;
       }
-      const double b_raw = block_sum<kAccThreads>(v_raw, s_red);
-      const double b_mod = block_sum<kAccThreads>(v_mod, s_red);
+      const double b_raw = block_sum<THREADS>(v_raw, s_red);
+      const double b_mod = block_sum<THREADS>(v_mod, s_red);
       if (threadIdx.x == 0) {
         out[2 * a.K + row] = b_raw;
         out[2 * a.K + a.A + row] = b_mod;
@@ -256,8 +260,8 @@ __global__ void __launch_bounds__(kAccThreads) returns_kernel(const ReturnsArgs 
         c += valid[j] ? (double)sum[j] : 0.0;
         viol += (valid[j] && a.thresholds && (double)sum[j] > thr) ? 1.0 : 0.0;
       }
-      const double bc = block_sum<kAccThreads>(c, s_red);
-      const double bv = block_sum<kAccThreads>(viol, s_red);
+      const double bc = block_sum<THREADS>(c, s_red);
+      const double bv = block_sum<THREADS>(viol, s_red);
       if (threadIdx.x == 0) {
         out[k] = bc;
         out[a.K + k] = bv;
@@ -373,17 +377,27 @@ extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* re
   a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma;
   a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
   a.A = n_agents; a.K = n_constraints; a.T = acc->n_steps; a.g_mode = acc->g_mode;
-  const int64_t n_chunks = (a.n_groups + kAccThreads - 1) / kAccThreads;
+  constexpr int threads = kReturnsThreads;
+  const int64_t n_chunks = (a.n_groups + threads - 1) / threads;
   const int64_t blocks = n_chunks * (n_agents + n_constraints);
   SMARL_REQUIRE(blocks <= 0x7fffffffLL, "too many blocks");
-  if (cost_dtype == SMARL_COST_U8)
-    returns_kernel<uint8_t><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
-  else if (cost_dtype == SMARL_COST_I32)
-    returns_kernel<int32_t><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
-  else if (cost_dtype == SMARL_COST_F32)
-    returns_kernel<float><<<(unsigned)blocks, kAccThreads, 0, (cudaStream_t)stream>>>(a);
-  else
+  cudaStream_t st = (cudaStream_t)stream;
+#define SMARL_LAUNCH_RETURNS(CT_)                                                                     \
+  switch (acc->g_mode) {                                                                              \
+    case 2: returns_kernel<CT_, threads, 2><<<(unsigned)blocks, threads, 0, st>>>(a); break;          \
+    case 3: returns_kernel<CT_, threads, 3><<<(unsigned)blocks, threads, 0, st>>>(a); break;          \
+    default: returns_kernel<CT_, threads, 1><<<(unsigned)blocks, threads, 0, st>>>(a); break;         \
+  }
+  if (cost_dtype == SMARL_COST_U8) {
+    SMARL_LAUNCH_RETURNS(uint8_t)
+  } else if (cost_dtype == SMARL_COST_I32) {
+    SMARL_LAUNCH_RETURNS(int32_t)
+  } else if (cost_dtype == SMARL_COST_F32) {
+    SMARL_LAUNCH_RETURNS(float)
+  } else {
     SMARL_REQUIRE(false, "bad cost_dtype %d", cost_dtype);
+  }
+#undef SMARL_LAUNCH_RETURNS
   SMARL_CUDA(cudaGetLastError());
   if (stats)
     return launch_stats_finalize(stats_scratch, n_chunks, n_agents, n_constraints, n_envs, stats,
