@@ -34,6 +34,17 @@ sys.path.insert(0, ROOT)
 METRIC = "agent-steps/sec (env step+cost+returns)"
 UNIT = "agent-steps/s"
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) also
+# write to fd 1, so keep a private handle on the real stdout for the result line and point fd 1 at
+# stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -84,7 +95,7 @@ def run_reference(a):
     v = statistics.mean(rates)
     sample = (f"{a.steps} x {per_step:.1f}s of whole episodes (env.step + MetaAgent.act + Buffer.append/step + "
               f"reward-to-go) on {cores} processes, one env each, recorded random actions")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -92,7 +103,7 @@ def run_reference(a):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,6 +191,8 @@ def run_ours(a):
     from safe_multiagent_rl_b200.rollout import make_accounting
 
     rank, world, local_rank = sd.init_from_env()
+    if world > 1:
+        sd.bind_to_gpu_numa(local_rank)
     if world != a.gpus and world > 1:
         a.gpus = world
     torch.cuda.set_device(local_rank)
@@ -341,7 +354,9 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, cores = cpu_rate(a, a.cpu_seconds)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        from oracle import scalar_port as sp
+        one_steps, one_el = sp.time_episodes("coverage", a.size, a.n_agents, a.max_t, a.gamma, 2.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "one_core": one_steps / one_el,
                "sample": f"{a.cpu_seconds:.0f}s of whole episodes of the same env config, one env per process on "
                          f"{cores} processes (oracle/scalar_port.py: env.step + MetaAgent.act + Buffer + reward-to-go)"}
         try:                                       # extra: the plain-C oracle (pthreads) on a 2^16-env slice
@@ -359,7 +374,7 @@ def run_ours(a):
             cpu["c_oracle"] = {"error": str(ex)[:200]}
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
@@ -368,7 +383,7 @@ def run_ours(a):
                        "agent_steps_per_step": world * agent_steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
             "roofline": roofline, "cpu_baseline": cpu, "fused": fused,
-        }))
+        })
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

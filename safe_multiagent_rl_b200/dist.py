@@ -26,6 +26,27 @@ def init_from_env(backend=None):
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Best effort: pin this process to the CPU cores NVML reports as local to its GPU, so that
+    pinned host staging buffers (first touch) and the copy threads live on the GPU's NUMA node.
+    Only matters for the host-buffer (PCIe) path when several ranks share one box."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return True
+    except Exception:
+        pass
+    return False
+
+
 def shard_range(n_envs_total: int, rank: int, world: int):
     """Contiguous env-id range [offset, offset + count) owned by ``rank``.  Ranges differ by at
     most one env and concatenate to [0, n_envs_total); env ids key the Philox noise stream, so
