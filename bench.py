@@ -306,7 +306,7 @@ def run_ours(a):
         del buf
         torch.cuda.empty_cache()
         sess = C.c_void_p()
-        _lib.check(lib.smarl_host_session_create(C.byref(sess), A, K, T, E))
+        _lib.check(lib.smarl_host_session_create(C.byref(sess), _lib.ENV_COVERAGE, A, T, E, 0))
         assert lib.smarl_host_session_ld(sess) == ld
         pin = dict(pin_memory=True)
         actions_h = torch.empty((T, A, ld), dtype=torch.uint8, **pin).copy_(actions)

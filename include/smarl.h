@@ -223,6 +223,8 @@ typedef struct {
   int32_t n_landmarks;   /* L >= 1                               collision_avoidance.py:62,101  */
   int32_t obs_landmarks; /* 1: obs has 2L extra rows (shuffle=True layout, :65-68,:141-142)    */
   double agents_size;    /* 0.25: reach radius, 2x = collision distance   :49,:123,:155        */
+  int32_t normalize_state; /* 1: obs = state / size (_normalize_state, :87-88,:146-147,:164-165)  */
+  int32_t reserved;
 } SmarlCollisionParams;
 
 /* CollisionAvoidance.reset/_restart (:72-98) for shuffle=False: state <- start, done <- 0.
@@ -298,21 +300,40 @@ int smarl_lambda_update(double* lambdas, const double* stats, const double* thre
  * products are in the host arrays.  Synchronous; one call at a time per session.
  * ---------------------------------------------------------------------------------- */
 typedef struct SmarlHostSession SmarlHostSession;   /* opaque: streams + device buffers */
+enum { SMARL_ENV_COVERAGE = 0, SMARL_ENV_CONGESTION = 1, SMARL_ENV_COLLISION = 2 };
 
-int smarl_host_session_create(SmarlHostSession** out, int32_t n_agents, int32_t n_constraints,
-                              int32_t n_steps, int64_t n_envs);
+/* One session per (env kind, n_agents, n_steps, n_envs[, n_landmarks]); K follows the env. */
+int smarl_host_session_create(SmarlHostSession** out, int32_t env_kind, int32_t n_agents, int32_t n_steps,
+                              int64_t n_envs, int32_t n_landmarks);
 void smarl_host_session_destroy(SmarlHostSession* s);
 /* ld (= padded n_envs) the host arrays of this session must use. */
 int64_t smarl_host_session_ld(const SmarlHostSession* s);
 
-/* CoverageDiscrete episode from host buffers.  p->lut / p->weights and lambdas_h are HOST
- * pointers here.  start_x_h,start_y_h u8 [A][ld]; actions_h u8 [T][A][ld];
- * R_h, modR_h f32 [A][ld]; C_h i32 [A][ld]; stats_h f64 [smarl_stats_len] (NULL ok). */
+/* CoverageDiscrete episodes from host buffers (main.py:28-57 for recorded actions).  p->lut /
+ * p->weights, acc->thresholds and lambdas_h are HOST pointers here.  start_x_h,start_y_h u8 [A][ld];
+ * actions_h u8 [T][A][ld]; R_h, modR_h f32 [A][ld]; C_h i32 [A][ld]; stats_h f64 [smarl_stats_len]
+ * (NULL ok). */
 int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p,
                                 const SmarlAccounting* acc, const uint8_t* start_x_h,
                                 const uint8_t* start_y_h, const uint8_t* actions_h,
                                 const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
                                 double* stats_h);
+
+/* Congestion episodes from host buffers.  p->demand is a HOST table; moves_h u8 [T][A][ld] only for
+ * noise_mode 1; C_h i32 [1][ld]. */
+int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCongestionParams* p,
+                                  const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                  const uint8_t* start_y_h, const uint8_t* actions_h,
+                                  const uint8_t* moves_h, const double* lambdas_h, float* R_h,
+                                  float* modR_h, int32_t* C_h, double* stats_h);
+
+/* CollisionAvoidance episodes from host buffers.  start_x_h,start_y_h f64 [A][ld]; landmarks_h f64
+ * [2L][ld]; actions_h f32 [T][2A][ld]; C_h i32 [1][ld]; n_active_h i32 [ld] (NULL ok). */
+int smarl_host_collision_rollout(SmarlHostSession* s, const SmarlCollisionParams* p,
+                                 const SmarlAccounting* acc, const double* start_x_h,
+                                 const double* start_y_h, const double* landmarks_h,
+                                 const float* actions_h, const double* lambdas_h, float* R_h, float* modR_h,
+                                 int32_t* C_h, int32_t* n_active_h, double* stats_h);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,8 @@ class CongestionParams(C.Structure):
 
 class CollisionParams(C.Structure):
     _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("n_landmarks", C.c_int32),
-                ("obs_landmarks", C.c_int32), ("agents_size", C.c_double)]
+                ("obs_landmarks", C.c_int32), ("agents_size", C.c_double), ("normalize_state", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 P = C.POINTER
@@ -74,14 +75,19 @@ PROTOTYPES = {
     "smarl_rollout_returns": (C.c_int, [P(Accounting), c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
-    "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64]),
+    "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64, i32]),
     "smarl_host_session_destroy": (None, [c_ptr]),
     "smarl_host_session_ld": (i64, [c_ptr]),
     "smarl_host_coverage_rollout": (C.c_int, [c_ptr, P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr,
                                               c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "smarl_host_congestion_rollout": (C.c_int, [c_ptr, P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr,
+                                                c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "smarl_host_collision_rollout": (C.c_int, [c_ptr, P(CollisionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,
+                                               c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
 COST_U8, COST_I32, COST_F32 = 0, 1, 2
+ENV_COVERAGE, ENV_CONGESTION, ENV_COLLISION = 0, 1, 2
 _lib = None
 
 

@@ -35,9 +35,16 @@ struct CollisionStepArgs {
   double agents_size;
   int32_t L;
   int32_t obs_landmarks;
+  int32_t normalize;
 };
 
 constexpr int kCollThreads = 128;
+
+// observation value of a coordinate: the state itself, or state / size with normalize_state
+// (collision_avoidance.py:164-165, a float64 division), rounded once to f32.
+__device__ __forceinline__ float obs_value(double v, double size, int normalize) {
+  return (float)(normalize ? __ddiv_rn(v, size) : v);
+}
 
 // numpy's pairwise float64 sum of n <= 128 contiguous values (what np.sum does to the A
 // per-agent minima at collision_avoidance.py:161): n < 8 sequential; otherwise 8 running
@@ -201,12 +208,13 @@ __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const Coll
     if (a.done_out) a.done_out[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
     a.reward[i * ld + e] = rf;
     if (a.obs) {
-      a.obs[(2 * i) * ld + e] = (float)px[i];
-      a.obs[(2 * i + 1) * ld + e] = (float)py[i];
+      a.obs[(2 * i) * ld + e] = obs_value(px[i], a.size, a.normalize);
+      a.obs[(2 * i + 1) * ld + e] = obs_value(py[i], a.size, a.normalize);
     }
   }
   if (a.obs && a.obs_landmarks) {                             // :141-142 (shuffle=True layout)
-    for (int l = 0; l < 2 * a.L; ++l) a.obs[(2 * A + l) * ld + e] = (float)a.landmarks[l * ld + e];
+    for (int l = 0; l < 2 * a.L; ++l)
+      a.obs[(2 * A + l) * ld + e] = obs_value(a.landmarks[l * ld + e], a.size, a.normalize);
   }
   a.cost[e] = collisions;
   if (a.episode_len && active) a.episode_len[e] += 1;
@@ -323,7 +331,7 @@ __global__ void collision_reset_kernel(const double* __restrict__ start_x, const
                                        const double* __restrict__ landmarks, double* __restrict__ pos_x,
                                        double* __restrict__ pos_y, uint8_t* __restrict__ done,
                                        int32_t* __restrict__ episode_len, float* __restrict__ obs, int A, int L,
-                                       int obs_landmarks, int64_t n_envs, int64_t ld) {
+                                       int obs_landmarks, int normalize, double size, int64_t n_envs, int64_t ld) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_envs) return;
   if (episode_len) episode_len[e] = 0;
@@ -333,12 +341,12 @@ __global__ void collision_reset_kernel(const double* __restrict__ start_x, const
     pos_y[i * ld + e] = y;
     done[i * ld + e] = 0;
     if (obs) {
-      obs[(2 * i) * ld + e] = (float)x;
-      obs[(2 * i + 1) * ld + e] = (float)y;
+      obs[(2 * i) * ld + e] = obs_value(x, size, normalize);
+      obs[(2 * i + 1) * ld + e] = obs_value(y, size, normalize);
     }
   }
   if (obs && obs_landmarks)
-    for (int l = 0; l < 2 * L; ++l) obs[(2 * A + l) * ld + e] = (float)landmarks[l * ld + e];
+    for (int l = 0; l < 2 * L; ++l) obs[(2 * A + l) * ld + e] = obs_value(landmarks[l * ld + e], size, normalize);
 }
 
 static int check_collision(const SmarlCollisionParams* p) {
@@ -367,7 +375,8 @@ extern "C" int smarl_collision_reset(const SmarlCollisionParams* p, const double
   const unsigned grid = (unsigned)((n_envs + 255) / 256);
   collision_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(start_x, start_y, landmarks, pos_x, pos_y,
                                                                  done, episode_len, obs, p->n_agents, p->n_landmarks,
-                                                                 p->obs_landmarks, n_envs, ld);
+                                                                 p->obs_landmarks, p->normalize_state, (double)p->size,
+                                                                 n_envs, ld);
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;
 }
@@ -387,6 +396,7 @@ extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x
   a.lambdas = lambdas;
   a.penalty = penalty; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size;
   a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
+  a.normalize = p->normalize_state;
   const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
   if (int rc = launch_collision_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;

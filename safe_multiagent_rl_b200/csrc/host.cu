@@ -3,22 +3,24 @@
 // host->device copy of chunk c+1, the fused rollout of chunk c and the device->host copy of
 // chunk c-1 overlap (PCIe is full duplex; the kernel is far shorter than either copy).
 #include <new>
-#include <vector>
 
 #include "stats.cuh"
 
 struct SmarlHostSession {
-  int32_t A, K, T;
+  int32_t kind, A, K, T, L;
   int64_t n_envs, ld;
   int n_chunks;
   int64_t chunk;            // envs per chunk (multiple of 16)
   cudaStream_t streams[2];
-  uint8_t* d_start_x;
-  uint8_t* d_start_y;
-  uint8_t* d_actions;       // [T][A][ld]
+  void* d_start_x;          // u8 (grid envs) or f64 (Collision) [A][ld]
+  void* d_start_y;
+  void* d_actions;          // u8 [T][A][ld] or f32 [T][2A][ld]
+  uint8_t* d_moves;         // Congestion recorded moves, allocated on first use
+  double* d_landmarks;      // Collision f64 [2L][ld]
   float* d_R;
   float* d_modR;
   int32_t* d_C;
+  int32_t* d_n_active;
   double* d_stats;          // [n_chunks][stats_len]
   double* d_scratch;        // [n_chunks][scratch_len(chunk)]
   int64_t scratch_per_chunk;
@@ -26,6 +28,7 @@ struct SmarlHostSession {
   float* d_weights;
   double* d_lambdas;
   double* d_thresholds;
+  double* d_demand;
   double* h_stats;          // pinned [n_chunks][stats_len]
 };
 
@@ -35,21 +38,26 @@ static void free_session(SmarlHostSession* s) {
   if (!s) return;
   for (auto st : s->streams)
     if (st) cudaStreamDestroy(st);
-  cudaFree(s->d_start_x); cudaFree(s->d_start_y); cudaFree(s->d_actions); cudaFree(s->d_R);
-  cudaFree(s->d_modR); cudaFree(s->d_C); cudaFree(s->d_stats); cudaFree(s->d_scratch);
-  cudaFree(s->d_lut); cudaFree(s->d_weights); cudaFree(s->d_lambdas); cudaFree(s->d_thresholds);
+  cudaFree(s->d_start_x); cudaFree(s->d_start_y); cudaFree(s->d_actions); cudaFree(s->d_moves);
+  cudaFree(s->d_landmarks); cudaFree(s->d_R); cudaFree(s->d_modR); cudaFree(s->d_C); cudaFree(s->d_n_active);
+  cudaFree(s->d_stats); cudaFree(s->d_scratch); cudaFree(s->d_lut); cudaFree(s->d_weights);
+  cudaFree(s->d_lambdas); cudaFree(s->d_thresholds); cudaFree(s->d_demand);
   if (s->h_stats) cudaFreeHost(s->h_stats);
   delete s;
 }
 
-extern "C" int smarl_host_session_create(SmarlHostSession** out, int32_t A, int32_t K, int32_t T,
-                                         int64_t n_envs) {
+extern "C" int smarl_host_session_create(SmarlHostSession** out, int32_t kind, int32_t A, int32_t T,
+                                         int64_t n_envs, int32_t n_landmarks) {
   SMARL_REQUIRE(out != nullptr, "out is NULL");
-  SMARL_REQUIRE(A >= 1 && A <= SMARL_MAX_AGENTS && K >= 1 && K <= SMARL_MAX_AGENTS, "bad A=%d / K=%d", A, K);
-  SMARL_REQUIRE(T >= 1 && T <= 255 && n_envs >= 1, "bad T=%d or n_envs=%lld", T, (long long)n_envs);
+  SMARL_REQUIRE(kind >= SMARL_ENV_COVERAGE && kind <= SMARL_ENV_COLLISION, "bad env kind %d", kind);
+  SMARL_REQUIRE(A >= 1 && A <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", A);
+  SMARL_REQUIRE(T >= 1 && n_envs >= 1, "bad T=%d or n_envs=%lld", T, (long long)n_envs);
+  SMARL_REQUIRE(kind != SMARL_ENV_COVERAGE || T <= 255, "Coverage fused rollout needs T <= 255");
+  SMARL_REQUIRE(kind != SMARL_ENV_COLLISION || (n_landmarks >= 1 && n_landmarks <= 64), "bad n_landmarks");
   SmarlHostSession* s = new (std::nothrow) SmarlHostSession();
   SMARL_REQUIRE(s != nullptr, "out of host memory");
-  s->A = A; s->K = K; s->T = T; s->n_envs = n_envs;
+  s->kind = kind; s->A = A; s->K = kind == SMARL_ENV_COVERAGE ? A : 1; s->T = T; s->L = n_landmarks;
+  s->n_envs = n_envs;
   s->ld = (n_envs + 15) / 16 * 16;
   // ~8 chunks, each a multiple of 16 envs and at least 64Ki envs so launches stay large.
   int64_t chunk = (s->ld / 8 + 15) / 16 * 16;
@@ -57,8 +65,10 @@ extern "C" int smarl_host_session_create(SmarlHostSession** out, int32_t A, int3
   if (chunk > s->ld) chunk = s->ld;
   s->chunk = chunk;
   s->n_chunks = (int)((n_envs + chunk - 1) / chunk);
-  const int sl = stats_len(A, K);
-  s->scratch_per_chunk = smarl_stats_scratch_len(A, K, chunk);
+  const int sl = stats_len(A, s->K);
+  s->scratch_per_chunk = smarl_stats_scratch_len(A, s->K, chunk);
+  const size_t pos_elem = kind == SMARL_ENV_COLLISION ? 8 : 1;
+  const size_t act_bytes = kind == SMARL_ENV_COLLISION ? (size_t)T * 2 * A * s->ld * 4 : (size_t)T * A * s->ld;
 #define SMARL_TRY(call)                                                              \
   do {                                                                               \
     cudaError_t e__ = (call);                                                        \
@@ -69,12 +79,17 @@ extern "C" int smarl_host_session_create(SmarlHostSession** out, int32_t A, int3
     }                                                                                \
   } while (0)
   for (auto& st : s->streams) SMARL_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  SMARL_TRY(cudaMalloc(&s->d_start_x, (size_t)A * s->ld));
-  SMARL_TRY(cudaMalloc(&s->d_start_y, (size_t)A * s->ld));
-  SMARL_TRY(cudaMalloc(&s->d_actions, (size_t)T * A * s->ld));
+  SMARL_TRY(cudaMalloc(&s->d_start_x, pos_elem * A * s->ld));
+  SMARL_TRY(cudaMalloc(&s->d_start_y, pos_elem * A * s->ld));
+  SMARL_TRY(cudaMalloc(&s->d_actions, act_bytes));
+  if (kind == SMARL_ENV_COLLISION) {
+    SMARL_TRY(cudaMalloc(&s->d_landmarks, sizeof(double) * 2 * n_landmarks * s->ld));
+    SMARL_TRY(cudaMalloc(&s->d_n_active, sizeof(int32_t) * s->ld));
+  }
+  if (kind == SMARL_ENV_CONGESTION) SMARL_TRY(cudaMalloc(&s->d_demand, sizeof(double) * 255 * 255));
   SMARL_TRY(cudaMalloc(&s->d_R, sizeof(float) * A * s->ld));
   SMARL_TRY(cudaMalloc(&s->d_modR, sizeof(float) * A * s->ld));
-  SMARL_TRY(cudaMalloc(&s->d_C, sizeof(int32_t) * K * s->ld));
+  SMARL_TRY(cudaMalloc(&s->d_C, sizeof(int32_t) * s->K * s->ld));
   SMARL_TRY(cudaMalloc(&s->d_stats, sizeof(double) * sl * s->n_chunks));
   SMARL_TRY(cudaMalloc(&s->d_scratch, sizeof(double) * s->scratch_per_chunk * s->n_chunks));
   SMARL_TRY(cudaMalloc(&s->d_lut, sizeof(float) * 12288));
@@ -91,51 +106,44 @@ extern "C" void smarl_host_session_destroy(SmarlHostSession* s) { free_session(s
 
 extern "C" int64_t smarl_host_session_ld(const SmarlHostSession* s) { return s ? s->ld : 0; }
 
-extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p,
-                                           const SmarlAccounting* acc, const uint8_t* start_x_h,
-                                           const uint8_t* start_y_h, const uint8_t* actions_h,
-                                           const double* lambdas_h, float* R_h, float* modR_h,
-                                           int32_t* C_h, double* stats_h) {
-  SMARL_REQUIRE(s && p && acc, "null session / params");
-  SMARL_REQUIRE(p->n_agents == s->A && s->K == s->A && acc->n_steps == s->T,
-                "session was created for A=%d K=%d T=%d", s->A, s->K, s->T);
-  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
-  SMARL_REQUIRE(p->lut_len >= 0 && p->lut_len <= 12287, "lut_len=%d outside 0..12287", p->lut_len);
-  SMARL_REQUIRE(start_x_h && start_y_h && actions_h && R_h && modR_h && C_h, "null host buffer");
-  const int A = s->A, T = s->T, sl = stats_len(A, A);
-  const int64_t ld = s->ld;
-  cudaStream_t s0 = s->streams[0];
-  // small parameters
-  if (p->lut_len) SMARL_CUDA(cudaMemcpyAsync(s->d_lut, p->lut, sizeof(float) * p->lut_len, cudaMemcpyHostToDevice, s0));
-  if (p->weights) SMARL_CUDA(cudaMemcpyAsync(s->d_weights, p->weights, sizeof(float) * A, cudaMemcpyHostToDevice, s0));
-  if (lambdas_h) SMARL_CUDA(cudaMemcpyAsync(s->d_lambdas, lambdas_h, sizeof(double) * A, cudaMemcpyHostToDevice, s0));
-  if (acc->thresholds) SMARL_CUDA(cudaMemcpyAsync(s->d_thresholds, acc->thresholds, sizeof(double) * A, cudaMemcpyHostToDevice, s0));
-  SMARL_CUDA(cudaStreamSynchronize(s0));
-  SmarlCoverageParams dp = *p;
-  dp.lut = s->d_lut;
-  dp.weights = p->weights ? s->d_weights : nullptr;
-  SmarlAccounting dacc = *acc;
-  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+namespace {
 
+struct Chunk {
+  int index;
+  int64_t e0, n, w;   // first env, envs in the chunk, envs copied per row (n rounded up to 16)
+  cudaStream_t st;
+};
+
+// rows x w elements of `elem` bytes between pitched [rows][ld] arrays, starting at env e0
+int copy_rows(void* dst, const void* src, size_t elem, int64_t rows, int64_t ld, const Chunk& c, cudaMemcpyKind kind) {
+  SMARL_CUDA(cudaMemcpy2DAsync(static_cast<char*>(dst) + c.e0 * elem, ld * elem,
+                               static_cast<const char*>(src) + c.e0 * elem, ld * elem, c.w * elem, (size_t)rows, kind,
+                               c.st));
+  return SMARL_OK;
+}
+
+int upload_small(SmarlHostSession* s, const double* lambdas_h, const double* thresholds_h, int K) {
+  cudaStream_t s0 = s->streams[0];
+  if (lambdas_h) SMARL_CUDA(cudaMemcpyAsync(s->d_lambdas, lambdas_h, sizeof(double) * K, cudaMemcpyHostToDevice, s0));
+  if (thresholds_h) SMARL_CUDA(cudaMemcpyAsync(s->d_thresholds, thresholds_h, sizeof(double) * K, cudaMemcpyHostToDevice, s0));
+  return SMARL_OK;
+}
+
+// Runs `body(chunk)` for every env chunk on alternating streams, then gathers the additive stats.
+template <class Body>
+int pipeline(SmarlHostSession* s, double* stats_h, Body body) {
+  const int sl = stats_len(s->A, s->K);
+  SMARL_CUDA(cudaStreamSynchronize(s->streams[0]));      // small parameter uploads are visible to both streams
   for (int c = 0; c < s->n_chunks; ++c) {
-    cudaStream_t st = s->streams[c & 1];
-    const int64_t e0 = (int64_t)c * s->chunk;
-    const int64_t n = (e0 + s->chunk <= s->n_envs) ? s->chunk : (s->n_envs - e0);
-    const int64_t w = (n + 15) / 16 * 16;          // bytes (u8) / elements copied per row
-    SMARL_CUDA(cudaMemcpy2DAsync(s->d_start_x + e0, ld, start_x_h + e0, ld, w, A, cudaMemcpyHostToDevice, st));
-    SMARL_CUDA(cudaMemcpy2DAsync(s->d_start_y + e0, ld, start_y_h + e0, ld, w, A, cudaMemcpyHostToDevice, st));
-    SMARL_CUDA(cudaMemcpy2DAsync(s->d_actions + e0, ld, actions_h + e0, ld, w, (size_t)T * A, cudaMemcpyHostToDevice, st));
-    int rc = smarl_coverage_rollout(&dp, &dacc, s->d_start_x + e0, s->d_start_y + e0, s->d_actions + e0,
-                                    lambdas_h ? s->d_lambdas : nullptr, nullptr, nullptr, s->d_R + e0,
-                                    s->d_modR + e0, s->d_C + e0, nullptr, nullptr,
-                                    s->d_stats + (int64_t)c * sl, s->d_scratch + (int64_t)c * s->scratch_per_chunk,
-                                    n, ld, st);
-    if (rc) return rc;
-    SMARL_CUDA(cudaMemcpy2DAsync(R_h + e0, ld * 4, s->d_R + e0, ld * 4, w * 4, A, cudaMemcpyDeviceToHost, st));
-    SMARL_CUDA(cudaMemcpy2DAsync(modR_h + e0, ld * 4, s->d_modR + e0, ld * 4, w * 4, A, cudaMemcpyDeviceToHost, st));
-    SMARL_CUDA(cudaMemcpy2DAsync(C_h + e0, ld * 4, s->d_C + e0, ld * 4, w * 4, A, cudaMemcpyDeviceToHost, st));
+    Chunk ch;
+    ch.index = c;
+    ch.st = s->streams[c & 1];
+    ch.e0 = (int64_t)c * s->chunk;
+    ch.n = (ch.e0 + s->chunk <= s->n_envs) ? s->chunk : (s->n_envs - ch.e0);
+    ch.w = (ch.n + 15) / 16 * 16;
+    if (int rc = body(ch)) return rc;
     SMARL_CUDA(cudaMemcpyAsync(s->h_stats + (int64_t)c * sl, s->d_stats + (int64_t)c * sl, sizeof(double) * sl,
-                               cudaMemcpyDeviceToHost, st));
+                               cudaMemcpyDeviceToHost, ch.st));
   }
   SMARL_CUDA(cudaStreamSynchronize(s->streams[0]));
   SMARL_CUDA(cudaStreamSynchronize(s->streams[1]));
@@ -147,4 +155,128 @@ extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCover
     }
   }
   return SMARL_OK;
+}
+
+}  // namespace
+
+extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                           const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                           const uint8_t* start_y_h, const uint8_t* actions_h,
+                                           const double* lambdas_h, float* R_h, float* modR_h,
+                                           int32_t* C_h, double* stats_h) {
+  SMARL_REQUIRE(s && p && acc, "null session / params");
+  SMARL_REQUIRE(s->kind == SMARL_ENV_COVERAGE && p->n_agents == s->A && acc->n_steps == s->T,
+                "session was created for kind=%d A=%d T=%d", s->kind, s->A, s->T);
+  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
+  SMARL_REQUIRE(p->lut_len >= 0 && p->lut_len <= 12287, "lut_len=%d outside 0..12287", p->lut_len);
+  SMARL_REQUIRE(start_x_h && start_y_h && actions_h && R_h && modR_h && C_h, "null host buffer");
+  const int A = s->A, T = s->T, sl = stats_len(A, A);
+  const int64_t ld = s->ld;
+  cudaStream_t s0 = s->streams[0];
+  if (p->lut_len) SMARL_CUDA(cudaMemcpyAsync(s->d_lut, p->lut, sizeof(float) * p->lut_len, cudaMemcpyHostToDevice, s0));
+  if (p->weights) SMARL_CUDA(cudaMemcpyAsync(s->d_weights, p->weights, sizeof(float) * A, cudaMemcpyHostToDevice, s0));
+  if (int rc = upload_small(s, lambdas_h, acc->thresholds, A)) return rc;
+  SmarlCoverageParams dp = *p;
+  dp.lut = s->d_lut;
+  dp.weights = p->weights ? s->d_weights : nullptr;
+  SmarlAccounting dacc = *acc;
+  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+  uint8_t* dx = static_cast<uint8_t*>(s->d_start_x);
+  uint8_t* dy = static_cast<uint8_t*>(s->d_start_y);
+  uint8_t* da = static_cast<uint8_t*>(s->d_actions);
+  return pipeline(s, stats_h, [&](const Chunk& c) -> int {
+    if (int rc = copy_rows(dx, start_x_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(dy, start_y_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(da, actions_h, 1, (int64_t)T * A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = smarl_coverage_rollout(&dp, &dacc, dx + c.e0, dy + c.e0, da + c.e0, lambdas_h ? s->d_lambdas : nullptr,
+                                        nullptr, nullptr, s->d_R + c.e0, s->d_modR + c.e0, s->d_C + c.e0, nullptr,
+                                        nullptr, s->d_stats + (int64_t)c.index * sl,
+                                        s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
+      return rc;
+    if (int rc = copy_rows(R_h, s->d_R, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    if (int rc = copy_rows(modR_h, s->d_modR, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    return copy_rows(C_h, s->d_C, 4, A, ld, c, cudaMemcpyDeviceToHost);
+  });
+}
+
+extern "C" int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCongestionParams* p,
+                                             const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                             const uint8_t* start_y_h, const uint8_t* actions_h,
+                                             const uint8_t* moves_h, const double* lambdas_h, float* R_h,
+                                             float* modR_h, int32_t* C_h, double* stats_h) {
+  SMARL_REQUIRE(s && p && acc, "null session / params");
+  SMARL_REQUIRE(s->kind == SMARL_ENV_CONGESTION && p->n_agents == s->A && acc->n_steps == s->T,
+                "session was created for kind=%d A=%d T=%d", s->kind, s->A, s->T);
+  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
+  SMARL_REQUIRE(p->size >= 1 && p->size <= 254 && p->demand, "bad size or demand table");
+  SMARL_REQUIRE(start_x_h && start_y_h && actions_h && R_h && modR_h && C_h, "null host buffer");
+  SMARL_REQUIRE(p->noise_mode != 1 || moves_h, "noise_mode 1 needs the recorded moves");
+  const int A = s->A, T = s->T, sl = stats_len(A, 1), W = p->size + 1;
+  const int64_t ld = s->ld;
+  cudaStream_t s0 = s->streams[0];
+  SMARL_CUDA(cudaMemcpyAsync(s->d_demand, p->demand, sizeof(double) * W * W, cudaMemcpyHostToDevice, s0));
+  if (int rc = upload_small(s, lambdas_h, acc->thresholds, 1)) return rc;
+  if (moves_h && !s->d_moves) SMARL_CUDA(cudaMalloc(&s->d_moves, (size_t)T * A * ld));
+  SmarlCongestionParams dp = *p;
+  dp.demand = s->d_demand;
+  SmarlAccounting dacc = *acc;
+  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+  uint8_t* dx = static_cast<uint8_t*>(s->d_start_x);
+  uint8_t* dy = static_cast<uint8_t*>(s->d_start_y);
+  uint8_t* da = static_cast<uint8_t*>(s->d_actions);
+  return pipeline(s, stats_h, [&](const Chunk& c) -> int {
+    if (int rc = copy_rows(dx, start_x_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(dy, start_y_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(da, actions_h, 1, (int64_t)T * A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (moves_h)
+      if (int rc = copy_rows(s->d_moves, moves_h, 1, (int64_t)T * A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    SmarlCongestionParams cp = dp;
+    cp.env_offset = dp.env_offset + c.e0;                 // Philox streams are keyed by the global env id
+    if (int rc = smarl_congestion_rollout(&cp, &dacc, dx + c.e0, dy + c.e0, da + c.e0, moves_h ? s->d_moves + c.e0 : nullptr,
+                                          lambdas_h ? s->d_lambdas : nullptr, nullptr, nullptr, s->d_R + c.e0,
+                                          s->d_modR + c.e0, s->d_C + c.e0, nullptr, nullptr,
+                                          s->d_stats + (int64_t)c.index * sl,
+                                          s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
+      return rc;
+    if (int rc = copy_rows(R_h, s->d_R, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    if (int rc = copy_rows(modR_h, s->d_modR, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    return copy_rows(C_h, s->d_C, 4, 1, ld, c, cudaMemcpyDeviceToHost);
+  });
+}
+
+extern "C" int smarl_host_collision_rollout(SmarlHostSession* s, const SmarlCollisionParams* p,
+                                            const SmarlAccounting* acc, const double* start_x_h,
+                                            const double* start_y_h, const double* landmarks_h,
+                                            const float* actions_h, const double* lambdas_h, float* R_h,
+                                            float* modR_h, int32_t* C_h, int32_t* n_active_h, double* stats_h) {
+  SMARL_REQUIRE(s && p && acc, "null session / params");
+  SMARL_REQUIRE(s->kind == SMARL_ENV_COLLISION && p->n_agents == s->A && acc->n_steps == s->T &&
+                    p->n_landmarks == s->L, "session was created for kind=%d A=%d T=%d L=%d", s->kind, s->A, s->T, s->L);
+  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
+  SMARL_REQUIRE(start_x_h && start_y_h && landmarks_h && actions_h && R_h && modR_h && C_h, "null host buffer");
+  const int A = s->A, T = s->T, L = s->L, sl = stats_len(A, 1);
+  const int64_t ld = s->ld;
+  if (int rc = upload_small(s, lambdas_h, acc->thresholds, 1)) return rc;
+  SmarlAccounting dacc = *acc;
+  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+  double* dx = static_cast<double*>(s->d_start_x);
+  double* dy = static_cast<double*>(s->d_start_y);
+  float* da = static_cast<float*>(s->d_actions);
+  return pipeline(s, stats_h, [&](const Chunk& c) -> int {
+    if (int rc = copy_rows(dx, start_x_h, 8, A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(dy, start_y_h, 8, A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(s->d_landmarks, landmarks_h, 8, 2 * L, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = copy_rows(da, actions_h, 4, (int64_t)T * 2 * A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (int rc = smarl_collision_rollout(p, &dacc, dx + c.e0, dy + c.e0, s->d_landmarks + c.e0, da + c.e0,
+                                         lambdas_h ? s->d_lambdas : nullptr, nullptr, nullptr, nullptr,
+                                         s->d_n_active + c.e0, s->d_R + c.e0, s->d_modR + c.e0, s->d_C + c.e0, nullptr,
+                                         nullptr, s->d_stats + (int64_t)c.index * sl,
+                                         s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
+      return rc;
+    if (int rc = copy_rows(R_h, s->d_R, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    if (int rc = copy_rows(modR_h, s->d_modR, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    if (n_active_h)
+      if (int rc = copy_rows(n_active_h, s->d_n_active, 4, 1, ld, c, cudaMemcpyDeviceToHost)) return rc;
+    return copy_rows(C_h, s->d_C, 4, 1, ld, c, cudaMemcpyDeviceToHost);
+  });
 }

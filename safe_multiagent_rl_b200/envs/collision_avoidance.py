@@ -32,9 +32,7 @@ class BatchedCollisionAvoidance(BatchedEnv):
         assert type(size) == int and type(n_agents) == int and type(n_landmarks) == int   # :51-53
         assert type(agents_size) in (float, int)
         self._init_common(size, n_agents, n_envs, device, env_offset)
-        if normalize_state:
-            raise NotImplementedError("normalize_state=True is not built yet")
-        self.shuffle, self.normalize_state, self.seed = bool(shuffle), False, int(seed)
+        self.shuffle, self.normalize_state, self.seed = bool(shuffle), bool(normalize_state), int(seed)
         self.agents_size = float(agents_size)
         A, E, dev = self.n_agents, self.n_envs, self.device
         self.n_landmarks = int(n_landmarks)
@@ -71,7 +69,8 @@ class BatchedCollisionAvoidance(BatchedEnv):
         self.cost = self._alloc(1, torch.int32)
         self.done = self._alloc(A, torch.uint8)
         self.penalty = self._alloc(1, torch.float32)[0]
-        self._params = _lib.CollisionParams(self.size, A, self.L, int(self.shuffle), self.agents_size)
+        self._params = _lib.CollisionParams(self.size, A, self.L, int(self.shuffle), self.agents_size,
+                                            int(self.normalize_state), 0)
 
     def _draw_starts(self, episode):
         self._draw_float_starts(episode, 2)                      # agents (:82-84) ...

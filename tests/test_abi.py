@@ -48,7 +48,7 @@ def test_abi_struct_sizes():
     assert C.sizeof(_lib.CoverageParams) == 32
     assert C.sizeof(_lib.Accounting) == 24
     assert C.sizeof(_lib.CongestionParams) == 48
-    assert C.sizeof(_lib.CollisionParams) == 24
+    assert C.sizeof(_lib.CollisionParams) == 32
 
 
 def test_validation_errors_before_any_cuda_work(lib):

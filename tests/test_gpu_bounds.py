@@ -120,7 +120,7 @@ def test_congestion_and_collision_stay_in_bounds(A, E):
     adone, dout, elen, nact = ar.make(A, ld, u8), ar.make(A, ld, u8), ar.make(1, ld, i32), ar.make(1, ld, i32)
     obs2 = ar.make(2 * A + 2 * L, ld, f32)
     gs2 = ar.make(2 * T, ld, f32)
-    kp = _lib.CollisionParams(S, A, L, 1, 0.25)
+    kp = _lib.CollisionParams(S, A, L, 1, 0.25, 1, 0)
     _lib.check(lib.smarl_collision_reset(C.byref(kp), P(fx), P(fy), P(lm), P(qx), P(qy), P(adone), P(elen), P(obs2), E, ld, st))
     for t in range(T):
         _lib.check(lib.smarl_collision_step(C.byref(kp), P(qx), P(qy), P(adone), P(fa[t * 2 * A:]), P(lm), P(obs2), P(rew),

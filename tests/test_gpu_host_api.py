@@ -1,0 +1,93 @@
+"""The host-buffer C-ABI entry points (numpy arrays in / out, chunked 2-stream pipeline inside)
+against the oracle, for all three envs, with more envs than one chunk so the pipeline is exercised."""
+import numpy as np
+import pytest
+
+from oracle import numpy_oracle as no
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, want, scale, rtol=1e-5):
+    np.testing.assert_allclose(np.asarray(got, np.float64), want, rtol=rtol, atol=rtol * scale)
+
+
+def test_host_coverage_rollout_multi_chunk():
+    from safe_multiagent_rl_b200.host import HostRollout
+    size, A, E, T, gamma = 7, 4, 150_001, 6, 0.99            # 3 chunks of 65536
+    rng = np.random.default_rng(0)
+    starts = rng.integers(0, size, (E, A, 2))
+    actions = rng.integers(0, 5, (T, E, A))
+    w, lam, thr = [1.0, 2.0, 3.0, 1.0], np.array([0.1, 0.2, 0.3, 0.4]), [3.0] * A
+    lut = no.coverage_penalty_lut(size, no.coverage_fieldview(size, A))
+    pos = starts.copy()
+
+    def step_fn(t):
+        nonlocal pos
+        pos, r, c, _ = no.coverage_discrete_step(pos, actions[t], size, lut, w)
+        return r, c
+    want = no.rollout(step_fn, T, gamma, lam)
+    h = HostRollout("coverage", A, T, E)
+    out = h.coverage(size, starts, actions, weights=w, lambdas=lam, gamma=gamma, thresholds=thr)
+    scale = np.abs(want["modR"]).max()
+    assert np.array_equal(out["C"], want["C"])
+    close(out["R"], want["R"], scale); close(out["modR"], want["modR"], scale)
+    st = out["stats"]
+    assert np.array_equal(st[:A], want["C"].sum(0)) and st[-1] == E
+    assert np.array_equal(st[A:2 * A], (want["C"] > 3.0).sum(0))
+    close(st[2 * A:3 * A], want["R"].sum(0), scale * E)
+    h.close()
+
+
+def test_host_congestion_rollout_multi_chunk():
+    from safe_multiagent_rl_b200.host import HostRollout
+    size, A, E, T, gamma, noise, seed, off = 6, 5, 70_000, 8, 0.9, 0.2, 31, 12345
+    rng = np.random.default_rng(1)
+    demand = rng.random((size + 1, size + 1)) * 8 + 2
+    starts = rng.integers(0, size, (E, A, 2)); starts[:, 0] = 0
+    actions = rng.integers(0, 5, (T, E, A))
+    pos = starts.copy()
+    ids = np.arange(off, off + E)
+
+    def step_fn(t):
+        nonlocal pos
+        u1, u2 = philox.congestion_uniforms(seed, ids, t, A)
+        mv = no.congestion_noise_moves(actions[t], u1, u2, noise)
+        pos, r, c, _, _ = no.congestion_step(pos, actions[t], mv, size, demand)
+        return r.astype(np.float32).astype(np.float64), c
+    want = no.rollout(step_fn, T, gamma, [0.4])
+    h = HostRollout("congestion", A, T, E)
+    out = h.congestion(size, starts, actions, demand, noise=noise, seed=seed, env_offset=off, lambdas=[0.4], gamma=gamma,
+                       thresholds=[2.0])
+    scale = np.abs(want["modR"]).max()
+    assert np.array_equal(out["C"], want["C"])                 # same Philox stream across chunk boundaries
+    close(out["R"], want["R"], scale); close(out["modR"], want["modR"], scale)
+    assert out["stats"][0] == want["C"].sum() and out["stats"][-1] == E
+    h.close()
+
+
+def test_host_collision_rollout_multi_chunk():
+    from safe_multiagent_rl_b200.host import HostRollout
+    size, A, L, E, T, gamma = 5, 3, 2, 66_000, 10, 0.99
+    rng = np.random.default_rng(2)
+    starts, lm = rng.random((E, A, 2)) * size, rng.random((E, L, 2)) * size
+    actions = rng.normal(0, 0.5, (T, E, A, 2)).astype(np.float32)
+    q = E // 4
+    actions[:, :q] = ((lm[:q, :1] - starts[:q]) / 3).astype(np.float32)[None]
+    pos, done = starts.copy(), np.zeros((E, A), bool)
+    n_active = np.zeros(E, np.int64)
+
+    def step_fn(t):
+        nonlocal pos, done, n_active
+        pos, r, c, done, active = no.collision_step(pos, done, actions[t].astype(np.float64), lm, size)
+        n_active += active
+        return r.astype(np.float32).astype(np.float64), c
+    want = no.rollout(step_fn, T, gamma, [0.5])
+    h = HostRollout("collision", A, T, E, n_landmarks=L)
+    out = h.collision(size, starts, lm, actions, lambdas=[0.5], gamma=gamma, thresholds=[1.0])
+    scale = np.abs(want["modR"]).max()
+    assert np.array_equal(out["C"], want["C"].astype(np.int64)) and np.array_equal(out["n_active"], n_active)
+    close(out["R"], want["R"], scale); close(out["modR"], want["modR"], scale)
+    assert (n_active < T).any()
+    h.close()

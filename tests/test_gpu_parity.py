@@ -506,3 +506,27 @@ def test_ppo_standardised_returns_coverage_and_collision():
     ref = no.ppo_standardised_returns(want["mod_reward"], 0.99, n_active)
     close(got[:, ok], ref[:, ok], 1.0, rtol=2e-5)
     assert np.isnan(got[0, n_active == 1]).all()            # torch: the std of a single sample is nan
+
+
+def test_collision_normalize_state_and_shuffle_obs():
+    """normalize_state=True: the returned state is state / size (collision_avoidance.py:87-88,:146-147,
+    :164-165) while the dynamics keep running on the raw positions; with shuffle the landmark rows are
+    normalised too."""
+    s = smarl()
+    rng = np.random.default_rng(3)
+    E, A, size = 77, 4, 5
+    starts, lm = rng.random((E, A, 2)) * size, rng.random((E, 1, 2)) * size
+    act = rng.normal(0, 0.5, (E, A, 2)).astype(np.float32)
+    plain = s.BatchedCollisionAvoidance(size, A, n_envs=E, starts=starts, landmarks=lm)
+    norm = s.BatchedCollisionAvoidance(size, A, n_envs=E, starts=starts, landmarks=lm, normalize_state=True)
+    o0 = norm.reset(); plain.reset()
+    assert np.array_equal(o0.cpu().numpy().reshape(E, A, 2), (starts / size).astype(np.float32))
+    o1, r1, c1, d1 = norm.step(act)
+    o2, r2, c2, d2 = plain.step(act)
+    assert torch.equal(norm.state(), plain.state()) and torch.equal(r1, r2) and torch.equal(c1, c2)
+    assert np.array_equal(o1.cpu().numpy().reshape(E, A, 2), (plain.state().cpu().numpy() / size).astype(np.float32))
+    sh = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=2, shuffle=True, normalize_state=True, seed=1)
+    o = sh.reset().cpu().numpy()
+    want = np.concatenate([sh.state().cpu().numpy().reshape(E, 2 * A),
+                           sh.landmarks[:, :E].t().cpu().numpy()], axis=1) / size
+    assert np.array_equal(o, want.astype(np.float32))
