@@ -284,6 +284,42 @@ def run_ours(a):
                 "bytes_per_launch": bytes_per_launch, "launch_ms": launch_ms, "peak_source": peak_src,
                 "share_of_step": step_kernel_ms / total_ms}
 
+    # ---- lean closed loop (extra): one env-reward row + no done flags in the rollout buffer ---------------
+    lean = None
+    if not a.no_fused:
+        lbuf = env.new_rollout_buffer(T, g_mode=s.G_REWARD_TO_GO, lean=True)
+        pshared = env._params_shared
+
+        def lean_loop(ev_a=None, ev_b=None):
+            _lib.check(lib.smarl_grid_reset(P(env.start_x), P(env.start_y), P(env.pos_x), P(env.pos_y), P(env.obs),
+                                            A, E, ld, stream))
+            if ev_a is not None:
+                ev_a.record()
+            for t in range(T):
+                _lib.check(lib.smarl_coverage_step(C.byref(pshared), P(env.pos_x), P(env.pos_y), P(actions[t]),
+                                                   P(env.obs), P(lbuf.reward[t]), P(lbuf.cost[t]), None,
+                                                   P(meta.lambdas), P(lbuf.penalty[t]), E, ld, stream))
+            if ev_b is not None:
+                ev_b.record()
+            _lib.check(lib.smarl_rollout_returns_shared(C.byref(acc), P(lbuf.reward), P(env._weights), P(lbuf.cost),
+                                                        lbuf.cost_code, P(lbuf.penalty), P(lbuf.R), P(lbuf.modR),
+                                                        P(lbuf.Csum), P(lbuf.G), P(lbuf.stats_vec),
+                                                        P(lbuf.stats_scratch), A, K, E, ld, stream))
+            sd.allreduce_stats(lbuf.stats_vec)
+            _lib.check(lib.smarl_lambda_update(P(meta.lambdas), P(lbuf.stats_vec), P(thr), 0.002, A, K, stream))
+        l_ms, l_step_ms = timed(lean_loop, a.steps, a.warmup, per_step_events=True)
+        l_ms /= a.steps
+        l_launch = l_step_ms / (a.steps * T)
+        l_bytes = (2 + 1 + 2 + 8 + 1 + 8.0 / A) * A * E        # pos in/out, action, obs, cost, (reward + penalty)/A
+        lean = {"value": world * agent_steps / (l_ms * 1e-3), "unit": UNIT, "ms_per_step": l_ms,
+                "mode": "closed loop, lean rollout buffer: one env-reward row (weights applied by "
+                        "smarl_rollout_returns_shared), no per-step done flags",
+                "roofline": {"bound": "hbm", "kernel": "coverage_step_kernel (reward_rows=1, done=NULL)",
+                             "achieved": l_bytes / (l_launch * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": l_bytes / (l_launch * 1e-3) / 1e9 / peak, "bytes_per_launch": l_bytes,
+                             "launch_ms": l_launch}}
+        del lbuf
+
     # ---- fused open-loop rollout (extra) ------------------------------------------------------------
     fused = None
     if not a.no_fused:
@@ -382,7 +418,7 @@ def run_ours(a):
                        "l2": "inputs larger than L2: each step launch streams 1.3 GB (19 B x 16 x 2^22)",
                        "agent_steps_per_step": world * agent_steps},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "fused": fused,
+            "roofline": roofline, "cpu_baseline": cpu, "fused": fused, "lean": lean,
         })
     if world > 1:
         dist.barrier()

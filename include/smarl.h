@@ -88,7 +88,10 @@ typedef struct {
   int32_t size;         /* coordinates clamp to [0,size]                 coverage.py:185-186 */
   int32_t n_agents;     /* A; also K = A constraints                     coverage.py:22      */
   int32_t lut_len;      /* penalties for squared distance q >= lut_len are 0                 */
-  int32_t reserved;
+  int32_t reward_rows;  /* step only: 0 (= A) per-agent weighted rewards [A][ld]; 1: ONE row with the
+                           unweighted env reward -- reward_a = w_a * rew is linear, so the accounting
+                           (smarl_rollout_returns_shared) can apply the weights; saves 4 - 4/A B per
+                           agent-step of HBM traffic                                              */
   const float* lut;     /* [lut_len] pen(q) = (fv - sqrt(q))^2 if sqrt(q) < fv else 0, f32
                            rounding of the reference's f64 value         coverage.py:80-83   */
   const float* weights; /* [A] per-agent reward weight, NULL = 1         coverage.py:86-87   */
@@ -99,7 +102,7 @@ typedef struct {
  * penalty <lambda, c> (safe_multi_agent_RL/meta_agent.py:21-22) fused in.
  *   pos_x,pos_y u8 [A][ld] in/out     actions u8 [A][ld] in 0..4
  *   obs     f32 [2A][ld]  out, NULL to skip
- *   reward  f32 [A][ld]   out   w_a * -(sum of pair penalties)
+ *   reward  f32 [A][ld]   out   w_a * -(sum of pair penalties)   ([1][ld] unweighted if p->reward_rows == 1)
  *   cost    u8  [A][ld]   out   1 for a non-stay action
  *   done    u8  [A][ld]   out, NULL to skip (always 0 for Coverage)
  *   lambdas f64 [A]  in, penalty f32 [ld] out = sum_k lambda_k c_k; both NULL to skip
@@ -285,6 +288,16 @@ int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const
                           float* modR, int32_t* C, float* G, double* stats, double* stats_scratch,
                           int32_t n_agents, int32_t n_constraints, int64_t n_envs, int64_t ld,
                           smarl_stream_t stream);
+
+/* Same accounting for a rollout buffer that stores ONE reward row per env and step (Coverage with
+ * reward_rows = 1; Collision, whose reward is identical for all agents): reward_a[t] = w_a * reward_env[t].
+ *   reward_env f32 [T][ld]   weights f32 [A] (NULL = 1)   everything else as smarl_rollout_returns
+ *   (g_mode 0, 1, 2).  Reads 8/A instead of 4 + 4/A reward/penalty bytes per agent-step. */
+int smarl_rollout_returns_shared(const SmarlAccounting* acc, const float* reward_env, const float* weights,
+                                 const void* cost, int32_t cost_dtype, const float* penalty, float* R,
+                                 float* modR, int32_t* C, float* G, double* stats, double* stats_scratch,
+                                 int32_t n_agents, int32_t n_constraints, int64_t n_envs, int64_t ld,
+                                 smarl_stream_t stream);
 
 /* MetaAgent.update (meta_agent.py:32-39, leq=True) from an (all-reduced) stats vector:
  *   lambda_k <- max(0, lambda_k + lr * (stats[k] / stats[count] - thr_k)).

@@ -12,7 +12,7 @@ c_ptr = C.c_void_p
 
 class CoverageParams(C.Structure):
     _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("lut_len", C.c_int32),
-                ("reserved", C.c_int32), ("lut", c_ptr), ("weights", c_ptr)]
+                ("reward_rows", C.c_int32), ("lut", c_ptr), ("weights", c_ptr)]
 
 
 class Accounting(C.Structure):
@@ -74,6 +74,8 @@ PROTOTYPES = {
     "smarl_rollout_penalty": (C.c_int, [c_ptr, i32, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_rollout_returns": (C.c_int, [P(Accounting), c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
+    "smarl_rollout_returns_shared": (C.c_int, [P(Accounting), c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr,
+                                               c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
     "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64, i32]),
     "smarl_host_session_destroy": (None, [c_ptr]),

@@ -50,9 +50,12 @@ def _headers_mtime() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    hm = _headers_mtime()
+    newest = max([hm] + [os.path.getmtime(os.path.join(CSRC, f)) for f in sources()])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH            # up to date (e.g. the prebuilt library shipped to the GPU box without objects)
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
-    hm = _headers_mtime()
     jobs = []
     objs = []
     for src in sources():

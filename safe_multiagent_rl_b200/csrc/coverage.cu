@@ -34,6 +34,7 @@ struct CoverageStepArgs {
   int64_t ld;
   int32_t size;
   int32_t lut_len;
+  int32_t reward_rows;
 };
 
 constexpr int kStepThreads = 128;
@@ -135,6 +136,10 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
     r1 = k == 1 ? r : r1;
     r2 = k == 2 ? r : r2;
     r3 = k == 3 ? r : r3;
+  }
+  if (a.reward_rows == 1) {                      // one unweighted row; the accounting applies w_a
+    st_stream_f4(a.reward + e0, make_float4(r0, r1, r2, r3));
+    return;
   }
   {
     uint32_t off = e0;
@@ -389,6 +394,7 @@ extern "C" int smarl_coverage_step(const SmarlCoverageParams* p, uint8_t* pos_x,
   a.cost = cost; a.done = done; a.lambdas = lambdas; a.penalty = penalty;
   a.lut = p->lut; a.weights = p->weights;
   a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.lut_len = p->lut_len;
+  a.reward_rows = p->reward_rows == 1 ? 1 : 0;
   if ((int64_t)(2 * p->n_agents + 1) * ld >= (1ll << 32)) {
     set_error("(2A+1)*ld = %lld exceeds 32-bit element offsets; split the env batch", (long long)((2 * p->n_agents + 1) * ld));
     return SMARL_EUNSUPPORTED;

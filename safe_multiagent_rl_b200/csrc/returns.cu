@@ -106,6 +106,8 @@ struct ReturnsArgs {
   int64_t n_envs;
   int64_t ld;
   int32_t A, K, T, g_mode;
+  int32_t cost_rows_only;  // 1: only the K constraint rows (the shared-reward kernel handles the agents)
+  const float* weights;    // shared-reward kernel: [A] or NULL
 };
 
 // One CTA = one row (agent a, or constraint k) x 512 envs.  Rows of the same env chunk get
@@ -115,8 +117,8 @@ struct ReturnsArgs {
 template <typename CT, int THREADS, int GM>
 __global__ void __launch_bounds__(THREADS) returns_kernel(const ReturnsArgs a) {
   __shared__ double s_red[THREADS / 32];
-  const int rows = a.A + a.K;
-  const int row = blockIdx.x % rows;
+  const int rows = (a.cost_rows_only ? 0 : a.A) + a.K;
+  const int row = (int)(blockIdx.x % rows) + (a.cost_rows_only ? a.A : 0);
   const int64_t chunk = blockIdx.x / rows;
   const int64_t g = chunk * THREADS + threadIdx.x;
   const bool live = g < a.n_groups;
@@ -270,6 +272,98 @@ __global__ void __launch_bounds__(THREADS) returns_kernel(const ReturnsArgs a) {
   }
 }
 
+// Shared-reward accounting: one reward row per env and step, reward_a[t] = w_a * rew[t].  One CTA per
+// 512-env chunk runs ONE backward Horner pair (G_rew, G_pen) per env and emits all A agents' rows:
+//   G[t][a] = w_a * G_rew[t] - G_pen[t],  R_a = w_a * G_rew[0],  modR_a = w_a * G_rew[0] - G_pen[0].
+template <int GM>
+__global__ void __launch_bounds__(kAccThreads) returns_shared_kernel(const ReturnsArgs a) {
+  __shared__ double s_red[kAccThreads / 32];
+  __shared__ float s_w[SMARL_MAX_AGENTS];
+  if (threadIdx.x < SMARL_MAX_AGENTS) s_w[threadIdx.x] = (a.weights && threadIdx.x < a.A) ? a.weights[threadIdx.x] : 1.0f;
+  __syncthreads();
+  const int64_t chunk = blockIdx.x;
+  const int64_t g = chunk * kAccThreads + threadIdx.x;
+  const bool live = g < a.n_groups;
+  const int64_t e0 = (live ? g : 0) * 4;
+  const int64_t ld = a.ld;
+  const int T = a.T, A = a.A;
+  const double gamma = a.gamma;
+  double g_rew[4] = {0, 0, 0, 0}, g_pen[4] = {0, 0, 0, 0};
+  if (GM != 2) {
+#pragma unroll 2
+    for (int t = T - 1; t >= 0; --t) {
+      const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+      const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g_rew[k] = (double)rr[k] + gamma * g_rew[k];
+        g_pen[k] = (double)pp[k] + gamma * g_pen[k];
+      }
+      if (a.g_mode == 1 && live) {
+        for (int i = 0; i < A; ++i) {
+          const double w = (double)s_w[i];
+          st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0,
+                       make_float4((float)(w * g_rew[0] - g_pen[0]), (float)(w * g_rew[1] - g_pen[1]),
+                                   (float)(w * g_rew[2] - g_pen[2]), (float)(w * g_rew[3] - g_pen[3])));
+        }
+      }
+    }
+  } else {
+    double disc = 1.0;
+    for (int t = 0; t < T; ++t) {
+      const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+      const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g_rew[k] += disc * (double)rr[k];
+        g_pen[k] += disc * (double)pp[k];
+      }
+      if (live) {
+        for (int i = 0; i < A; ++i) {
+          const double w = (double)s_w[i];
+          st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0,
+                       make_float4((float)(disc * (w * rr[0] - pp[0])), (float)(disc * (w * rr[1] - pp[1])),
+                                   (float)(disc * (w * rr[2] - pp[2])), (float)(disc * (w * rr[3] - pp[3]))));
+        }
+      }
+      disc *= gamma;
+    }
+  }
+  if (live) {
+    for (int i = 0; i < A; ++i) {
+      const double w = (double)s_w[i];
+      st_stream_f4(a.R + (int64_t)i * ld + e0, make_float4((float)(w * g_rew[0]), (float)(w * g_rew[1]),
+                                                           (float)(w * g_rew[2]), (float)(w * g_rew[3])));
+      st_stream_f4(a.modR + (int64_t)i * ld + e0,
+                   make_float4((float)(w * g_rew[0] - g_pen[0]), (float)(w * g_rew[1] - g_pen[1]),
+                               (float)(w * g_rew[2] - g_pen[2]), (float)(w * g_rew[3] - g_pen[3])));
+    }
+  }
+  if (a.partials) {
+    double* out = a.partials + chunk * stats_len(a.A, a.K);
+    double v_rew = 0.0, v_pen = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool valid = live && (e0 + k < a.n_envs);
+      v_rew += valid ? g_rew[k] : 0.0;
+      v_pen += valid ? g_pen[k] : 0.0;
+    }
+    const double b_rew = block_sum<kAccThreads>(v_rew, s_red);
+    const double b_pen = block_sum<kAccThreads>(v_pen, s_red);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < A; ++i) {
+        out[2 * a.K + i] = (double)s_w[i] * b_rew;
+        out[2 * a.K + A + i] = (double)s_w[i] * b_rew - b_pen;
+      }
+      out[2 * a.K + 2 * A] = 0.0;
+    }
+  }
+}
+
 // stats[j] = sum over rows of partials[row][j], fixed order; the count slot is n_envs.
 __global__ void __launch_bounds__(256)
 stats_finalize_kernel(const double* __restrict__ partials, int64_t n_rows, int n_stats, double count,
@@ -377,6 +471,7 @@ extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* re
   a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma;
   a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
   a.A = n_agents; a.K = n_constraints; a.T = acc->n_steps; a.g_mode = acc->g_mode;
+  a.cost_rows_only = 0; a.weights = nullptr;
   constexpr int threads = kReturnsThreads;
   const int64_t n_chunks = (a.n_groups + threads - 1) / threads;
   const int64_t blocks = n_chunks * (n_agents + n_constraints);
@@ -402,6 +497,51 @@ extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* re
   if (stats)
     return launch_stats_finalize(stats_scratch, n_chunks, n_agents, n_constraints, n_envs, stats,
                                  (cudaStream_t)stream);
+  return SMARL_OK;
+}
+
+extern "C" int smarl_rollout_returns_shared(const SmarlAccounting* acc, const float* reward_env,
+                                            const float* weights, const void* cost, int32_t cost_dtype,
+                                            const float* penalty, float* R, float* modR, int32_t* C, float* G,
+                                            double* stats, double* stats_scratch, int32_t n_agents,
+                                            int32_t n_constraints, int64_t n_envs, int64_t ld,
+                                            smarl_stream_t stream) {
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(acc != nullptr, "accounting params is NULL");
+  SMARL_REQUIRE(acc->n_steps >= 1, "n_steps=%d must be >= 1", acc->n_steps);
+  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 2, "shared-reward accounting supports g_mode 0..2 (got %d)", acc->g_mode);
+  SMARL_REQUIRE(n_agents >= 1 && n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", n_agents);
+  SMARL_REQUIRE(n_constraints >= 1 && n_constraints <= SMARL_MAX_AGENTS, "n_constraints=%d outside 1..32",
+                n_constraints);
+  SMARL_REQUIRE(reward_env && cost && R && modR && C, "null required pointer");
+  SMARL_REQUIRE(acc->g_mode == 0 || G, "g_mode != 0 needs G");
+  SMARL_REQUIRE((stats == nullptr) == (stats_scratch == nullptr), "stats and stats_scratch go together");
+  SMARL_REQUIRE(aligned16(reward_env) && aligned16(cost) && aligned16(penalty) && aligned16(R) && aligned16(modR) &&
+                    aligned16(C) && aligned16(G), "pointers must be 16-byte aligned");
+  ReturnsArgs a;
+  a.reward = reward_env; a.cost = cost; a.penalty = penalty; a.n_active = nullptr; a.R = R; a.modR = modR; a.C = C;
+  a.G = G; a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma;
+  a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
+  a.A = n_agents; a.K = n_constraints; a.T = acc->n_steps; a.g_mode = acc->g_mode;
+  a.cost_rows_only = 1; a.weights = weights;
+  const int64_t n_chunks = (a.n_groups + kAccThreads - 1) / kAccThreads;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (acc->g_mode == 2)
+    returns_shared_kernel<2><<<(unsigned)n_chunks, kAccThreads, 0, st>>>(a);
+  else
+    returns_shared_kernel<1><<<(unsigned)n_chunks, kAccThreads, 0, st>>>(a);
+  const int64_t blocks = n_chunks * n_constraints;      // the K constraint rows: C_k, violation counts
+  if (cost_dtype == SMARL_COST_U8)
+    returns_kernel<uint8_t, kReturnsThreads, 1><<<(unsigned)blocks, kReturnsThreads, 0, st>>>(a);
+  else if (cost_dtype == SMARL_COST_I32)
+    returns_kernel<int32_t, kReturnsThreads, 1><<<(unsigned)blocks, kReturnsThreads, 0, st>>>(a);
+  else if (cost_dtype == SMARL_COST_F32)
+    returns_kernel<float, kReturnsThreads, 1><<<(unsigned)blocks, kReturnsThreads, 0, st>>>(a);
+  else
+    SMARL_REQUIRE(false, "bad cost_dtype %d", cost_dtype);
+  SMARL_CUDA(cudaGetLastError());
+  if (stats)
+    return launch_stats_finalize(stats_scratch, n_chunks, n_agents, n_constraints, n_envs, stats, st);
   return SMARL_OK;
 }
 

@@ -102,12 +102,20 @@ class BatchedEnv:
         act = self._ingest_actions(actions, agent_major)
         if out is not None:
             buf, t = out
-            reward, cost, done, penalty = buf.reward[t], buf.cost[t], buf.done[t], buf.penalty[t]
+            reward, cost, penalty = buf.reward[t], buf.cost[t], buf.penalty[t]
+            done = buf.done[t] if buf.done is not None else None
         else:
             reward, cost, done, penalty = self.reward, self.cost, self.done, self.penalty
         self._step_impl(act, reward, cost, done, lambdas, penalty if lambdas is not None else None)
         self.t += 1
+        if done is None:                       # not stored per step: this env's agents never finish
+            done = self._zero_done()
         return self._views(reward, cost, done)
+
+    def _zero_done(self):
+        if not hasattr(self, "_done_zeros"):
+            self._done_zeros = self._alloc(self.n_agents, torch.uint8)
+        return self._done_zeros
 
     def _rollout_outputs(self, T, g_mode, out, g_scratch_rows):
         """Allocate (or reuse from ``out``) the product buffers of a fused rollout."""
@@ -135,9 +143,16 @@ class BatchedEnv:
                  G=None if o["G_"] is None else env_major(o["G_"], E), stats=Stats(o["stats_vec"], A, K))
         return o
 
-    def new_rollout_buffer(self, n_steps, g_mode=G_REWARD_TO_GO):
+    def new_rollout_buffer(self, n_steps, g_mode=G_REWARD_TO_GO, lean=False):
+        """Device slabs for one batch of episodes.  ``lean=True`` (envs that support it) stores only what
+        the accounting needs: one env-reward row instead of n_agents weighted rows, and no per-step done
+        flags when agents never finish -- fewer HBM bytes per step; ``env.step`` then returns the
+        ``[E, 1]`` env reward and per-agent rewards are ``buffer.rewards()``."""
+        if lean and not getattr(self, "supports_lean", False):
+            raise ValueError(f"{type(self).__name__} has no lean rollout buffer")
         return RolloutBuffer(n_steps, self.n_agents, self.n_constraints, self.n_envs, self.cost_dtype,
-                             self.device, g_mode)
+                             self.device, g_mode, shared_reward=lean, weights=getattr(self, "_weights", None) if lean else None,
+                             store_done=not (lean and getattr(self, "never_done", False)))
 
     def rollout_closed_loop(self, policy, n_steps, lambdas, gamma, thresholds=None, buffer=None,
                             g_mode=G_REWARD_TO_GO):

@@ -43,6 +43,8 @@ class BatchedCoverageDiscrete(BatchedEnv):
     action_space = 5
     cost_dtype = torch.uint8
     action_dtype = torch.uint8
+    never_done = True          # check_done is all-False (coverage.py:97-98)
+    supports_lean = True       # reward_a = w_a * rew: one env-reward row is enough
 
     def __init__(self, size, n_agents, n_envs=1, shuffle=False, agents_size=0.5, fieldview_size=None,
                  weights=None, device="cuda", starts=None, env_offset=0, seed=0):
@@ -72,6 +74,8 @@ class BatchedCoverageDiscrete(BatchedEnv):
             torch.as_tensor(np.asarray(self.weights[:A], dtype=np.float64), dtype=torch.float32).to(dev)
         self._params = _lib.CoverageParams(self.size, A, len(table), 0, _lib.ptr(self._lut),
                                            _lib.ptr(self._weights))
+        self._params_shared = _lib.CoverageParams(self.size, A, len(table), 1, _lib.ptr(self._lut),
+                                                  _lib.ptr(self._weights))
         if starts is None:
             draws = np.random.rand(E, 2 * A, 2)
             starts = np.floor(draws[:, A:, :] * self.size)
@@ -104,8 +108,11 @@ class BatchedCoverageDiscrete(BatchedEnv):
                                              self.n_agents, self.n_envs, self.ld, _lib.stream_ptr()))
 
     def _step_impl(self, act, reward, cost, done, lambdas, penalty):
+        params = self._params
+        if reward.shape[0] == 1 and self.n_agents > 1:        # lean rollout buffer: one unweighted env-reward row
+            params = self._params_shared
         _lib.check(self.lib.smarl_coverage_step(
-            C.byref(self._params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(act),
+            C.byref(params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(act),
             _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
             _lib.ptr(penalty), self.n_envs, self.ld, _lib.stream_ptr()))
 

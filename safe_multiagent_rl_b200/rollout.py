@@ -70,7 +70,10 @@ class RolloutBuffer:
     """[T, rows, ld] device slabs for one batch of n_envs episodes."""
 
     def __init__(self, n_steps, n_agents, n_constraints, n_envs, cost_dtype=torch.uint8, device="cuda",
-                 g_mode=G_REWARD_TO_GO):
+                 g_mode=G_REWARD_TO_GO, shared_reward=False, weights=None, store_done=True):
+        """shared_reward: store ONE reward row per env and step (the unweighted env reward; ``weights``
+        [A] f32 device tensor or None are applied by the accounting kernel) instead of A per-agent rows.
+        store_done: keep per-step done flags (envs whose agents never finish do not need them)."""
         self.T, self.A, self.K, self.E = int(n_steps), int(n_agents), int(n_constraints), int(n_envs)
         self.ld = pad_ld(n_envs)
         self.device = torch.device(device)
@@ -79,9 +82,10 @@ class RolloutBuffer:
         self.cost_dtype = cost_dtype
         self.cost_code = {torch.uint8: _lib.COST_U8, torch.int32: _lib.COST_I32, torch.float32: _lib.COST_F32}[cost_dtype]
         T, A, K, E = self.T, self.A, self.K, self.E
-        self.reward = alloc(A, E, torch.float32, device, (T,))
+        self.shared_reward, self.weights = bool(shared_reward), weights
+        self.reward = alloc(1 if shared_reward else A, E, torch.float32, device, (T,))
         self.cost = alloc(K, E, cost_dtype, device, (T,))
-        self.done = alloc(A, E, torch.uint8, device, (T,))
+        self.done = alloc(A, E, torch.uint8, device, (T,)) if store_done else None
         self.penalty = alloc(1, E, torch.float32, device, (T,))[:, 0]
         self.R = alloc(A, E, torch.float32, device)
         self.modR = alloc(A, E, torch.float32, device)
@@ -94,7 +98,11 @@ class RolloutBuffer:
 
     # ---- views in the reference's orientation ([.., env, agent]) ------------------------------
     def rewards(self):
-        return env_major(self.reward, self.E)                # [T, E, A]
+        """[T, E, A] per-agent rewards (materialised from the env reward and the weights if shared)."""
+        if self.shared_reward:
+            w = self.weights if self.weights is not None else torch.ones(self.A, device=self.reward.device)
+            return self.reward[:, 0, : self.E, None] * w[None, None, :]
+        return env_major(self.reward, self.E)
 
     def modified_rewards(self):
         return self.rewards() - self.penalty[:, : self.E, None]
@@ -112,6 +120,14 @@ class RolloutBuffer:
             raise ValueError("buffer was created without G storage")
         thr = device_thresholds(thresholds, self.device)
         acc = make_accounting(gamma, self.T, g_mode, thr)
+        if self.shared_reward:
+            _lib.check(lib.smarl_rollout_returns_shared(
+                C.byref(acc), _lib.ptr(self.reward), _lib.ptr(self.weights), _lib.ptr(self.cost), self.cost_code,
+                _lib.ptr(self.penalty), _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum),
+                _lib.ptr(self.G if g_mode else None), _lib.ptr(self.stats_vec), _lib.ptr(self.stats_scratch), self.A,
+                self.K, self.E, self.ld, _lib.stream_ptr()))
+            return dict(R=env_major(self.R, self.E), modR=env_major(self.modR, self.E), C=env_major(self.Csum, self.E),
+                        G=env_major(self.G, self.E) if g_mode else None, stats=Stats(self.stats_vec, self.A, self.K))
         _lib.check(lib.smarl_rollout_returns(
             C.byref(acc), _lib.ptr(self.reward), _lib.ptr(self.cost), self.cost_code, _lib.ptr(self.penalty),
             _lib.ptr(n_active), _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum), _lib.ptr(self.G if g_mode else None),

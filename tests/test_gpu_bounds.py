@@ -71,6 +71,16 @@ def test_coverage_step_rollout_returns_stay_in_bounds(A, E):
         _lib.check(lib.smarl_coverage_rollout(C.byref(p), C.byref(acc), P(sx), P(sy), P(acts), P(lam), P(px),
                                               P(py), P(R), P(M), P(Cs), P(G) if g_mode else None,
                                               P(gs) if g_mode == 1 else None, P(stats), P(scratch), E, ld, st))
+    # lean path: one unweighted env-reward row per step, no done flags, shared-reward accounting
+    ps = _lib.CoverageParams(S, A, 9, 1, P(lut), P(w))
+    renv = ar.make(T, ld, f32)
+    for t in range(T):
+        _lib.check(lib.smarl_coverage_step(C.byref(ps), P(px), P(py), P(acts[t * A:]), P(obs), P(renv[t:]),
+                                           P(cost[t * A:]), None, P(lam), P(pen[t:]), E, ld, st))
+    for g_mode in (0, 1, 2):
+        acc = _lib.Accounting(0.99, T, g_mode, P(thr))
+        _lib.check(lib.smarl_rollout_returns_shared(C.byref(acc), P(renv), P(w), P(cost), 0, P(pen), P(R), P(M), P(Cs),
+                                                    P(G) if g_mode else None, P(stats), P(scratch), A, A, E, ld, st))
     _lib.check(lib.smarl_lambda_update(P(lam), P(stats), P(thr), 0.01, A, A, st))
     torch.cuda.synchronize()
     ar.check()

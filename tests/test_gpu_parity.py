@@ -530,3 +530,32 @@ def test_collision_normalize_state_and_shuffle_obs():
     want = np.concatenate([sh.state().cpu().numpy().reshape(E, 2 * A),
                            sh.landmarks[:, :E].t().cpu().numpy()], axis=1) / size
     assert np.array_equal(o, want.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- lean rollout buffer
+@pytest.mark.parametrize("size,A,E,T,fv,seed", COVERAGE_CASES[:4])
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+def test_coverage_lean_rollout_buffer(size, A, E, T, fv, seed, g_mode):
+    """lean=True stores one env-reward row (weights applied in the accounting kernel) and no done flags;
+    the episode products must match the oracle and the default buffer."""
+    s = smarl()
+    starts, actions, weights, lut = coverage_setup(size, A, E, T, fv, seed)
+    gamma, lam_np, thr = 0.999, np.linspace(0.1, 0.5, A), np.full(A, 0.4 * T)
+    lam = torch.as_tensor(lam_np, dtype=torch.float64, device="cuda")
+    env = s.BatchedCoverageDiscrete(size, A, n_envs=E, weights=weights, fieldview_size=fv, starts=starts)
+    pos = starts.copy()
+    def step_fn(t):
+        nonlocal pos
+        pos, r, c, _ = no.coverage_discrete_step(pos, actions[t], size, lut, weights)
+        return r, c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    want_G = {0: None, 1: want["G"], 2: no.discounted_terms(want["mod_reward"], gamma)}[g_mode]
+    scale = np.max(np.abs(want["modR"])) + 1e-12
+    act = torch.as_tensor(actions.astype(np.uint8), device="cuda")
+    lean = env.new_rollout_buffer(T, g_mode=max(g_mode, 1), lean=True)
+    assert lean.reward.shape[1] == 1 and lean.done is None
+    out = env.rollout_closed_loop(lambda obs, t: act[t], T, lam, gamma, thresholds=thr, buffer=lean, g_mode=g_mode)
+    check_products(out, want, want_G, thr, E, scale)
+    close(lean.rewards().cpu().numpy(), want["reward"], np.abs(want["reward"]).max() + 1e-12)
+    obs, r, c, d = env.step(act[0], out=(lean, 0))
+    assert r.shape == (E, 1) and d.shape == (E, A) and not d.any()
