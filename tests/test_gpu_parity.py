@@ -559,3 +559,36 @@ def test_coverage_lean_rollout_buffer(size, A, E, T, fv, seed, g_mode):
     close(lean.rewards().cpu().numpy(), want["reward"], np.abs(want["reward"]).max() + 1e-12)
     obs, r, c, d = env.step(act[0], out=(lean, 0))
     assert r.shape == (E, 1) and d.shape == (E, A) and not d.any()
+
+
+# ----------------------------------------------------------------------------- drop-in protocol (lists in / lists out)
+def test_single_env_adapter_follows_the_reference_protocol():
+    """SingleEnvAdapter(n_envs=1) behaves like a reference env object for the unmodified driver loop
+    (main.py:28-57): lists in, lists out, same values as the one-env CPU port."""
+    from oracle import scalar_port as sp
+    s = smarl()
+    rng = np.random.default_rng(0)
+    size, A, T = 5, 3, 25
+    starts = rng.integers(0, size, (A, 2))
+    port = sp.CoveragePort(size, A, starts, weights=[1.0, 2.0, 3.0])
+    env = s.SingleEnvAdapter(s.BatchedCoverageDiscrete(size, A, n_envs=1, weights=[1.0, 2.0, 3.0], starts=starts[None]))
+    assert env.action_space == 5 and env.state_space == 2 * A and env.constraint_space == [1] * A   # attrs main.py reads
+    st, st_p = env.reset(), port.reset()
+    assert st == st_p and isinstance(st, list) and isinstance(st[0], list)
+    for t in range(T):
+        actions = [int(a) for a in rng.integers(0, 5, A)]
+        st, r, c, d = env.step(actions)
+        st_p, r_p, c_p, d_p = port.step(actions)
+        assert st == st_p and c == c_p and d == d_p
+        np.testing.assert_allclose(r, r_p, rtol=1e-6)
+    # continuous actions arrive as nested [[dx, dy]] lists (agent.py:124-125)
+    lm, cs = rng.random((1, 2)) * 5, rng.random((A, 2)) * 5
+    cport = sp.CollisionPort(5, A, cs, lm)
+    cenv = s.SingleEnvAdapter(s.BatchedCollisionAvoidance(5, A, n_envs=1, starts=cs[None], landmarks=lm[None]))
+    assert cenv.reset() == cport.reset()
+    for t in range(T):
+        act = rng.normal(0, 0.5, (A, 1, 2)).astype(np.float32).astype(np.float64).tolist()
+        st, r, c, d = cenv.step(act)
+        st_p, r_p, c_p, d_p = cport.step(act)
+        assert st == st_p and d == d_p and c == [float(c_p[0])]
+        np.testing.assert_allclose(r, r_p, rtol=1e-6)
