@@ -227,7 +227,8 @@ typedef struct {
   int32_t obs_landmarks; /* 1: obs has 2L extra rows (shuffle=True layout, :65-68,:141-142)    */
   double agents_size;    /* 0.25: reach radius, 2x = collision distance   :49,:123,:155        */
   int32_t normalize_state; /* 1: obs = state / size (_normalize_state, :87-88,:146-147,:164-165)  */
-  int32_t reserved;
+  int32_t reward_rows;     /* step only: 0 (= A) identical per-agent rows (:130); 1: one row [1][ld]
+                              for smarl_rollout_returns_shared                                    */
 } SmarlCollisionParams;
 
 /* CollisionAvoidance.reset/_restart (:72-98) for shuffle=False: state <- start, done <- 0.

@@ -35,7 +35,7 @@ class CongestionParams(C.Structure):
 class CollisionParams(C.Structure):
     _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("n_landmarks", C.c_int32),
                 ("obs_landmarks", C.c_int32), ("agents_size", C.c_double), ("normalize_state", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reward_rows", C.c_int32)]
 
 
 P = C.POINTER

@@ -36,6 +36,7 @@ struct CollisionStepArgs {
   int32_t L;
   int32_t obs_landmarks;
   int32_t normalize;
+  int32_t reward_rows;
 };
 
 constexpr int kCollThreads = 128;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const Coll
       a.done[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
     }
     if (a.done_out) a.done_out[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
-    a.reward[i * ld + e] = rf;
+    if (a.reward_rows != 1 || i == 0) a.reward[i * ld + e] = rf;
     if (a.obs) {
       a.obs[(2 * i) * ld + e] = obs_value(px[i], a.size, a.normalize);
       a.obs[(2 * i + 1) * ld + e] = obs_value(py[i], a.size, a.normalize);
@@ -397,6 +398,7 @@ extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x
   a.penalty = penalty; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size;
   a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
   a.normalize = p->normalize_state;
+  a.reward_rows = p->reward_rows == 1 ? 1 : 0;
   const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
   if (int rc = launch_collision_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;

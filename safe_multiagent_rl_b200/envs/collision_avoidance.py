@@ -26,6 +26,7 @@ class BatchedCollisionAvoidance(BatchedEnv):
     action_space = 2
     cost_dtype = torch.int32
     action_dtype = torch.float32
+    supports_lean = True       # the reward is one value shared by all agents (collision_avoidance.py:129-130)
 
     def __init__(self, size, n_agents, n_envs=1, n_landmarks=1, shuffle=False, agents_size=0.25,
                  normalize_state=False, device="cuda", starts=None, landmarks=None, env_offset=0, seed=0):
@@ -71,6 +72,8 @@ class BatchedCollisionAvoidance(BatchedEnv):
         self.penalty = self._alloc(1, torch.float32)[0]
         self._params = _lib.CollisionParams(self.size, A, self.L, int(self.shuffle), self.agents_size,
                                             int(self.normalize_state), 0)
+        self._params_shared = _lib.CollisionParams(self.size, A, self.L, int(self.shuffle), self.agents_size,
+                                                   int(self.normalize_state), 1)
 
     def _draw_starts(self, episode):
         self._draw_float_starts(episode, 2)                      # agents (:82-84) ...
@@ -91,8 +94,9 @@ class BatchedCollisionAvoidance(BatchedEnv):
             _lib.ptr(self.obs), self.n_envs, self.ld, _lib.stream_ptr()))
 
     def _step_impl(self, act, reward, cost, done, lambdas, penalty):
+        params = self._params_shared if (reward.shape[0] == 1 and self.n_agents > 1) else self._params
         _lib.check(self.lib.smarl_collision_step(
-            C.byref(self._params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done),
+            C.byref(params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.agent_done),
             _lib.ptr(act), _lib.ptr(self.landmarks), _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost),
             _lib.ptr(done), _lib.ptr(self.episode_len), _lib.ptr(lambdas), _lib.ptr(penalty), self.n_envs, self.ld,
             _lib.stream_ptr()))

@@ -592,3 +592,24 @@ def test_single_env_adapter_follows_the_reference_protocol():
         st_p, r_p, c_p, d_p = cport.step(act)
         assert st == st_p and d == d_p and c == [float(c_p[0])]
         np.testing.assert_allclose(r, r_p, rtol=1e-6)
+
+
+def test_collision_lean_rollout_buffer():
+    s = smarl()
+    size, A, L, E, T, seed = COLLISION_CASES[0]
+    starts, landmarks, actions = collision_setup(size, A, L, E, T, seed)
+    gamma, lam_np, thr = 0.99, np.array([0.5]), np.array([1.0])
+    env = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=L, starts=starts, landmarks=landmarks)
+    pos, done = starts.copy(), np.zeros((E, A), dtype=bool)
+    def step_fn(t):
+        nonlocal pos, done
+        pos, r, c, done, _ = no.collision_step(pos, done, actions[t].astype(np.float64), landmarks, size)
+        return r.astype(np.float32).astype(np.float64), c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    act = torch.as_tensor(actions, device="cuda")
+    lean = env.new_rollout_buffer(T, lean=True)
+    assert lean.reward.shape[1] == 1 and lean.done is not None          # agents do finish here: done flags are kept
+    out = env.rollout_closed_loop(lambda obs, t: act[t], T, torch.as_tensor(lam_np, device="cuda"), gamma,
+                                  thresholds=thr, buffer=lean)
+    check_products(out, want, want["G"], thr, E, np.abs(want["modR"]).max())
+    assert np.array_equal(lean.done[T - 1][:, :E].t().cpu().numpy().astype(bool), done)
