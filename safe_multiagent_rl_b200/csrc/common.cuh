@@ -80,6 +80,21 @@ __device__ __forceinline__ float4 ld_stream_f4(const void* p) {
                : "l"(p));
   return v;
 }
+// State that is re-read by the NEXT launch (positions between env steps): ask L2 to keep it
+// (evict_last) so that, when a batch's positions fit in the 126 MB L2, they never round-trip HBM.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint32_t ld_keep_u32(const void* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_keep_u32(void* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
 // Coherent load for data this kernel wrote itself earlier (scratch re-reads): never .nc.
 __device__ __forceinline__ float4 ld_f4(const void* p) {
   float4 v;

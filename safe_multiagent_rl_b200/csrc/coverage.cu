@@ -6,6 +6,8 @@
 // envs share the SIMD-in-word move / cost logic (one byte per env); the pair loop runs per env
 // on agents packed (x | y << 8).  No shared-memory staging of state: every byte is touched
 // once, already coalesced.  Shared memory only holds the penalty table.
+#include <stdlib.h>
+
 #include "coverage.cuh"
 #include "stats.cuh"
 
@@ -35,6 +37,7 @@ struct CoverageStepArgs {
   int32_t size;
   int32_t lut_len;
   int32_t reward_rows;
+  int32_t keep_pos;   // positions fit in L2: load/store them with an evict_last policy
 };
 
 constexpr int kStepThreads = 128;
@@ -88,12 +91,18 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
   const uint32_t e0 = (uint32_t)g * 4u;
 
   uint32_t xw[A], yw[A], aw[A];
+  const uint64_t keep = l2_keep_policy();
   {
     uint32_t off = e0;
 #pragma unroll
     for (int i = 0; i < A; ++i, off += ld) {
-      xw[i] = ld_stream_u32(a.pos_x + off);
-      yw[i] = ld_stream_u32(a.pos_y + off);
+      if (a.keep_pos) {
+        xw[i] = ld_keep_u32(a.pos_x + off, keep);
+        yw[i] = ld_keep_u32(a.pos_y + off, keep);
+      } else {
+        xw[i] = ld_stream_u32(a.pos_x + off);
+        yw[i] = ld_stream_u32(a.pos_y + off);
+      }
       aw[i] = ld_stream_u32(a.actions + off);
     }
   }
@@ -105,8 +114,13 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
     for (int i = 0; i < A; ++i, off += ld, obs_off += 2u * ld) {
       grid_move4_s127(xw[i], yw[i], aw[i], ge_bias);       // coverage.py:174-189
       const uint32_t cw = move_cost4(aw[i]);               // coverage.py:191-196
-      st_stream_u32(a.pos_x + off, xw[i]);
-      st_stream_u32(a.pos_y + off, yw[i]);
+      if (a.keep_pos) {
+        st_keep_u32(a.pos_x + off, xw[i], keep);
+        st_keep_u32(a.pos_y + off, yw[i], keep);
+      } else {
+        st_stream_u32(a.pos_x + off, xw[i]);
+        st_stream_u32(a.pos_y + off, yw[i]);
+      }
       st_stream_u32(a.cost + off, cw);
       if (a.done) st_stream_u32(a.done + off, 0u);         // coverage.py:97-98
       if (a.obs) {
@@ -395,6 +409,12 @@ extern "C" int smarl_coverage_step(const SmarlCoverageParams* p, uint8_t* pos_x,
   a.lut = p->lut; a.weights = p->weights;
   a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.lut_len = p->lut_len;
   a.reward_rows = p->reward_rows == 1 ? 1 : 0;
+  {
+    // positions (2 B per agent and env) are re-read by the next step: keep them in L2 when they fit comfortably
+    static const char* env_keep = getenv("SMARL_KEEP_POS");
+    const int64_t pos_bytes = 2 * (int64_t)p->n_agents * n_envs;
+    a.keep_pos = env_keep ? atoi(env_keep) : (pos_bytes <= (48ll << 20) ? 1 : 0);
+  }
   if ((int64_t)(2 * p->n_agents + 1) * ld >= (1ll << 32)) {
     set_error("(2A+1)*ld = %lld exceeds 32-bit element offsets; split the env batch", (long long)((2 * p->n_agents + 1) * ld));
     return SMARL_EUNSUPPORTED;

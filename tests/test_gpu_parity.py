@@ -613,3 +613,43 @@ def test_collision_lean_rollout_buffer():
                                   thresholds=thr, buffer=lean)
     check_products(out, want, want["G"], thr, E, np.abs(want["modR"]).max())
     assert np.array_equal(lean.done[T - 1][:, :E].t().cpu().numpy().astype(bool), done)
+
+
+# ----------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("E", [1, 2, 3, 4, 5, 15, 16, 17])
+def test_tiny_batches_all_envs(E):
+    """n_envs around the 4-env thread group and the 16-env padding, one-step episodes, one agent,
+    gamma = 1, no lambdas / thresholds."""
+    s = smarl()
+    rng = np.random.default_rng(E)
+    # Coverage, single agent: no pairs, reward 0, cost = moved
+    env = s.BatchedCoverageDiscrete(4, 1, n_envs=E, starts=rng.integers(0, 4, (E, 1, 2)))
+    act = rng.integers(0, 5, (1, E, 1)).astype(np.uint8)
+    out = env.rollout_closed_loop(lambda obs, t: torch.as_tensor(act[t], device="cuda"), 1, None, 1.0)
+    assert np.array_equal(out["C"].cpu().numpy(), (act[0] != 4).astype(np.int64)) and float(out["R"].abs().max()) == 0.0
+    assert float(out["stats"].count) == E
+    # Congestion with two agents on a 1x1 grid, T = 3, gamma = 1
+    st = np.zeros((E, 2, 2), dtype=np.int64)
+    dem = np.array([[2.0, 3.0], [4.0, 5.0]])
+    cenv = s.BatchedCongestion(1, 2, n_envs=E, noise=0.0, starts=st, demand_rate=dem)
+    acts = rng.integers(0, 5, (3, E, 2))
+    pos = st.copy()
+    def step_fn(t):
+        nonlocal pos
+        pos, r, c, _, _ = no.congestion_step(pos, acts[t], acts[t], 1, dem)
+        return r.astype(np.float32).astype(np.float64), c
+    want = no.rollout(step_fn, 3, 1.0, [0.0])
+    a_dev = torch.as_tensor(acts.astype(np.uint8), device="cuda")
+    o = cenv.rollout_closed_loop(lambda obs, t: a_dev[t], 3, None, 1.0)
+    assert np.array_equal(cenv.state().cpu().numpy(), pos) and np.array_equal(o["C"].cpu().numpy(), want["C"])
+    close(o["R"].cpu().numpy(), want["R"], np.abs(want["R"]).max() + 1e-9)
+    fo = cenv.rollout(kernel_layout(acts.astype(np.uint8), cenv.ld), gamma=1.0, g_mode=1)
+    close(fo["G"].cpu().numpy(), want["G"], np.abs(want["R"]).max() + 1e-9)
+    # Collision with a single agent that starts on the landmark: done after the first step, episode length 1
+    lm = rng.random((E, 1, 2)) * 3
+    kenv = s.BatchedCollisionAvoidance(3, 1, n_envs=E, starts=lm.copy(), landmarks=lm)
+    zero = torch.zeros(4, 2, kenv.ld, device="cuda")
+    ko = kenv.rollout(zero, gamma=0.9, g_mode=1)
+    assert np.array_equal(ko["n_active"].cpu().numpy(), np.ones(E, dtype=np.int32))
+    assert float(ko["R"].abs().max()) == 0.0 and bool(kenv.agent_done[:, :E].all())
+    assert float(ko["G"].abs().max()) == 0.0
