@@ -132,6 +132,12 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_torch = None
+
+
 def stream_ptr():
-    import torch
-    return torch.cuda.current_stream().cuda_stream
+    global _torch
+    if _torch is None:
+        import torch
+        _torch = torch
+    return _torch.cuda.current_stream().cuda_stream

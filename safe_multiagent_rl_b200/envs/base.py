@@ -42,6 +42,8 @@ class BatchedEnv:
         """Return an ``[action_rows, ld]`` device tensor in the kernel layout (zero-copy when the
         caller already hands one over, e.g. ``env.action_buffer`` filled by the policies)."""
         rows = self.action_rows
+        if actions is self.action_buffer:                       # policies wrote the env's own buffer in place
+            return actions
         kernel_shape = isinstance(actions, torch.Tensor) and tuple(actions.shape) == (rows, self.ld)
         if kernel_shape and (agent_major or (rows, self.ld) != (self.n_envs, rows)):
             # already in the kernel layout (unambiguous shape, or the caller said so): zero-copy
@@ -101,16 +103,24 @@ class BatchedEnv:
         """
         act = self._ingest_actions(actions, agent_major)
         if out is not None:
-            buf, t = out
-            reward, cost, penalty = buf.reward[t], buf.cost[t], buf.penalty[t]
-            done = buf.done[t] if buf.done is not None else None
+            reward, cost, done, penalty, reward_v, cost_v, done_v = out[0].slot(out[1])
         else:
-            reward, cost, done, penalty = self.reward, self.cost, self.done, self.penalty
+            own = self.__dict__.get("_own_slot")
+            if own is None:
+                E = self.n_envs
+                own = self._own_slot = (self.reward, self.cost, self.done, self.penalty, env_major(self.reward, E),
+                                        env_major(self.cost, E), env_major(self.done, E))
+            reward, cost, done, penalty, reward_v, cost_v, done_v = own
         self._step_impl(act, reward, cost, done, lambdas, penalty if lambdas is not None else None)
         self.t += 1
-        if done is None:                       # not stored per step: this env's agents never finish
-            done = self._zero_done()
-        return self._views(reward, cost, done)
+        if done_v is None:                     # not stored per step: this env's agents never finish
+            done_v = self.__dict__.get("_done_zeros_v")
+            if done_v is None:
+                done_v = self._done_zeros_v = env_major(self._zero_done(), self.n_envs)
+        obs_v = self.__dict__.get("_obs_v")
+        if obs_v is None:
+            obs_v = self._obs_v = env_major(self.obs, self.n_envs)
+        return obs_v, reward_v, cost_v, done_v
 
     def _zero_done(self):
         if not hasattr(self, "_done_zeros"):

@@ -96,6 +96,20 @@ class RolloutBuffer:
         self.stats_scratch = torch.zeros(max(1, lib.smarl_stats_scratch_len(A, K, E)), dtype=torch.float64,
                                          device=device)
 
+    def slot(self, t):
+        """Step t's slabs and their reference-oriented views, built once and cached (tensor indexing
+        and view construction would otherwise dominate the host cost of a small-batch step)."""
+        try:
+            return self._slots[t]
+        except (AttributeError, KeyError):
+            if not hasattr(self, "_slots"):
+                self._slots = {}
+            r, c, p = self.reward[t], self.cost[t], self.penalty[t]
+            d = self.done[t] if self.done is not None else None
+            self._slots[t] = (r, c, d, p, env_major(r, self.E), env_major(c, self.E),
+                              env_major(d, self.E) if d is not None else None)
+            return self._slots[t]
+
     # ---- views in the reference's orientation ([.., env, agent]) ------------------------------
     def rewards(self):
         """[T, E, A] per-agent rewards (materialised from the env reward and the weights if shared)."""
