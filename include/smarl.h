@@ -180,6 +180,16 @@ int smarl_coverage_float_step(const SmarlCoverageFloatParams* p, double* pos_x, 
                               uint8_t* done, const double* lambdas, float* penalty, int64_t n_envs,
                               int64_t ld, smarl_stream_t stream);
 
+/* Fused open-loop episode of the float-position Coverage envs (as smarl_coverage_rollout).
+ *   start_x,start_y f64 [A][ld]; actions f32 [T][2A][ld] (mode 0) or u8 [T][A][ld] (mode 1)
+ *   final_x,final_y f64 [A][ld] (NULL ok); R, modR f32 [A][ld]; C f32 [A][ld] (float cost sums);
+ *   G f32 [T][A][ld] per g_mode (0..2); g_scratch f32 [2][T][ld] for g_mode 1. */
+int smarl_coverage_float_rollout(const SmarlCoverageFloatParams* p, const SmarlAccounting* acc,
+                                 const double* start_x, const double* start_y, const void* actions,
+                                 const double* lambdas, double* final_x, double* final_y, float* R, float* modR,
+                                 float* C, float* G, float* g_scratch, double* stats, double* stats_scratch,
+                                 int64_t n_envs, int64_t ld, smarl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Congestion
  * ---------------------------------------------------------------------------------- */

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "smarl_coverage_float_reset": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_coverage_float_step": (C.c_int, [P(CoverageFloatParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                             c_ptr, c_ptr, i64, i64, c_ptr]),
+    "smarl_coverage_float_rollout": (C.c_int, [P(CoverageFloatParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                               c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i64, i64, c_ptr]),
     "smarl_congestion_step": (C.c_int, [P(CongestionParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_congestion_rollout": (C.c_int, [P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,

@@ -3,6 +3,7 @@
 // float64 operations one by one (bit-exact); the pair penalty uses a multiply where the reference's
 // numpy scalar power calls libm pow (<= 1 ulp per term, invisible after the f32 rounding of rewards).
 #include "common.cuh"
+#include "stats.cuh"
 
 #ifndef SMARL_TU
 #define SMARL_TU -1
@@ -32,26 +33,18 @@ constexpr int kCovFThreads = 128;
 
 int launch_coverage_float_step(int mode, int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s);
 
-#if SMARL_TU_IS(0) || SMARL_TU_IS(1)
+#if SMARL_TU_IS(0) || SMARL_TU_IS(1) || SMARL_TU_IS(3) || SMARL_TU_IS(4)
+// One step of one env held in registers: moves every agent, returns the per-agent costs (f64) and the
+// unweighted env reward.  `act` points at this env's lane of step t's action rows.
 template <int A, int MODE>
-__global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const CoverageFloatArgs a) {
-  const int64_t e = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
-  if (e >= a.n_envs) return;
-  const int64_t ld = a.ld;
-  double px[A], py[A];
-  double pen = 0.0;
+__device__ __forceinline__ void coverage_float_env_step(double (&px)[A], double (&py)[A], const void* act, int64_t ld,
+                                                        const CoverageFloatArgs& a, double (&cost)[A], double& rew) {
 #pragma unroll
   for (int i = 0; i < A; ++i) {
-    px[i] = a.pos_x[i * ld + e];
-    py[i] = a.pos_y[i * ld + e];
-  }
-#pragma unroll
-  for (int i = 0; i < A; ++i) {
-    double cost;
     if (MODE == 0) {                                   // CoverageContinuous.transition, coverage.py:54-74
-      const float* act = static_cast<const float*>(a.actions);
-      double dx = (double)act[(2 * i) * ld + e], dy = (double)act[(2 * i + 1) * ld + e];
-      cost = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));          // :94 np.linalg.norm(action)
+      const float* af = static_cast<const float*>(act);
+      double dx = (double)af[(2 * i) * ld], dy = (double)af[(2 * i + 1) * ld];
+      cost[i] = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));       // :94 np.linalg.norm(action)
       if (a.has_coarseness) {
         const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // :65
         if (__dsqrt_rn(norm) > a.max_norm) {                           // :67 (sic: sqrt of the norm)
@@ -62,27 +55,17 @@ __global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const
       px[i] = fmax(0.0, fmin(a.size, __dadd_rn(px[i], dx)));            // :70
       py[i] = fmax(0.0, fmin(a.size, __dadd_rn(py[i], dy)));
     } else {                                           // CoverageDiscretized.transition, coverage.py:219-234
-      const uint32_t m = static_cast<const uint8_t*>(a.actions)[i * ld + e];
+      const uint32_t m = static_cast<const uint8_t*>(act)[i * ld];
       // directions (:221): x +1,-1,0,0,+1,+1,-1,-1,0 ; y 0,0,-1,+1,+1,-1,+1,-1,0
       const int dxi = (m == 0 || m == 4 || m == 5) ? 1 : ((m == 1 || m == 6 || m == 7) ? -1 : 0);
       const int dyi = (m == 3 || m == 4 || m == 6) ? 1 : ((m == 2 || m == 5 || m == 7) ? -1 : 0);
       px[i] = __ddiv_rn(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(px[i], a.zoom), (double)dxi))), a.zoom);   // :230
       py[i] = __ddiv_rn(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(py[i], a.zoom), (double)dyi))), a.zoom);
-      cost = m < 4 ? a.cost_axis : (m < 8 ? a.cost_diag : 0.0);        // :237
+      cost[i] = m < 4 ? a.cost_axis : (m < 8 ? a.cost_diag : 0.0);     // :237
     }
-    a.pos_x[i * ld + e] = px[i];
-    a.pos_y[i * ld + e] = py[i];
-    a.cost[i * ld + e] = (float)cost;
-    if (a.done) a.done[i * ld + e] = 0;                                 // :97-98
-    if (a.obs) {
-      a.obs[(2 * i) * ld + e] = (float)px[i];
-      a.obs[(2 * i + 1) * ld + e] = (float)py[i];
-    }
-    if (a.penalty) pen += __ldg(a.lambdas + i) * cost;                  // meta_agent.py:21-22
   }
-  if (a.penalty) a.penalty[e] = (float)pen;
   // reward, coverage.py:76-89: i-major sequential f64 sum over overlapping pairs
-  double rew = 0.0;
+  rew = 0.0;
 #pragma unroll
   for (int i = 0; i < A; ++i) {
 #pragma unroll
@@ -92,11 +75,40 @@ __global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const
       if (gap > 0.0) rew = __dadd_rn(rew, -__dmul_rn(gap, gap));
     }
   }
+}
+#endif
+
+#if SMARL_TU_IS(0) || SMARL_TU_IS(1)
+template <int A, int MODE>
+__global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const CoverageFloatArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
+  if (e >= a.n_envs) return;
+  const int64_t ld = a.ld;
+  double px[A], py[A], cost[A];
+  double pen = 0.0, rew;
 #pragma unroll
   for (int i = 0; i < A; ++i) {
+    px[i] = a.pos_x[i * ld + e];
+    py[i] = a.pos_y[i * ld + e];
+  }
+  const void* act = MODE == 0 ? static_cast<const void*>(static_cast<const float*>(a.actions) + e)
+                              : static_cast<const void*>(static_cast<const uint8_t*>(a.actions) + e);
+  coverage_float_env_step<A, MODE>(px, py, act, ld, a, cost, rew);
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    a.pos_x[i * ld + e] = px[i];
+    a.pos_y[i * ld + e] = py[i];
+    a.cost[i * ld + e] = (float)cost[i];
+    if (a.done) a.done[i * ld + e] = 0;                                 // :97-98
+    if (a.obs) {
+      a.obs[(2 * i) * ld + e] = (float)px[i];
+      a.obs[(2 * i + 1) * ld + e] = (float)py[i];
+    }
+    if (a.penalty) pen += __ldg(a.lambdas + i) * cost[i];               // meta_agent.py:21-22
     const double w = a.weights ? (double)__ldg(a.weights + i) : 1.0;
     a.reward[i * ld + e] = (float)__dmul_rn(rew, w);
   }
+  if (a.penalty) a.penalty[e] = (float)pen;
 }
 
 #define SMARL_DEFINE_COVF_STEP(M)                                                                        \
@@ -113,6 +125,130 @@ SMARL_DEFINE_COVF_STEP(0)
 #endif
 #if SMARL_TU_IS(1)
 SMARL_DEFINE_COVF_STEP(1)
+#endif
+
+struct CoverageFloatRolloutArgs {
+  CoverageFloatArgs env;      // env.pos_x/pos_y = start positions (read only), env.actions = [T][rows][ld]
+  double* final_x;
+  double* final_y;
+  float* R;
+  float* modR;
+  float* C;                   // [A][ld] f32 cost sums
+  float* G;
+  float* g_scratch;           // [2][T][ld]
+  double* partials;
+  const double* thresholds;
+  double gamma;
+  int32_t n_steps;
+  int32_t g_mode;
+};
+int launch_coverage_float_rollout_m0(int A, const CoverageFloatRolloutArgs& a, unsigned grid, cudaStream_t s);
+int launch_coverage_float_rollout_m1(int A, const CoverageFloatRolloutArgs& a, unsigned grid, cudaStream_t s);
+
+#if SMARL_TU_IS(3) || SMARL_TU_IS(4)
+// Fused open-loop episode of the float-position Coverage envs: positions, per-agent cost sums and the
+// (S_rew, S_pen) discounted sums stay in registers; reward_a = w_a * rew, so one pair serves every agent.
+template <int A, int MODE>
+__global__ void __launch_bounds__(kCovFThreads) coverage_float_rollout_kernel(const CoverageFloatRolloutArgs r) {
+  __shared__ double s_red[kCovFThreads / 32];
+  const CoverageFloatArgs& a = r.env;
+  const int64_t eg = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
+  const bool live = eg < a.n_envs;
+  const int64_t e = live ? eg : 0;
+  const int64_t ld = a.ld;
+  const int T = r.n_steps;
+  constexpr int kRows = MODE == 0 ? 2 * A : A;
+  double px[A], py[A], csum[A], lam[A];
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    px[i] = a.pos_x[i * ld + e];
+    py[i] = a.pos_y[i * ld + e];
+    csum[i] = 0.0;
+    lam[i] = a.lambdas ? __ldg(a.lambdas + i) : 0.0;
+  }
+  double s_rew = 0.0, s_pen = 0.0, disc = 1.0;
+  for (int t = 0; t < T; ++t) {
+    const void* act = MODE == 0
+        ? static_cast<const void*>(static_cast<const float*>(a.actions) + (int64_t)t * kRows * ld + e)
+        : static_cast<const void*>(static_cast<const uint8_t*>(a.actions) + (int64_t)t * kRows * ld + e);
+    double cost[A], rew, pen = 0.0;
+    coverage_float_env_step<A, MODE>(px, py, act, ld, a, cost, rew);
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      csum[i] += (double)(float)cost[i];             // the step kernel publishes costs as f32
+      pen += lam[i] * cost[i];
+    }
+    const float pf = (float)pen;
+    s_rew += disc * rew;
+    s_pen += disc * (double)pf;
+    if (r.g_mode == 1 && live) {
+      r.g_scratch[(int64_t)t * ld + e] = (float)rew;
+      r.g_scratch[((int64_t)T + t) * ld + e] = pf;
+    } else if (r.g_mode == 2 && live) {
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        const double w = a.weights ? (double)__ldg(a.weights + i) : 1.0;
+        r.G[((int64_t)t * A + i) * ld + e] = (float)(disc * ((double)(float)__dmul_rn(rew, w) - (double)pf));
+      }
+    }
+    disc *= r.gamma;
+  }
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const double w = a.weights ? (double)__ldg(a.weights + i) : 1.0;
+      if (r.final_x) r.final_x[i * ld + e] = px[i];
+      if (r.final_y) r.final_y[i * ld + e] = py[i];
+      r.R[i * ld + e] = (float)(w * s_rew);
+      r.modR[i * ld + e] = (float)(w * s_rew - s_pen);
+      r.C[i * ld + e] = (float)csum[i];
+    }
+  }
+  if (r.partials) {
+    double* out = r.partials + (int64_t)blockIdx.x * stats_len(A, A);
+    const double b_rew = block_sum<kCovFThreads>(live ? s_rew : 0.0, s_red);
+    const double b_pen = block_sum<kCovFThreads>(live ? s_pen : 0.0, s_red);
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const double thr = r.thresholds ? __ldg(r.thresholds + i) : 0.0;
+      const double c = (double)(float)csum[i];
+      const double bc = block_sum<kCovFThreads>(live ? c : 0.0, s_red);
+      const double bv = block_sum<kCovFThreads>((live && r.thresholds && c > thr) ? 1.0 : 0.0, s_red);
+      if (threadIdx.x == 0) {
+        const double w = a.weights ? (double)__ldg(a.weights + i) : 1.0;
+        out[i] = bc;
+        out[A + i] = bv;
+        out[2 * A + i] = w * b_rew;
+        out[3 * A + i] = w * b_rew - b_pen;
+      }
+    }
+    if (threadIdx.x == 0) out[4 * A] = 0.0;
+  }
+  if (r.g_mode == 1 && live) {                          // agent.py:200-206
+    double g_rew = 0.0, g_pen = 0.0;
+    for (int t = T - 1; t >= 0; --t) {
+      g_rew = (double)r.g_scratch[(int64_t)t * ld + e] + r.gamma * g_rew;
+      g_pen = (double)r.g_scratch[((int64_t)T + t) * ld + e] + r.gamma * g_pen;
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        const double w = a.weights ? (double)__ldg(a.weights + i) : 1.0;
+        r.G[((int64_t)t * A + i) * ld + e] = (float)(w * g_rew - g_pen);
+      }
+    }
+  }
+}
+#define SMARL_DEFINE_COVF_ROLLOUT(M)                                                                              \
+  int launch_coverage_float_rollout_m##M(int A, const CoverageFloatRolloutArgs& a, unsigned grid, cudaStream_t s) { \
+    SMARL_DISPATCH_A(A, coverage_float_rollout_kernel<kA, M><<<grid, kCovFThreads, 0, s>>>(a));                   \
+    SMARL_CUDA(cudaGetLastError());                                                                               \
+    return SMARL_OK;                                                                                              \
+  }
+#endif
+#if SMARL_TU_IS(3)
+SMARL_DEFINE_COVF_ROLLOUT(0)
+#endif
+#if SMARL_TU_IS(4)
+SMARL_DEFINE_COVF_ROLLOUT(1)
 #endif
 
 #if SMARL_TU_IS(2)
@@ -170,5 +306,39 @@ extern "C" int smarl_coverage_float_step(const SmarlCoverageFloatParams* p, doub
   const unsigned grid = (unsigned)((n_envs + kCovFThreads - 1) / kCovFThreads);
   return p->mode == 0 ? launch_coverage_float_step_m0(p->n_agents, a, grid, (cudaStream_t)stream)
                       : launch_coverage_float_step_m1(p->n_agents, a, grid, (cudaStream_t)stream);
+}
+
+extern "C" int smarl_coverage_float_rollout(const SmarlCoverageFloatParams* p, const SmarlAccounting* acc,
+                                            const double* start_x, const double* start_y, const void* actions,
+                                            const double* lambdas, double* final_x, double* final_y, float* R,
+                                            float* modR, float* C, float* G, float* g_scratch, double* stats,
+                                            double* stats_scratch, int64_t n_envs, int64_t ld,
+                                            smarl_stream_t stream) {
+  SMARL_REQUIRE(p != nullptr && acc != nullptr, "params is NULL");
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(p->size >= 1 && (p->mode == 0 || p->mode == 1), "bad size / mode");
+  SMARL_REQUIRE(p->mode == 0 || p->zoom > 0.0, "mode 1 needs zoom > 0");
+  SMARL_REQUIRE(acc->n_steps >= 1 && acc->g_mode >= 0 && acc->g_mode <= 2, "bad n_steps / g_mode");
+  SMARL_REQUIRE(start_x && start_y && actions && R && modR && C, "null required pointer");
+  SMARL_REQUIRE(acc->g_mode == 0 || G, "g_mode != 0 needs G");
+  SMARL_REQUIRE(acc->g_mode != 1 || g_scratch, "g_mode 1 needs g_scratch [2][T][ld]");
+  SMARL_REQUIRE((stats == nullptr) == (stats_scratch == nullptr), "stats and stats_scratch go together");
+  CoverageFloatRolloutArgs r;
+  CoverageFloatArgs& a = r.env;
+  a.pos_x = const_cast<double*>(start_x); a.pos_y = const_cast<double*>(start_y); a.actions = actions;
+  a.obs = nullptr; a.reward = nullptr; a.cost = nullptr; a.done = nullptr; a.lambdas = lambdas; a.penalty = nullptr;
+  a.weights = p->weights; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size; a.fieldview = p->fieldview;
+  a.max_norm = p->max_norm; a.zoom = p->zoom; a.hi = p->hi; a.cost_axis = p->cost_axis; a.cost_diag = p->cost_diag;
+  a.has_coarseness = p->has_coarseness;
+  r.final_x = final_x; r.final_y = final_y; r.R = R; r.modR = modR; r.C = C; r.G = G; r.g_scratch = g_scratch;
+  r.partials = stats_scratch; r.thresholds = acc->thresholds; r.gamma = acc->gamma; r.n_steps = acc->n_steps;
+  r.g_mode = acc->g_mode;
+  const unsigned grid = (unsigned)((n_envs + kCovFThreads - 1) / kCovFThreads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = p->mode == 0 ? launch_coverage_float_rollout_m0(p->n_agents, r, grid, st)
+                            : launch_coverage_float_rollout_m1(p->n_agents, r, grid, st))
+    return rc;
+  if (stats) return launch_stats_finalize(stats_scratch, grid, p->n_agents, p->n_agents, n_envs, stats, st);
+  return SMARL_OK;
 }
 #endif

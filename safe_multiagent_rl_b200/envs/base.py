@@ -137,7 +137,8 @@ class BatchedEnv:
             if name not in o:
                 o[name] = self._alloc(rows, dtype, lead)
             return o[name]
-        buf("R_", A, torch.float32), buf("modR_", A, torch.float32), buf("C_", K, torch.int32)
+        buf("R_", A, torch.float32), buf("modR_", A, torch.float32)
+        buf("C_", K, torch.float32 if self.cost_dtype == torch.float32 else torch.int32)
         o["G_"] = buf("G_buf", A, torch.float32, (T,)) if g_mode != G_NONE else None
         o["gs_"] = buf("g_scratch", 1, torch.float32, (g_scratch_rows,)) if g_mode == G_REWARD_TO_GO else None
         if "stats_vec" not in o:

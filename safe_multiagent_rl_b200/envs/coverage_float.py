@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..rollout import G_NONE, device_thresholds, make_accounting
 from .base import BatchedEnv
 
 
@@ -58,6 +59,24 @@ class _CoverageFloat(BatchedEnv):
             _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas), _lib.ptr(penalty), self.n_envs,
             self.ld, _lib.stream_ptr()))
 
+
+    def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None):
+        """Open-loop fused episode (one launch).  actions in the kernel layout: float32 ``[T, 2*n_agents, ld]``
+        (Continuous) or uint8 ``[T, n_agents, ld]`` (Discretized).  ``C`` holds float cost sums."""
+        T = int(actions.shape[0])
+        A, E, dev = self.n_agents, self.n_envs, self.device
+        assert actions.dtype == self.action_dtype and tuple(actions.shape) == (T, self.action_rows, self.ld) \
+            and actions.is_contiguous()
+        o = self._rollout_outputs(T, g_mode, out, 2 * T)
+        thr = device_thresholds(thresholds, dev)
+        acc = make_accounting(gamma, T, g_mode, thr)
+        self._maybe_shuffle()
+        _lib.check(self.lib.smarl_coverage_float_rollout(
+            C.byref(self._params), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y), _lib.ptr(actions),
+            _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(o["R_"]), _lib.ptr(o["modR_"]),
+            _lib.ptr(o["C_"]), _lib.ptr(o["G_"]), _lib.ptr(o["gs_"]), _lib.ptr(o["stats_vec"]),
+            _lib.ptr(o["stats_scratch"]), E, self.ld, _lib.stream_ptr()))
+        return self._rollout_result(o)
 
     def _draw_starts(self, episode):
         zoom = getattr(self, "zoom_fac", None)

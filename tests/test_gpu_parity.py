@@ -653,3 +653,47 @@ def test_tiny_batches_all_envs(E):
     assert np.array_equal(ko["n_active"].cpu().numpy(), np.ones(E, dtype=np.int32))
     assert float(ko["R"].abs().max()) == 0.0 and bool(kenv.agent_done[:, :E].all())
     assert float(ko["G"].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind,size,A,E,T,coarse,seed", [("continuous", 5, 3, 300, 40, 6, 1), ("continuous", 10, 8, 130, 15, None, 2),
+                                                          ("discretized", 5, 3, 300, 40, 20, 0), ("discretized", 3, 32, 33, 6, 3, 3)])
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+def test_coverage_float_fused_rollout(kind, size, A, E, T, coarse, seed, g_mode):
+    s = smarl()
+    rng = np.random.default_rng(seed)
+    w = (1.0 + (np.arange(A) % 3)).tolist()
+    fv = no.coverage_fieldview(size, A)
+    lam_np, gamma, thr = np.linspace(0.1, 0.3, A), 0.99, np.full(A, 0.3 * T)
+    if kind == "continuous":
+        starts = rng.random((E, A, 2)) * size
+        actions = rng.normal(0, 0.8, size=(T, E, A, 2)).astype(np.float32)
+        env = s.BatchedCoverageContinuous(size, A, n_envs=E, weights=w, coarseness=coarse, starts=starts)
+        act_k = kernel_layout(actions.reshape(T, E, 2 * A), env.ld)
+    else:
+        zoom = coarse / size
+        starts = np.floor(rng.random((E, A, 2)) * size * zoom) / zoom
+        actions = rng.integers(0, 9, size=(T, E, A))
+        env = s.BatchedCoverageDiscretized(size, A, n_envs=E, coarseness=coarse, weights=w, starts=starts)
+        act_k = kernel_layout(actions.astype(np.uint8), env.ld)
+    pos = starts.copy()
+    def step_fn(t):
+        nonlocal pos
+        if kind == "continuous":
+            pos, r, c, _ = no.coverage_continuous_step(pos, actions[t].astype(np.float64), size, fv, w, coarse, exact_pow=False)
+        else:
+            pos, r, c, _ = no.coverage_discretized_step(pos, actions[t], size, coarse, fv, w, exact_pow=False)
+        return r.astype(np.float32).astype(np.float64), c.astype(np.float32).astype(np.float64)
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    want_G = {0: None, 1: want["G"], 2: no.discounted_terms(want["mod_reward"], gamma)}[g_mode]
+    out = env.rollout(act_k, lambdas=torch.as_tensor(lam_np, device="cuda"), gamma=gamma, thresholds=thr, g_mode=g_mode)
+    assert np.array_equal(env.state().cpu().numpy(), pos)                       # bit-exact float64 final positions
+    scale = np.abs(want["modR"]).max()
+    close(out["R"].cpu().numpy(), want["R"], scale)
+    close(out["modR"].cpu().numpy(), want["modR"], scale)
+    close(out["C"].cpu().numpy(), want["C"], np.abs(want["C"]).max())
+    if g_mode:
+        close(out["G"].cpu().numpy(), want_G, scale)
+    st = out["stats"]
+    close(st.cost_sum.cpu().numpy(), want["C"].sum(0), np.abs(want["C"].sum(0)).max())
+    close(st.return_sum.cpu().numpy(), want["R"].sum(0), scale * E)
+    assert float(st.count) == E
