@@ -6,11 +6,12 @@ with ctypes).  There is no CPU fallback: constructing an env without CUDA raises
 """
 from .envs import (BatchedCollisionAvoidance, BatchedCongestion, BatchedCoverageContinuous, BatchedCoverageDiscrete,
                    BatchedCoverageDiscretized, BatchedEnv, SingleEnvAdapter)
+from .graph import GraphedClosedLoop
 from .meta_agent import BatchedMetaAgent
 from .rollout import (G_DISCOUNTED_TERMS, G_NONE, G_PPO_STANDARDISED, G_REWARD_TO_GO, BatchedBuffer, RolloutBuffer,
                       Stats)
 from .util import make_env
 
 __all__ = ["BatchedCoverageDiscrete", "BatchedCoverageContinuous", "BatchedCoverageDiscretized", "BatchedCongestion", "BatchedCollisionAvoidance", "BatchedEnv",
-           "SingleEnvAdapter", "BatchedMetaAgent", "BatchedBuffer", "RolloutBuffer", "Stats", "make_env",
+           "SingleEnvAdapter", "BatchedMetaAgent", "GraphedClosedLoop", "BatchedBuffer", "RolloutBuffer", "Stats", "make_env",
            "G_NONE", "G_REWARD_TO_GO", "G_DISCOUNTED_TERMS", "G_PPO_STANDARDISED"]

@@ -54,3 +54,24 @@ def test_closed_loop_in_one_cuda_graph(env_name):
         g = got[k][..., :E].transpose(-1, -2)
         assert torch.equal(g, want[k]), k
     assert torch.equal(env.state(), want_pos)
+
+
+def test_graphed_closed_loop_helper_with_changing_actions():
+    """GraphedClosedLoop: record once, replay with new action contents; matches the eager loop."""
+    import safe_multiagent_rl_b200 as s
+    rng = np.random.default_rng(1)
+    E, A, T = 50, 3, 50                                   # BASELINE config 1
+    env = s.BatchedCoverageDiscrete(5, A, n_envs=E, weights=[1.0, 2.0, 3.0], starts=rng.integers(0, 5, (E, A, 2)))
+    lam = torch.full((A,), 0.2, dtype=torch.float64, device="cuda")
+    actions = torch.zeros(T, A, env.ld, dtype=torch.uint8, device="cuda")
+
+    def policy(obs, t):
+        env.action_buffer.copy_(actions[t])
+    g = s.GraphedClosedLoop(env, T, policy, lam, 0.999, thresholds=[25.0] * A)
+    for trial in range(2):
+        actions.copy_(torch.as_tensor(rng.integers(0, 5, (T, A, env.ld)).astype(np.uint8), device="cuda"))
+        out = g.replay()
+        got = {k: out[k].clone() for k in ("R", "modR", "C", "G")}
+        eager = env.rollout_closed_loop(lambda obs, t: actions[t], T, lam, 0.999, thresholds=[25.0] * A)
+        for k in got:
+            assert torch.equal(got[k], eager[k]), (trial, k)
