@@ -37,8 +37,6 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Checks the shared layout contract of smarl.h for one call.
 int check_layout(int64_t n_envs, int64_t ld);
 
-int sm_count();
-
 // Dispatch a compile-time agent count 1..32.
 #define SMARL_CASE_A(N, ...) \
   case N: {                  \
@@ -104,11 +102,6 @@ __device__ __forceinline__ float4 ld_f4(const void* p) {
                : "memory");
   return v;
 }
-__device__ __forceinline__ double2 ld_stream_d2(const void* p) {
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
   asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -121,9 +114,6 @@ __device__ __forceinline__ void st_stream_i4(void* p, int4 v) {
   asm volatile("st.global.cs.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
-}
-__device__ __forceinline__ void st_stream_d2(void* p, double2 v) {
-  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
 // Byte k (0..3) of a packed word as float, exact: PRMT builds 0x4B0000bb (= 2^23 + b), one FADD.

@@ -27,17 +27,6 @@ int check_layout(int64_t n_envs, int64_t ld) {
   return SMARL_OK;
 }
 
-int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
-      cached = n;
-  }
-  return cached ? cached : 148;
-}
-
 constexpr int kAccThreads = 128;
 constexpr int kReturnsThreads = 128;   // default CTA size of returns_kernel (>= 64: stats scratch rows are sized for 64)
 
