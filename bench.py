@@ -384,6 +384,37 @@ def run_ours(a):
                "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps,
                "api": "smarl_host_coverage_rollout (pinned host buffers, fused rollout, chunked 2-stream pipeline)",
                "check": {"mean_cost_agent0": float(st_h[0] / st_h[-1]), "episodes": float(st_h[-1])}}
+        # extra: the same call with 4-bit packed actions (half the PCIe bytes; expanded on the device)
+        try:
+            packed_h = torch.empty((T, A, ld // 2), dtype=torch.uint8, **pin)
+            packed_h.copy_(actions[:, :, 0::2] | (actions[:, :, 1::2] << 4))
+            R_ref = R_h.clone()
+
+            def host_call4():
+                _lib.check(lib.smarl_host_coverage_rollout_packed4(sess, C.byref(hp), C.byref(hacc), sx_h.data_ptr(),
+                                                                   sy_h.data_ptr(), packed_h.data_ptr(), lam_h.data_ptr(),
+                                                                   R_h.data_ptr(), M_h.data_ptr(), C_h.data_ptr(),
+                                                                   st_h.data_ptr()))
+            for _ in range(2):
+                host_call4()
+            same = bool(torch.equal(R_h, R_ref))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_call4()
+            el4 = time.perf_counter() - t0
+            tt = torch.tensor([el4], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el4 = float(tt.item())
+            e2e["packed4"] = {"value": world * agent_steps * e2e_steps / el4, "unit": UNIT,
+                              "h2d_bytes_per_step": int(T * A * ld // 2 + 2 * A * ld), "ms_per_step": 1e3 * el4 / e2e_steps,
+                              "api": "smarl_host_coverage_rollout_packed4 (two 4-bit actions per byte)",
+                              "same_results_as_u8": same}
+        except Exception as ex:
+            e2e["packed4"] = {"error": str(ex)[:200]}
         lib.smarl_host_session_destroy(sess)
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------

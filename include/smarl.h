@@ -343,6 +343,15 @@ int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* 
                                 const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
                                 double* stats_h);
 
+/* Same with 4-bit packed actions (actions are 0..4): actions4_h u8 [T][A][ld/2], byte j of a row holds
+ * env 2j in its low and env 2j+1 in its high nibble.  Halves the PCIe bytes of this PCIe-bound call; the
+ * nibbles are expanded on the device. */
+int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                        const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                        const uint8_t* start_y_h, const uint8_t* actions4_h,
+                                        const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
+                                        double* stats_h);
+
 /* Congestion episodes from host buffers.  p->demand is a HOST table; moves_h u8 [T][A][ld] only for
  * noise_mode 1; C_h i32 [1][ld]. */
 int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCongestionParams* p,

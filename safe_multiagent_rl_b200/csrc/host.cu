@@ -15,6 +15,7 @@ struct SmarlHostSession {
   void* d_start_x;          // u8 (grid envs) or f64 (Collision) [A][ld]
   void* d_start_y;
   void* d_actions;          // u8 [T][A][ld] or f32 [T][2A][ld]
+  uint8_t* d_packed;        // Coverage 4-bit packed actions [T][A][ld/2], allocated on first use
   uint8_t* d_moves;         // Congestion recorded moves, allocated on first use
   double* d_landmarks;      // Collision f64 [2L][ld]
   float* d_R;
@@ -38,7 +39,7 @@ static void free_session(SmarlHostSession* s) {
   if (!s) return;
   for (auto st : s->streams)
     if (st) cudaStreamDestroy(st);
-  cudaFree(s->d_start_x); cudaFree(s->d_start_y); cudaFree(s->d_actions); cudaFree(s->d_moves);
+  cudaFree(s->d_start_x); cudaFree(s->d_start_y); cudaFree(s->d_actions); cudaFree(s->d_moves); cudaFree(s->d_packed);
   cudaFree(s->d_landmarks); cudaFree(s->d_R); cudaFree(s->d_modR); cudaFree(s->d_C); cudaFree(s->d_n_active);
   cudaFree(s->d_stats); cudaFree(s->d_scratch); cudaFree(s->d_lut); cudaFree(s->d_weights);
   cudaFree(s->d_lambdas); cudaFree(s->d_thresholds); cudaFree(s->d_demand);
@@ -108,6 +109,24 @@ extern "C" int64_t smarl_host_session_ld(const SmarlHostSession* s) { return s ?
 
 namespace {
 
+// 4-bit packed actions -> one byte per action.  Byte j of a packed row holds env 2j (low nibble) and
+// env 2j+1 (high nibble); a thread expands 8 packed bytes into 16 action bytes (one 16-byte store).
+__global__ void unpack4_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ actions, int64_t rows,
+                               int64_t ld, int64_t e0, int64_t w) {
+  const int64_t per_row = w / 16;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * per_row) return;
+  const int64_t row = i / per_row, col = (i % per_row) * 16;
+  const uint2 v = *reinterpret_cast<const uint2*>(packed + row * (ld / 2) + (e0 + col) / 2);
+  auto spread = [](uint32_t h) {          // 4 nibbles in the low 16 bits -> 4 bytes
+    uint32_t x = (h | (h << 8)) & 0x00FF00FFu;
+    return (x | (x << 4)) & 0x0F0F0F0Fu;
+  };
+  uint4 o;
+  o.x = spread(v.x & 0xFFFFu); o.y = spread(v.x >> 16); o.z = spread(v.y & 0xFFFFu); o.w = spread(v.y >> 16);
+  *reinterpret_cast<uint4*>(actions + row * ld + e0 + col) = o;
+}
+
 struct Chunk {
   int index;
   int64_t e0, n, w;   // first env, envs in the chunk, envs copied per row (n rounded up to 16)
@@ -159,11 +178,10 @@ int pipeline(SmarlHostSession* s, double* stats_h, Body body) {
 
 }  // namespace
 
-extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p,
-                                           const SmarlAccounting* acc, const uint8_t* start_x_h,
-                                           const uint8_t* start_y_h, const uint8_t* actions_h,
-                                           const double* lambdas_h, float* R_h, float* modR_h,
-                                           int32_t* C_h, double* stats_h) {
+static int host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p, const SmarlAccounting* acc,
+                                 const uint8_t* start_x_h, const uint8_t* start_y_h, const uint8_t* actions_h,
+                                 bool packed4, const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
+                                 double* stats_h) {
   SMARL_REQUIRE(s && p && acc, "null session / params");
   SMARL_REQUIRE(s->kind == SMARL_ENV_COVERAGE && p->n_agents == s->A && acc->n_steps == s->T,
                 "session was created for kind=%d A=%d T=%d", s->kind, s->A, s->T);
@@ -184,10 +202,20 @@ extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCover
   uint8_t* dx = static_cast<uint8_t*>(s->d_start_x);
   uint8_t* dy = static_cast<uint8_t*>(s->d_start_y);
   uint8_t* da = static_cast<uint8_t*>(s->d_actions);
+  if (packed4 && !s->d_packed) SMARL_CUDA(cudaMalloc(&s->d_packed, (size_t)T * A * ld / 2));
   return pipeline(s, stats_h, [&](const Chunk& c) -> int {
     if (int rc = copy_rows(dx, start_x_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
     if (int rc = copy_rows(dy, start_y_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
-    if (int rc = copy_rows(da, actions_h, 1, (int64_t)T * A, ld, c, cudaMemcpyHostToDevice)) return rc;
+    if (packed4) {                      // half the PCIe bytes: copy nibbles, expand on the device
+      const int64_t rows = (int64_t)T * A;
+      SMARL_CUDA(cudaMemcpy2DAsync(s->d_packed + c.e0 / 2, ld / 2, actions_h + c.e0 / 2, ld / 2, c.w / 2, (size_t)rows,
+                                   cudaMemcpyHostToDevice, c.st));
+      const int64_t n = rows * (c.w / 16);
+      unpack4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(s->d_packed, da, rows, ld, c.e0, c.w);
+      SMARL_CUDA(cudaGetLastError());
+    } else if (int rc = copy_rows(da, actions_h, 1, (int64_t)T * A, ld, c, cudaMemcpyHostToDevice)) {
+      return rc;
+    }
     if (int rc = smarl_coverage_rollout(&dp, &dacc, dx + c.e0, dy + c.e0, da + c.e0, lambdas_h ? s->d_lambdas : nullptr,
                                         nullptr, nullptr, s->d_R + c.e0, s->d_modR + c.e0, s->d_C + c.e0, nullptr,
                                         nullptr, s->d_stats + (int64_t)c.index * sl,
@@ -197,6 +225,22 @@ extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCover
     if (int rc = copy_rows(modR_h, s->d_modR, 4, A, ld, c, cudaMemcpyDeviceToHost)) return rc;
     return copy_rows(C_h, s->d_C, 4, A, ld, c, cudaMemcpyDeviceToHost);
   });
+}
+
+extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                           const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                           const uint8_t* start_y_h, const uint8_t* actions_h,
+                                           const double* lambdas_h, float* R_h, float* modR_h,
+                                           int32_t* C_h, double* stats_h) {
+  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions_h, false, lambdas_h, R_h, modR_h, C_h, stats_h);
+}
+
+extern "C" int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                                   const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                                   const uint8_t* start_y_h, const uint8_t* actions4_h,
+                                                   const double* lambdas_h, float* R_h, float* modR_h,
+                                                   int32_t* C_h, double* stats_h) {
+  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions4_h, true, lambdas_h, R_h, modR_h, C_h, stats_h);
 }
 
 extern "C" int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCongestionParams* p,

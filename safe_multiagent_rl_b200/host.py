@@ -54,8 +54,9 @@ class HostRollout:
         return dict(R=R[:, :E].T, modR=M[:, :E].T, C=Cs[:, :E].T, stats=st, **extra)
 
     def coverage(self, size, starts, actions, weights=None, lambdas=None, gamma=0.99, thresholds=None,
-                 fieldview_size=None):
-        """starts [E, A, 2] ints, actions [T, E, A] ints 0..4 -> dict(R [E,A], modR [E,A], C [E,A], stats)."""
+                 fieldview_size=None, packed4=False):
+        """starts [E, A, 2] ints, actions [T, E, A] ints 0..4 -> dict(R [E,A], modR [E,A], C [E,A], stats).
+        packed4: ship the actions as two 4-bit values per byte (half the PCIe traffic)."""
         A, ld = self.A, self.ld
         _, table = penalty_table(size, A, fieldview_size)
         lut = np.ascontiguousarray(table if A > 1 else table[:0], dtype=np.float32)
@@ -67,8 +68,12 @@ class HostRollout:
         R, M, Cs, st = self._outputs()
         p = _lib.CoverageParams(size, A, len(lut), 0, _p(lut) if len(lut) else None, _p(w))
         acc = _lib.Accounting(gamma, self.T, 0, _p(thr))
-        _lib.check(self.lib.smarl_host_coverage_rollout(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act),
-                                                        _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
+        fn = self.lib.smarl_host_coverage_rollout
+        if packed4:
+            act = np.ascontiguousarray(act[..., 0::2] | (act[..., 1::2] << 4))        # [T, A, ld/2]
+            fn = self.lib.smarl_host_coverage_rollout_packed4
+        _lib.check(fn(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act), _p(lam), _p(R), _p(M), _p(Cs),
+                      _p(st)))
         return self._result(R, M, Cs, st)
 
     def congestion(self, size, starts, actions, demand_rate, noise=0.0, seed=0, env_offset=0, moves=None, lambdas=None,

@@ -37,6 +37,10 @@ def test_host_coverage_rollout_multi_chunk():
     assert np.array_equal(st[:A], want["C"].sum(0)) and st[-1] == E
     assert np.array_equal(st[A:2 * A], (want["C"] > 3.0).sum(0))
     close(st[2 * A:3 * A], want["R"].sum(0), scale * E)
+    packed = h.coverage(size, starts, actions, weights=w, lambdas=lam, gamma=gamma, thresholds=thr, packed4=True)
+    for k in ("R", "modR", "C"):
+        assert np.array_equal(packed[k], out[k]), k                     # 4-bit packed actions: identical products
+    assert np.array_equal(packed["stats"], st)
     h.close()
 
 
