@@ -697,3 +697,42 @@ def test_coverage_float_fused_rollout(kind, size, A, E, T, coarse, seed, g_mode)
     close(st.cost_sum.cpu().numpy(), want["C"].sum(0), np.abs(want["C"].sum(0)).max())
     close(st.return_sum.cpu().numpy(), want["R"].sum(0), scale * E)
     assert float(st.count) == E
+
+
+# ----------------------------------------------------------------------------- host mirrors: MetaAgent gating, Buffer
+def test_meta_agent_gating_and_buffer_mirror_follow_main_py():
+    """main.py:25-68: lambda is updated once per meta cycle from the episodes of the LAST
+    (n_agents_learning_cycles - start) agent cycles only (meta_agent.py:19,:25-39); Buffer.mean_score
+    reports means over the last n episodes with costs relative to the thresholds (buffer.py:45-48)."""
+    import argparse
+    s = smarl()
+    rng = np.random.default_rng(0)
+    size, A, E, T, gamma, lr, decay = 5, 3, 64, 12, 0.99, 0.05, 2.0
+    thr = [4.0, 5.0, 6.0]
+    env = s.BatchedCoverageDiscrete(size, A, n_envs=E, weights=[1.0, 2.0, 3.0], starts=rng.integers(0, size, (E, A, 2)))
+    n_cycles, start = 5, 3
+    meta = s.BatchedMetaAgent(env.constraint_space, gamma, lr, thr, start_learning_cycle=start, decay=decay, lambda_0=0.1,
+                              n_agents=A)
+    hist = s.BatchedBuffer(argparse.Namespace(gamma=gamma, thresholds=thr))
+    lam_ref, lr_ref = np.full(A, 0.1), lr
+    for mc in range(3):
+        recorded = []
+        for ac in range(n_cycles):
+            act = torch.as_tensor(rng.integers(0, 5, (T, E, A)).astype(np.uint8), device="cuda")
+            out = env.rollout_closed_loop(lambda obs, t: act[t], T, meta.lambdas, gamma, thresholds=thr)
+            hist.extend(out["R"], out["modR"], out["C"])
+            meta.step(out["stats"])
+            if ac >= start:
+                recorded.append(out["C"].cpu().numpy().astype(np.float64))
+            meta.increment_learning_cycle()
+        meta.update()
+        hist.append_lambdas(meta.lambdas)
+        lam_ref = no.lambda_update(lam_ref, np.concatenate(recorded).mean(0), thr, lr_ref)
+        lr_ref /= decay
+        np.testing.assert_allclose(meta.lambdas.cpu().numpy(), lam_ref, rtol=1e-13)
+        assert meta.learning_cycle == 0 and abs(meta.lr - lr_ref) < 1e-15
+    assert hist.scores.shape == (3 * n_cycles * E, A) and hist.constraints.shape == (3 * n_cycles * E, A)
+    sc, msc, viol = hist.mean_score(n=100)
+    np.testing.assert_allclose(sc, hist.scores[-100:].mean(0))
+    np.testing.assert_allclose(viol, hist.constraints[-100:].mean(0) - np.array(thr))
+    assert len(hist.lambdas) == 3 and np.allclose(hist.lambdas[-1], lam_ref)
