@@ -204,6 +204,10 @@ typedef struct {
   uint64_t seed;         /* mode 2: Philox4x32-10 key                                         */
   int64_t env_offset;    /* mode 2: global id of env 0 (counter = (id, t, agent>>1)), so the
                             stream does not depend on how envs are sharded over GPUs          */
+  const float* wait_reward; /* optional [A][(size+1)^2]: f32(-30*(con+1)/demand[x][y] + 7.5 - 4) for
+                            con = 0..A-1, i.e. the waiting-branch reward (congestion.py:86-87)
+                            evaluated in f64 on the host and rounded once; replaces a float64
+                            division per agent-step in the kernels.  NULL = compute from demand.  */
 } SmarlCongestionParams;
 
 /* One Congestion.step (congestion.py:106-111 = transition :49-75 + reward :77-90 with

@@ -29,7 +29,8 @@ class CoverageFloatParams(C.Structure):
 class CongestionParams(C.Structure):
     _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("demand", c_ptr),
                 ("noise_mode", C.c_int32), ("reserved", C.c_int32),
-                ("keep_threshold", C.c_uint64), ("seed", C.c_uint64), ("env_offset", C.c_int64)]
+                ("keep_threshold", C.c_uint64), ("seed", C.c_uint64), ("env_offset", C.c_int64),
+                ("wait_reward", c_ptr)]
 
 
 class CollisionParams(C.Structure):

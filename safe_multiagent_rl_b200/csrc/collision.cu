@@ -105,18 +105,14 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
     const double lx = lm[(2 * l) * ld], ly = lm[(2 * l + 1) * ld];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2); (lx-px) == -(px-lx) exactly
       const double ax = __dadd_rn(px[i], -lx), ay = __dadd_rn(py[i], -ly);
-      const double ax2 = __dmul_rn(ax, ax);
-      const double d = __dsqrt_rn(__dadd_rn(ax2, __dmul_rn(ay, ay)));
+      // np.linalg.norm(state - land) = sqrt(ddot) = sqrt(fma(ay, ay, ax*ax))   [probed, OpenBLAS]
+      const double nrm = __dsqrt_rn(__fma_rn(ay, ay, __dmul_rn(ax, ax)));
+      reach |= (nrm < agents_size) ? (1u << i) : 0u;
+      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2)
+      const double bx = __dadd_rn(lx, -px[i]), by = __dadd_rn(ly, -py[i]);
+      const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)));
       mind[i] = fmin(mind[i], d);
-      // landmark reach uses np.linalg.norm(state - land) = sqrt(ddot) = sqrt(fma(ay, ay, ax*ax))
-      // [probed, OpenBLAS]: it differs from d by at most an ulp or two, so the fused form is only
-      // evaluated when d is within 1e-9 (relative) of the radius.
-      bool hit = d < agents_size;
-      if (fabs(d - agents_size) <= 1e-9 * agents_size)
-        hit = __dsqrt_rn(__fma_rn(ay, ay, ax2)) < agents_size;
-      reach |= hit ? (1u << i) : 0u;
     }
   }
   done_mask |= reach & ~done_mask;   // only agents that moved this step are tested; done ones stay done
@@ -191,6 +187,7 @@ __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const Coll
     ady[i] = a.actions[(2 * i + 1) * ld + e];
     done_mask |= a.done[i * ld + e] ? (1u << i) : 0u;
   }
+  const int32_t steps_before = a.episode_len ? a.episode_len[e] : 0;
   const uint32_t all = A == 32 ? 0xFFFFFFFFu : ((1u << A) - 1u);
   const bool active = done_mask != all;                       // main.py:51: episode already over
   double reward = 0.0;
@@ -208,17 +205,28 @@ __global__ void __launch_bounds__(kCollThreads) collision_step_kernel(const Coll
     }
     if (a.done_out) a.done_out[i * ld + e] = (uint8_t)((done_mask >> i) & 1u);
     if (a.reward_rows != 1 || i == 0) a.reward[i * ld + e] = rf;
-    if (a.obs) {
-      a.obs[(2 * i) * ld + e] = obs_value(px[i], a.size, a.normalize);
-      a.obs[(2 * i + 1) * ld + e] = obs_value(py[i], a.size, a.normalize);
+  }
+  if (a.obs) {
+    if (!a.normalize) {                                       // the common case stays free of float64 divisions
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        a.obs[(2 * i) * ld + e] = (float)px[i];
+        a.obs[(2 * i + 1) * ld + e] = (float)py[i];
+      }
+      if (a.obs_landmarks)                                    // :141-142 (shuffle=True layout)
+        for (int l = 0; l < 2 * a.L; ++l) a.obs[(2 * A + l) * ld + e] = (float)a.landmarks[l * ld + e];
+    } else {                                                  // _normalize_state, :164-165
+#pragma unroll 1
+      for (int i = 0; i < A; ++i) {
+        a.obs[(2 * i) * ld + e] = obs_value(px[i], a.size, 1);
+        a.obs[(2 * i + 1) * ld + e] = obs_value(py[i], a.size, 1);
+      }
+      if (a.obs_landmarks)
+        for (int l = 0; l < 2 * a.L; ++l) a.obs[(2 * A + l) * ld + e] = obs_value(a.landmarks[l * ld + e], a.size, 1);
     }
   }
-  if (a.obs && a.obs_landmarks) {                             // :141-142 (shuffle=True layout)
-    for (int l = 0; l < 2 * a.L; ++l)
-      a.obs[(2 * A + l) * ld + e] = obs_value(a.landmarks[l * ld + e], a.size, a.normalize);
-  }
   a.cost[e] = collisions;
-  if (a.episode_len && active) a.episode_len[e] += 1;
+  if (a.episode_len && active) a.episode_len[e] = steps_before + 1;
   if (a.penalty) a.penalty[e] = (float)(__ldg(a.lambdas) * (double)collisions);   // meta_agent.py:21-22
 }
 

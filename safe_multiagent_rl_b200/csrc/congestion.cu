@@ -25,6 +25,7 @@ struct CongestionStepArgs {
   const double* lambdas;
   float* penalty;
   const double* demand;
+  const float* wait_reward;
   uint64_t keep_threshold;
   uint64_t seed;
   int64_t env_offset;
@@ -73,6 +74,7 @@ struct CongestionRolloutArgs {
   double* partials;
   const double* thresholds;
   const double* demand;
+  const float* wait_reward;
   double gamma;
   uint64_t keep_threshold;
   uint64_t seed;
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(kCongThreads) congestion_step_kernel(const Con
     float r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      r[k] = (float)congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
-                                      (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W);
+      r[k] = congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
+                               (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W, a.wait_reward);
     st_stream_f4(a.reward + i * ld + e0, make_float4(r[0], r[1], r[2], r[3]));
   }
 }
@@ -239,8 +241,8 @@ __global__ void __launch_bounds__(kCongRollThreads) congestion_rollout_kernel(co
       float r[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        r[k] = (float)congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
-                                        (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W);
+        r[k] = congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
+                                 (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W, a.wait_reward);
         s_acc[(i * 4 + k) * kCongRollThreads + tid] += disc * (double)r[k];
       }
       if (a.g_mode == 1 && live) {
@@ -397,7 +399,7 @@ extern "C" int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* po
   CongestionStepArgs a;
   a.pos_x = pos_x; a.pos_y = pos_y; a.actions = actions; a.moves = moves; a.obs = obs;
   a.reward = reward; a.cost = cost; a.done = done; a.lambdas = lambdas; a.penalty = penalty;
-  a.demand = p->demand; a.keep_threshold = p->keep_threshold; a.seed = p->seed;
+  a.demand = p->demand; a.wait_reward = p->wait_reward; a.keep_threshold = p->keep_threshold; a.seed = p->seed;
   a.env_offset = p->env_offset; a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.t = t;
   const unsigned grid = (unsigned)((a.n_groups + kCongThreads - 1) / kCongThreads);
   cudaStream_t s = (cudaStream_t)stream;
@@ -429,7 +431,8 @@ extern "C" int smarl_congestion_rollout(const SmarlCongestionParams* p, const Sm
   a.start_x = start_x; a.start_y = start_y; a.actions = actions; a.moves = moves; a.lambdas = lambdas;
   a.final_x = final_x; a.final_y = final_y; a.R = R; a.modR = modR; a.C = C; a.G = G;
   a.g_scratch = g_scratch; a.partials = stats_scratch; a.thresholds = acc->thresholds;
-  a.demand = p->demand; a.gamma = acc->gamma; a.keep_threshold = p->keep_threshold; a.seed = p->seed;
+  a.demand = p->demand; a.wait_reward = p->wait_reward; a.gamma = acc->gamma; a.keep_threshold = p->keep_threshold;
+  a.seed = p->seed;
   a.env_offset = p->env_offset; a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
   a.size = p->size; a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
   const unsigned grid = (unsigned)((a.n_groups + kCongRollThreads - 1) / kCongRollThreads);

@@ -89,13 +89,23 @@ __device__ __forceinline__ int congestion_env(const uint32_t (&xw)[A], const uin
   return at_origin;
 }
 
-// Congestion.reward (congestion.py:82-87) for one agent, f64 in the reference's operation order.
-__device__ __forceinline__ double congestion_reward(uint32_t act, uint32_t con, uint32_t nx, uint32_t ny,
-                                                    const double* __restrict__ demand, int W) {
-  if (act < 4u) return -SMARL_AVERAGE_RIDE_COST - (double)con * SMARL_CONGESTION_COST;
+// Waiting-branch reward in f64, the reference's operation order (congestion.py:86-87).
+__device__ __forceinline__ double congestion_reward_f64(uint32_t con, uint32_t nx, uint32_t ny,
+                                                        const double* __restrict__ demand, int W) {
   const double d = __ldg(demand + nx * W + ny);
   const double q = __ddiv_rn(-SMARL_HOURLY_COMPENSATION * (double)(con + 1u), d);
   return __dadd_rn(__dadd_rn(q, SMARL_AVERAGE_RIDE_COMPENSATION), -SMARL_AVERAGE_RIDE_COST);
+}
+
+// Congestion.reward (congestion.py:82-87) for one agent, rounded to f32 exactly once.  The waiting
+// branch comes from the host-built table wait[con][cell] when given (same f64 expression, same single
+// rounding), otherwise it is evaluated here in f64 in the reference's operation order.
+__device__ __forceinline__ float congestion_reward(uint32_t act, uint32_t con, uint32_t nx, uint32_t ny,
+                                                   const double* __restrict__ demand, int W,
+                                                   const float* __restrict__ wait) {
+  if (act < 4u) return -4.0f - 2.0f * (float)con;                   // exact: small integers
+  if (wait) return __ldg(wait + (con * W + nx) * W + ny);
+  return (float)congestion_reward_f64(con, nx, ny, demand, W);
 }
 
 }  // namespace smarl

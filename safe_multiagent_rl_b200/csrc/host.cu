@@ -263,6 +263,7 @@ extern "C" int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCon
   if (moves_h && !s->d_moves) SMARL_CUDA(cudaMalloc(&s->d_moves, (size_t)T * A * ld));
   SmarlCongestionParams dp = *p;
   dp.demand = s->d_demand;
+  dp.wait_reward = nullptr;             // host callers pass the demand table only; the kernel divides
   SmarlAccounting dacc = *acc;
   dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
   uint8_t* dx = static_cast<uint8_t*>(s->d_start_x);

@@ -67,6 +67,11 @@ class BatchedCongestion(BatchedEnv):
         assert demand_rate.shape == (self.size + 1, self.size + 1)
         self.demand_rate = demand_rate
         self._demand = torch.as_tensor(np.ascontiguousarray(demand_rate)).to(dev)
+        # waiting-branch reward (congestion.py:86-87) for every congestion level and cell, evaluated in f64 in the
+        # reference's operation order and rounded once to f32: saves a float64 division per agent-step on the device
+        con = np.arange(A, dtype=np.float64)[:, None, None]
+        wait = -30.0 * (con + 1) / demand_rate[None] + 7.5 - 4.0
+        self._wait_reward = torch.as_tensor(np.ascontiguousarray(wait.astype(np.float32))).to(dev)
         if starts is None:
             starts = np.zeros((E, A, 2))
             if A > 1:
@@ -90,7 +95,8 @@ class BatchedCongestion(BatchedEnv):
 
     def _params(self, mode):
         return _lib.CongestionParams(self.size, self.n_agents, _lib.ptr(self._demand), mode, 0,
-                                     keep_threshold(self.noise), self.seed & (2 ** 64 - 1), self.env_offset)
+                                     keep_threshold(self.noise), self.seed & (2 ** 64 - 1), self.env_offset,
+                                     _lib.ptr(self._wait_reward))
 
     def _draw_starts(self, episode):
         self._draw_grid_starts(episode, 1)        # agent 0 restarts at (0,0), congestion.py:215-216

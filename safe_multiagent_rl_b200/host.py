@@ -88,7 +88,7 @@ class HostRollout:
         mv = None if moves is None else _am(moves, ld, np.uint8)
         mode = 1 if moves is not None else (2 if noise > 0 else 0)
         R, M, Cs, st = self._outputs()
-        p = _lib.CongestionParams(size, A, _p(dem), mode, 0, keep_threshold(noise), seed & (2 ** 64 - 1), env_offset)
+        p = _lib.CongestionParams(size, A, _p(dem), mode, 0, keep_threshold(noise), seed & (2 ** 64 - 1), env_offset, None)
         acc = _lib.Accounting(gamma, self.T, 0, _p(thr))
         _lib.check(self.lib.smarl_host_congestion_rollout(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act),
                                                           _p(mv), _p(lam), _p(R), _p(M), _p(Cs), _p(st)))

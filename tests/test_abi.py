@@ -47,7 +47,7 @@ def test_abi_struct_sizes():
     from safe_multiagent_rl_b200 import _lib
     assert C.sizeof(_lib.CoverageParams) == 32
     assert C.sizeof(_lib.Accounting) == 24
-    assert C.sizeof(_lib.CongestionParams) == 48
+    assert C.sizeof(_lib.CongestionParams) == 56
     assert C.sizeof(_lib.CollisionParams) == 32
 
 
