@@ -74,6 +74,24 @@ __device__ __forceinline__ double numpy_sum(const double (&v)[N]) {
   return s;
 }
 
+// sqrt_rn(q) < lim, out of line: only ever reached inside the 1e-9 / 1e-6 bands around lim^2 (practically
+// never), so the call sites stay three instructions instead of an inlined f64 square root each.
+static __device__ __noinline__ bool sqrt_below(double q, double lim) { return __dsqrt_rn(q) < lim; }
+
+// Exact recount of the colliding pairs (sqrt on every pair) for the rare env with a pair inside the
+// 1e-6 band around (2 agents_size)^2; rolled loops over a local-memory copy keep it out of the hot code.
+static __device__ __noinline__ int collisions_exact(const double* x, const double* y, int A, uint32_t alive,
+                                                    double lim) {
+  int n = 0;
+  for (int i = 0; i < A; ++i)
+    for (int j = i + 1; j < A; ++j) {
+      const double dx = __dadd_rn(x[i], -x[j]), dy = __dadd_rn(y[i], -y[j]);
+      const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      n += (__dsqrt_rn(q) < lim && ((alive >> i) & (alive >> j) & 1u)) ? 1 : 0;
+    }
+  return n;
+}
+
 // One CollisionAvoidance.step for one env held in registers.  Returns the env reward (same for
 // every agent) and the collision count; updates px/py/done_mask in place.
 template <int A>
@@ -88,49 +106,75 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
     if ((done_mask >> i) & 1u) continue;
     double dx = (double)adx[i], dy = (double)ady[i];
     // :113  fp32-origin components: dx**2 == dx*dx exactly, so this is the reference's norm
-    const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-    if (norm > 1.0) {                                       // :114-117
-      dx = __ddiv_rn(dx, norm);
-      dy = __ddiv_rn(dy, norm);
+    // sqrt_rn is monotonic with sqrt_rn(1) == 1, so norm > 1 needs q > 1: the sqrt (and the two
+    // divisions) are only evaluated for actions that can actually be clipped.
+    const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (q > 1.0) {
+      const double norm = __dsqrt_rn(q);
+      if (norm > 1.0) {                                     // :114-117
+        dx = __ddiv_rn(dx, norm);
+        dy = __ddiv_rn(dy, norm);
+      }
     }
     px[i] = fmax(0.0, fmin(size, __dadd_rn(px[i], dx)));   // :118
     py[i] = fmax(0.0, fmin(size, __dadd_rn(py[i], dy)));   // :119
   }
-  // landmark reach (:122-124) and per-agent min landmark distance (:158-161)
-  double mind[A];
+  // landmark reach (:122-124) and per-agent min landmark distance (:158-161).  Both compare / minimise
+  // square roots; sqrt_rn is monotonic, so the reach test is decided on the squared norm outside a
+  // 1e-9 band around agents_size^2 and the minimum is taken over the squared distances, leaving ONE
+  // sqrt per agent (instead of two per agent and landmark).
+  double minq[A];
   uint32_t reach = 0u;
+  const double as2 = agents_size * agents_size;
+  const double as2_lo = as2 * 0.999999999, as2_hi = as2 * 1.000000001;
 #pragma unroll
-  for (int i = 0; i < A; ++i) mind[i] = 1.0e300;
+  for (int i = 0; i < A; ++i) minq[i] = 1.0e300;
   for (int l = 0; l < L; ++l) {
     const double lx = lm[(2 * l) * ld], ly = lm[(2 * l + 1) * ld];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       const double ax = __dadd_rn(px[i], -lx), ay = __dadd_rn(py[i], -ly);
+      const double axx = __dmul_rn(ax, ax);
       // np.linalg.norm(state - land) = sqrt(ddot) = sqrt(fma(ay, ay, ax*ax))   [probed, OpenBLAS]
-      const double nrm = __dsqrt_rn(__fma_rn(ay, ay, __dmul_rn(ax, ax)));
-      reach |= (nrm < agents_size) ? (1u << i) : 0u;
-      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2)
-      const double bx = __dadd_rn(lx, -px[i]), by = __dadd_rn(ly, -py[i]);
-      const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)));
-      mind[i] = fmin(mind[i], d);
+      const double qn = __fma_rn(ay, ay, axx);
+      bool hit = qn < as2_lo;
+      if (!hit && qn < as2_hi) hit = sqrt_below(qn, agents_size);
+      reach |= hit ? (1u << i) : 0u;
+      // distance_matrix(states, landmarks): sqrt((lx-px)^2 + (ly-py)^2); (lx-px)^2 == (px-lx)^2 exactly
+      minq[i] = fmin(minq[i], __dadd_rn(axx, __dmul_rn(ay, ay)));
     }
   }
+  double mind[A];
+#pragma unroll
+  for (int i = 0; i < A; ++i) mind[i] = __dsqrt_rn(minq[i]);
   done_mask |= reach & ~done_mask;   // only agents that moved this step are tested; done ones stay done
   reward = -numpy_sum<A>(mind);      // :127-130, all agents incl. done ones
   // collisions among agents not done after this step (:150-156)
   int n = 0;
+  const double lim = 2.0 * agents_size;
+  const double lim2 = lim * lim;
+  const double lim2_lo = lim2 * 0.999999, lim2_hi = lim2 * 1.000001;
+  const uint32_t alive = ~done_mask;
+  bool band = false;
 #pragma unroll
   for (int i = 0; i < A; ++i) {
 #pragma unroll
     for (int j = i + 1; j < A; ++j) {
       const double dx = __dadd_rn(px[i], -px[j]), dy = __dadd_rn(py[i], -py[j]);
       const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      bool hit = false;
-      const double lim = 2.0 * agents_size;
-      const double lim2 = lim * lim;
-      if (q < lim2 * 1.000001) hit = (q < lim2 * 0.999999) || (__dsqrt_rn(q) < lim);
-      n += (hit && !((done_mask >> i) & 1u) && !((done_mask >> j) & 1u)) ? 1 : 0;
+      const bool below_lo = q < lim2_lo, below_hi = q < lim2_hi;
+      n += (below_lo && ((alive >> i) & (alive >> j) & 1u)) ? 1 : 0;
+      band |= below_lo != below_hi;
     }
+  }
+  if (band) {
+    double cx[A], cy[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      cx[i] = px[i];
+      cy[i] = py[i];
+    }
+    n = collisions_exact(cx, cy, A, alive, lim);
   }
   collisions = n;
 }

@@ -90,12 +90,15 @@ def run(env_name, S, A, E, T):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--cfg", action="append", default=[], help="env,size,agents,envs,T (repeatable): run only these")
     a = ap.parse_args()
     cfgs = [("coverage", 5, 3, 50, 50),            # configs[0]
             ("collision", 5, 3, 65536, 50),        # configs[1]
             ("congestion", 10, 8, 1 << 20, 100),   # configs[2]
             ("coverage", 32, 16, 1 << 22, 50)]     # configs[3] per GPU
-    if not a.quick:                                  # configs[4]: sweep
+    if a.cfg:
+        cfgs = [(c.split(",")[0], *map(int, c.split(",")[1:])) for c in a.cfg]
+    elif not a.quick:                                # configs[4]: sweep
         for env_name in ("coverage", "congestion", "collision"):
             for S, A in [(5, 3), (8, 4), (16, 8), (32, 16), (64, 32)]:
                 for E in [1 << 10, 1 << 13, 1 << 16, 1 << 20, 1 << 22]:
@@ -104,10 +107,11 @@ if __name__ == "__main__":
                     if E * A * 50 > 4e9:
                         continue
                     cfgs.append((env_name, S, A, E, 50))
-    print("| env | size | agents | envs | T | closed-loop agent-steps/s (CUDA graph) | ms | fused agent-steps/s | ms |")
-    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+    print("| env | size | agents | envs | T | closed-loop agent-steps/s (CUDA graph) | ms | closed-loop algorithmic GB/s "
+          "(fraction of the 6551 GB/s HBM peak) | fused agent-steps/s | ms |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     for c in cfgs:
         r = run(*c)
         print(f"| {r['env']} | {r['S']} | {r['A']} | {r['E']} | {r['T']} | {r['closed']:.3g} | {r['ms_closed']:.3f} | "
-              f"{r['fused']:.3g} | {r['ms_fused']:.3f} |", flush=True)
+              f"{r['closed_gbs']:.0f} ({r['closed_gbs'] / PEAK:.2f}) | {r['fused']:.3g} | {r['ms_fused']:.3f} |", flush=True)
         torch.cuda.empty_cache()
