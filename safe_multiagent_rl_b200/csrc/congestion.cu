@@ -36,6 +36,11 @@ struct CongestionStepArgs {
 };
 
 constexpr int kCongThreads = 128;
+// Both Congestion kernels are issue / latency-bound, so up to 8 agents the register budget is capped
+// (64 per thread in the step kernel, 128 in the rollout kernel: no or a few bytes of spills) to run 8 CTAs
+// per SM; measured on config 2 (A=8): rollout 5.28 -> 4.39 ms, closed loop 6.53 -> 6.29 ms.  Larger
+// agent counts would spill hundreds of bytes and get slower, so they keep the compiler's choice.
+constexpr int cong_min_blocks(int A) { return A <= 8 ? 8 : 1; }
 
 // One Congestion transition for four envs (congestion.py:49-75): applies the effective moves,
 // leaves the new positions in xw/yw and the displacement codes in dcw.
@@ -98,7 +103,7 @@ int launch_congestion_rollout_m2(int A, const CongestionRolloutArgs& a, unsigned
 
 #if SMARL_TU_IS(0) || SMARL_TU_IS(1) || SMARL_TU_IS(2)
 template <int A, int MODE>
-__global__ void __launch_bounds__(kCongThreads) congestion_step_kernel(const CongestionStepArgs a) {
+__global__ void __launch_bounds__(kCongThreads, cong_min_blocks(A)) congestion_step_kernel(const CongestionStepArgs a) {
   const int64_t g = (int64_t)blockIdx.x * kCongThreads + threadIdx.x;
   if (g >= a.n_groups) return;
   const int64_t e0 = g * 4;
@@ -180,7 +185,7 @@ SMARL_DEFINE_CONG_STEP(2)
 #if SMARL_TU_IS(3) || SMARL_TU_IS(4) || SMARL_TU_IS(5)
 
 template <int A, int MODE>
-__global__ void __launch_bounds__(kCongRollThreads) congestion_rollout_kernel(const CongestionRolloutArgs a) {
+__global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congestion_rollout_kernel(const CongestionRolloutArgs a) {
   extern __shared__ double s_acc[];                      // [A][4][kCongRollThreads]
   __shared__ double s_red[kCongRollThreads / 32];
   const int tid = threadIdx.x;
