@@ -200,9 +200,10 @@ typedef struct {
   /* action noise (congestion.py:64-67): move = a if u1 < 1-noise else int(u2*5)              */
   int32_t noise_mode;    /* 0 = none, 1 = recorded effective moves, 2 = on-device Philox      */
   int32_t reserved;
-  uint64_t keep_threshold; /* mode 2: keep action iff w1 < keep_threshold, = ceil((1-noise)*2^32) */
+  uint64_t keep_threshold; /* mode 2: keep action iff w < keep_threshold, = ceil((1-noise)*2^32);
+                              otherwise the move is w mod 5 (w = word a&3 of the Philox output)    */
   uint64_t seed;         /* mode 2: Philox4x32-10 key                                         */
-  int64_t env_offset;    /* mode 2: global id of env 0 (counter = (id, t, agent>>1)), so the
+  int64_t env_offset;    /* mode 2: global id of env 0 (counter = (id, t, agent>>2)), so the
                             stream does not depend on how envs are sharded over GPUs          */
   const float* wait_reward; /* optional [A][(size+1)^2]: f32(-30*(con+1)/demand[x][y] + 7.5 - 4) for
                             con = 0..A-1, i.e. the waiting-branch reward (congestion.py:86-87)

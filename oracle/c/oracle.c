@@ -148,7 +148,7 @@ static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 }
 
 /* Congestion episode(s): envs/congestion.py:49-137, accounting as above.
- *   noise_mode 0 none, 1 recorded moves u8 [T][A][ld], 2 Philox(seed, env_offset+e, t, agent>>1)
+ *   noise_mode 0 none, 1 recorded moves u8 [T][A][ld], 2 Philox(seed, env_offset+e, t, agent>>2)
  *   demand f64 [(size+1)^2]; rewards are rounded to f32 before accounting when round_f32 != 0
  *   (the product publishes f32 rewards).  R/modR f64 [A][ld], C i32 [ld], G f64 [T][A][ld] (NULL ok) */
 typedef struct {
@@ -184,12 +184,11 @@ static void congestion_range(void* vctx, int64_t lo, int64_t hi) {
         if (noise_mode == 1) {
           for (int i = 0; i < A; ++i) mv[i] = moves[((int64_t)t * A + i) * ld + e];
         } else if (noise_mode == 2) {
-          for (int j = 0; j < (A + 1) / 2; ++j) {
+          for (int j = 0; j < (A + 3) / 4; ++j) {
             uint32_t c[4] = {(uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, (uint32_t)j};
             philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-            mv[2 * j] = ((uint64_t)c[0] < keep_threshold) ? act[2 * j] : (int)(((uint64_t)c[1] * 5u) >> 32);
-            if (2 * j + 1 < A)
-              mv[2 * j + 1] = ((uint64_t)c[2] < keep_threshold) ? act[2 * j + 1] : (int)(((uint64_t)c[3] * 5u) >> 32);
+            for (int q = 0; q < 4 && 4 * j + q < A; ++q)      /* u1 = w 2^-32, int(u2 5) = w mod 5 (oracle/philox.py) */
+              mv[4 * j + q] = ((uint64_t)c[q] < keep_threshold) ? act[4 * j + q] : (int)(c[q] % 5u);
           }
         } else {
           for (int i = 0; i < A; ++i) mv[i] = act[i];

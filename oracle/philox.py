@@ -5,12 +5,14 @@ The reference draws Congestion's action noise from Python's unseeded ``random``
 path uses a counter-based generator keyed by the *global* env id, so results do not
 depend on how envs are sharded over GPUs:
 
-    out = philox4x32_10(counter=(env_lo, env_hi, t, agent >> 1), key=(seed_lo, seed_hi))
-    agent a uses words (w1, w2) = (out[2*(a&1)], out[2*(a&1)+1])
-    u1 = w1 * 2**-32,  u2 = w2 * 2**-32          (exact in f64)
+    out = philox4x32_10(counter=(env_lo, env_hi, t, agent >> 2), key=(seed_lo, seed_hi))
+    agent a uses the word w = out[a & 3]
+    u1 = w * 2**-32,  u2 = (w mod 5 + 0.5) / 5     (both exact enough in f64: int(u2 * 5) == w mod 5)
     move = action if u1 < 1 - noise else int(u2 * 5)      (congestion.py:64-67)
 
-In integers:  keep <=> w1 < ceil((1-noise) * 2**32);  int(u2*5) == (w2 * 5) >> 32.
+In integers:  keep <=> w < ceil((1-noise) * 2**32);  replacement = w mod 5.  Conditional on the move
+being replaced (w >= threshold), w mod 5 is uniform on 0..4 up to one count in 2**32 per outcome, the
+same resolution a second 32-bit word would give, so one generator call serves four agents.
 This file restates the generator so the test-suite can replay the very same
 uniforms through the reference's ``random()`` hook and through the oracle.
 """
@@ -43,26 +45,26 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def congestion_words(seed, env_ids, t, n_agents):
-    """uint32 words (w1, w2), each [E, A], for global env ids ``env_ids`` at step ``t``."""
+    """uint32 word w, [E, A], for global env ids ``env_ids`` at step ``t``."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     E = env_ids.shape[0]
-    pairs = (n_agents + 1) // 2
+    quads = (n_agents + 3) // 4
     c0 = (env_ids & MASK)[:, None]
     c1 = (env_ids >> np.uint64(32))[:, None]
     c2 = np.full((1, 1), t, dtype=np.uint64)
-    c3 = np.arange(pairs, dtype=np.uint64)[None, :]
-    o = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)   # 4 x [E, pairs]
-    w1 = np.empty((E, 2 * pairs), dtype=np.uint32)
-    w2 = np.empty((E, 2 * pairs), dtype=np.uint32)
-    w1[:, 0::2], w2[:, 0::2] = o[0], o[1]
-    w1[:, 1::2], w2[:, 1::2] = o[2], o[3]
-    return w1[:, :n_agents], w2[:, :n_agents]
+    c3 = np.arange(quads, dtype=np.uint64)[None, :]
+    o = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)   # 4 x [E, quads]
+    w = np.empty((E, 4 * quads), dtype=np.uint32)
+    for q in range(4):
+        w[:, q::4] = o[q]
+    return w[:, :n_agents]
 
 
 def congestion_uniforms(seed, env_ids, t, n_agents):
-    """The f64 uniforms (u1, u2) in [0,1) equivalent to the device's integer tests."""
-    w1, w2 = congestion_words(seed, env_ids, t, n_agents)
-    return w1.astype(np.float64) * 2.0 ** -32, w2.astype(np.float64) * 2.0 ** -32
+    """The f64 uniforms (u1, u2) in [0,1) equivalent to the device's integer tests: feeding them to the
+    reference's two ``random()`` calls (congestion.py:64,67) reproduces the device's moves."""
+    w = congestion_words(seed, env_ids, t, n_agents)
+    return w.astype(np.float64) * 2.0 ** -32, ((w % np.uint32(5)).astype(np.float64) + 0.5) / 5.0
 
 
 def keep_threshold(noise):

@@ -11,9 +11,12 @@ namespace smarl {
 #define SMARL_CONGESTION_COST 2.0
 
 // Effective (post-noise) moves of four envs for every agent, from Philox4x32-10:
-//   counter = (env_id lo, env_id hi, t, agent >> 1), key = seed; agent a reads words
-//   (2*(a&1), 2*(a&1)+1);  move = action if w1 < keep_threshold else (w2 * 5) >> 32,
-// the integer form of congestion.py:64-67 (u1 < 1 - noise ? a : int(u2 * 5)).
+//   counter = (env_id lo, env_id hi, t, agent >> 2), key = seed; agent a reads word w = out[a & 3];
+//   move = action if w < keep_threshold else w mod 5,
+// the integer form of congestion.py:64-67 (u1 < 1 - noise ? a : int(u2 * 5)) with u1 = w * 2^-32 and
+// u2 = (w mod 5 + 0.5) / 5.  Given w >= keep_threshold, w mod 5 is uniform on 0..4 up to one count in
+// 2^32 per outcome -- the same resolution as drawing a second 32-bit word -- so one generator call serves
+// four agents.
 template <int A>
 __device__ __forceinline__ void congestion_noise_moves(const uint32_t (&aw)[A], uint32_t (&mw)[A],
                                                        uint64_t seed, uint64_t keep_threshold,
@@ -25,17 +28,16 @@ __device__ __forceinline__ void congestion_noise_moves(const uint32_t (&aw)[A], 
   for (int k = 0; k < 4; ++k) {
     const uint64_t id = (uint64_t)(env0 + k);
 #pragma unroll
-    for (int j = 0; j < (A + 1) / 2; ++j) {
+    for (int j = 0; j < (A + 3) / 4; ++j) {
       const uint4 o = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), t, (uint32_t)j), key);
-      {
-        const uint32_t act = (aw[2 * j] >> (8 * k)) & 0xFFu;
-        const uint32_t mv = ((uint64_t)o.x < keep_threshold) ? act : __umulhi(o.y, 5u);
-        mw[2 * j] |= mv << (8 * k);
-      }
-      if (2 * j + 1 < A) {
-        const uint32_t act = (aw[2 * j + 1] >> (8 * k)) & 0xFFu;
-        const uint32_t mv = ((uint64_t)o.z < keep_threshold) ? act : __umulhi(o.w, 5u);
-        mw[2 * j + 1] |= mv << (8 * k);
+      const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (4 * j + q < A) {
+          const uint32_t act = (aw[4 * j + q] >> (8 * k)) & 0xFFu;
+          const uint32_t mv = ((uint64_t)w[q] < keep_threshold) ? act : w[q] % 5u;
+          mw[4 * j + q] |= mv << (8 * k);
+        }
       }
     }
   }

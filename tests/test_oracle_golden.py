@@ -109,6 +109,34 @@ def test_keep_threshold_is_exact():
         assert np.array_equal(w * 2.0 ** -32 < 1 - noise, w < thr)
 
 
+def test_single_word_noise_stream_matches_the_two_draw_model():
+    """One Philox word per agent: u1 = w 2^-32 decides keep, int(u2 * 5) = w mod 5 replaces.  The pair
+    (u1, u2) fed to congestion.py:64-67 must reproduce the integer rule, and the moves must follow the
+    reference's two-draw distribution (keep with prob 1 - noise, else uniform on 0..4)."""
+    A, E = 6, 50000
+    w = philox.congestion_words(9, np.arange(E), 3, A)
+    u1, u2 = philox.congestion_uniforms(9, np.arange(E), 3, A)
+    assert w.shape == (E, A) and np.array_equal((u2 * 5).astype(np.int64), w % 5)
+    # counter layout: agents 4q..4q+3 share call q, agent a reads output word a & 3
+    o = philox.philox4x32_10(np.arange(E), 0, 3, 1, 9, 0)
+    assert np.array_equal(w[:, 4], o[0]) and np.array_equal(w[:, 5], o[1])
+    actions = np.full((E, A), 7)
+    for noise in (0.1, 0.5):
+        thr = philox.keep_threshold(noise)
+        moves = no.congestion_noise_moves(actions, u1, u2, noise)
+        assert np.array_equal(moves, np.where(w < thr, 7, w % 5))
+        n = E * A
+        replaced = moves != 7
+        assert abs(replaced.mean() - noise) < 5 * np.sqrt(noise * (1 - noise) / n)
+        counts = np.bincount(moves[replaced], minlength=5)
+        expect = replaced.sum() / 5.0
+        assert ((counts - expect) ** 2 / expect).sum() < 25.0          # chi-square, 4 dof (p ~ 5e-5)
+        # replacement value is independent of how far above the threshold the word landed
+        hi = (w >= thr + (2 ** 32 - thr) // 2) & replaced
+        c_hi = np.bincount(moves[hi], minlength=5)
+        assert ((c_hi - hi.sum() / 5.0) ** 2 / (hi.sum() / 5.0)).sum() < 25.0
+
+
 @pytest.mark.parametrize("name", ["coverage_continuous_paper.npz", "coverage_discretized.npz"])
 def test_coverage_float_golden(name):
     g = load(name)
