@@ -308,7 +308,7 @@ int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const
 /* Same accounting for a rollout buffer that stores ONE reward row per env and step (Coverage with
  * reward_rows = 1; Collision, whose reward is identical for all agents): reward_a[t] = w_a * reward_env[t].
  *   reward_env f32 [T][ld]   weights f32 [A] (NULL = 1)   everything else as smarl_rollout_returns
- *   (g_mode 0, 1, 2).  Reads 8/A instead of 4 + 4/A reward/penalty bytes per agent-step. */
+ *   (g_mode 0..3).  Reads 8/A instead of 4 + 4/A reward/penalty bytes per agent-step. */
 int smarl_rollout_returns_shared(const SmarlAccounting* acc, const float* reward_env, const float* weights,
                                  const void* cost, int32_t cost_dtype, const float* penalty, float* R,
                                  float* modR, int32_t* C, float* G, double* stats, double* stats_scratch,

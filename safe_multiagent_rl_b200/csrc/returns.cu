@@ -278,7 +278,58 @@ __global__ void __launch_bounds__(kAccThreads) returns_shared_kernel(const Retur
   const int T = a.T, A = a.A;
   const double gamma = a.gamma;
   double g_rew[4] = {0, 0, 0, 0}, g_pen[4] = {0, 0, 0, 0};
-  if (GM != 2) {
+  if (GM == 3) {
+    // PPO standardisation (agent.py:276-281) of x_t = w G_rew[t] - G_pen[t] per agent and env.  Its mean and
+    // unbiased variance over t follow from five sums of the one Horner pair:
+    //   sum x = w S_r - S_p,   sum x^2 = w^2 S_rr - 2 w S_rp + S_pp.
+    double s_r[4] = {0, 0, 0, 0}, s_p[4] = {0, 0, 0, 0}, s_rr[4] = {0, 0, 0, 0}, s_rp[4] = {0, 0, 0, 0},
+           s_pp[4] = {0, 0, 0, 0};
+    for (int t = T - 1; t >= 0; --t) {
+      const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+      const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g_rew[k] = (double)rr[k] + gamma * g_rew[k];
+        g_pen[k] = (double)pp[k] + gamma * g_pen[k];
+        s_r[k] += g_rew[k];
+        s_p[k] += g_pen[k];
+        s_rr[k] += g_rew[k] * g_rew[k];
+        s_rp[k] += g_rew[k] * g_pen[k];
+        s_pp[k] += g_pen[k] * g_pen[k];
+      }
+    }
+    const double n = (double)T;
+    double h_rew[4] = {0, 0, 0, 0}, h_pen[4] = {0, 0, 0, 0};
+    for (int t = T - 1; t >= 0; --t) {
+      const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.penalty) p = ld_stream_f4(a.penalty + (int64_t)t * ld + e0);
+      const float rr[4] = {r.x, r.y, r.z, r.w}, pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        h_rew[k] = (double)rr[k] + gamma * h_rew[k];
+        h_pen[k] = (double)pp[k] + gamma * h_pen[k];
+      }
+      if (live) {
+        for (int i = 0; i < A; ++i) {
+          const double w = (double)s_w[i];
+          float o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double mean = (w * s_r[k] - s_p[k]) / n;
+            const double sq = w * w * s_rr[k] - 2.0 * w * s_rp[k] + s_pp[k];
+            const double var = (sq - n * mean * mean) / (n - 1.0);
+            double inv = 1.0 / (sqrt(fmax(var, 0.0)) + 1e-7);
+            if (T < 2) inv = __longlong_as_double(0x7ff8000000000000ll);   // torch: std of one sample is nan
+            o[k] = (float)(((w * h_rew[k] - h_pen[k]) - mean) * inv);
+          }
+          st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0, make_float4(o[0], o[1], o[2], o[3]));
+        }
+      }
+    }
+  } else if (GM != 2) {
 #pragma unroll 2
     for (int t = T - 1; t >= 0; --t) {
       const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
@@ -498,7 +549,7 @@ extern "C" int smarl_rollout_returns_shared(const SmarlAccounting* acc, const fl
   if (int rc = check_layout(n_envs, ld)) return rc;
   SMARL_REQUIRE(acc != nullptr, "accounting params is NULL");
   SMARL_REQUIRE(acc->n_steps >= 1, "n_steps=%d must be >= 1", acc->n_steps);
-  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 2, "shared-reward accounting supports g_mode 0..2 (got %d)", acc->g_mode);
+  SMARL_REQUIRE(acc->g_mode >= 0 && acc->g_mode <= 3, "bad g_mode %d", acc->g_mode);
   SMARL_REQUIRE(n_agents >= 1 && n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", n_agents);
   SMARL_REQUIRE(n_constraints >= 1 && n_constraints <= SMARL_MAX_AGENTS, "n_constraints=%d outside 1..32",
                 n_constraints);
@@ -517,6 +568,8 @@ extern "C" int smarl_rollout_returns_shared(const SmarlAccounting* acc, const fl
   cudaStream_t st = (cudaStream_t)stream;
   if (acc->g_mode == 2)
     returns_shared_kernel<2><<<(unsigned)n_chunks, kAccThreads, 0, st>>>(a);
+  else if (acc->g_mode == 3)
+    returns_shared_kernel<3><<<(unsigned)n_chunks, kAccThreads, 0, st>>>(a);
   else
     returns_shared_kernel<1><<<(unsigned)n_chunks, kAccThreads, 0, st>>>(a);
   const int64_t blocks = n_chunks * n_constraints;      // the K constraint rows: C_k, violation counts

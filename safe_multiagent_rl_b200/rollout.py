@@ -8,6 +8,8 @@ buffer (a zero-copy ``Buffer.append``); ``finish`` runs one accounting kernel ov
 from __future__ import annotations
 
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import torch
@@ -211,3 +213,54 @@ class BatchedBuffer:
         thr = np.asarray(self.params.thresholds, dtype=np.float64)
         return (self.scores[-n:].mean(axis=0), self.modified_scores[-n:].mean(axis=0),
                 list(self.constraints[-n:].mean(axis=0) - thr))
+
+    # -- persistence (buffer.py:50-65,141-153; the matplotlib figures are out of scope) ---------------
+    @staticmethod
+    def _batch_means(series, batch_size, first):
+        """The per-batch series the reference plots (buffer.py:155-177): entry 0 is ``first``, then the
+        means over episodes [0, b), [b, 2b), ... for every multiple of ``batch_size`` below the length."""
+        out = [np.asarray(first, dtype=np.float64)]
+        lo = 0
+        for hi in range(batch_size, len(series), batch_size):
+            out.append(series[lo:hi].mean(axis=0))
+            lo = hi
+        return np.stack(out)
+
+    def batch_scores(self):
+        """(scores, modified scores) averaged per batch of ``params.batch_size`` episodes, [batches, A]."""
+        b = int(self.params.batch_size)
+        sc, ms = self.scores, self.modified_scores
+        return self._batch_means(sc, b, sc[0]), self._batch_means(ms, b, ms[0])
+
+    def batch_constraints(self):
+        """Per-batch mean cost minus threshold, [batches, K] (buffer.py:168-177)."""
+        thr = np.asarray(self.params.thresholds, dtype=np.float64)
+        c = self.constraints
+        return self._batch_means(c - thr, int(self.params.batch_size), c[0] - thr)
+
+    def _results_dir(self):
+        if self.save_path is None:
+            p = self.params
+            stem = os.path.join("results", f"{p.environment}_s{p.size}_n{p.n_agents}_{p.numpy_seed}-{p.torch_seed}_{p.algo}_")
+            if not self.constrained:
+                stem += "unconstr_"
+            i = 0
+            while os.path.isdir(stem + str(i)):
+                i += 1
+            self.save_path = stem + str(i)
+        os.makedirs(self.save_path, exist_ok=True)
+        return self.save_path
+
+    def save_results(self):
+        """Write the files the reference's analysis scripts read (make_graphs.py:17-21):
+        ``params.json``, ``constr<numpy_seed>.npy`` [episodes, K], ``scores<numpy_seed>.npy`` [episodes, A]
+        and, when constrained, ``lambdas.npy`` [meta cycles, K]; same directory naming as buffer.py:51-64."""
+        path = self._results_dir()
+        with open(os.path.join(path, "params.json"), "w") as fh:
+            json.dump(vars(self.params), fh)
+        seed = str(self.params.numpy_seed)
+        np.save(os.path.join(path, "constr" + seed + ".npy"), self.constraints)
+        np.save(os.path.join(path, "scores" + seed + ".npy"), self.scores)
+        if self.constrained:
+            np.save(os.path.join(path, "lambdas.npy"), np.asarray(self.lambdas, dtype=np.float64))
+        return path

@@ -561,6 +561,29 @@ def test_coverage_lean_rollout_buffer(size, A, E, T, fv, seed, g_mode):
     assert r.shape == (E, 1) and d.shape == (E, A) and not d.any()
 
 
+def test_coverage_lean_rollout_buffer_ppo_standardised():
+    """g_mode 3 through the shared-reward accounting kernel: the standardised reward-to-go of every agent
+    (agent.py:276-281) from one Horner pair per env and five running sums."""
+    s = smarl()
+    size, A, E, T, fv, seed = COVERAGE_CASES[1]
+    starts, actions, weights, lut = coverage_setup(size, A, E, T, fv, seed)
+    gamma, lam_np = 0.999, np.linspace(0.1, 0.5, A)
+    env = s.BatchedCoverageDiscrete(size, A, n_envs=E, weights=weights, fieldview_size=fv, starts=starts)
+    pos = starts.copy()
+    def step_fn(t):
+        nonlocal pos
+        pos, r, c, _ = no.coverage_discrete_step(pos, actions[t], size, lut, weights)
+        return r, c
+    want = no.rollout(step_fn, T, gamma, lam_np)
+    act = torch.as_tensor(actions.astype(np.uint8), device="cuda")
+    lean = env.new_rollout_buffer(T, g_mode=s.G_PPO_STANDARDISED, lean=True)
+    out = env.rollout_closed_loop(lambda obs, t: act[t], T, torch.as_tensor(lam_np, device="cuda"), gamma,
+                                  buffer=lean, g_mode=s.G_PPO_STANDARDISED)
+    close(out["G"].cpu().numpy(), no.ppo_standardised_returns(want["mod_reward"], gamma), 1.0, rtol=2e-5)
+    close(out["modR"].cpu().numpy(), want["modR"], np.abs(want["modR"]).max())
+    close(out["R"].cpu().numpy(), want["R"], np.abs(want["R"]).max())
+
+
 # ----------------------------------------------------------------------------- drop-in protocol (lists in / lists out)
 def test_single_env_adapter_follows_the_reference_protocol():
     """SingleEnvAdapter(n_envs=1) behaves like a reference env object for the unmodified driver loop

@@ -215,3 +215,60 @@ def test_ppo_standardised_returns_match_reference():
         want = rh.run_ppo_returns(m, gamma)                          # torch float32
         got = no.ppo_standardised_returns(m[:, None, None], gamma)[:, 0, 0]
         np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------ Buffer persistence (buffer.py:50-65,141-177)
+def test_batched_buffer_save_results_matches_reference_files(tmp_path, monkeypatch):
+    """The .npy / params.json files and the per-batch series of BatchedBuffer equal the reference Buffer's
+    (its matplotlib calls are replaced by a recording no-op: figures are out of scope)."""
+    import argparse
+    import json
+    import sys
+    from unittest import mock
+
+    import torch
+
+    from safe_multiagent_rl_b200.rollout import BatchedBuffer
+
+    ref = rh.load()
+    rng = np.random.default_rng(5)
+    A, K, T, batches, bsz = 3, 2, 7, 4, 5
+    params = argparse.Namespace(gamma=0.95, thresholds=[1.5, 2.0], batch_size=bsz, n_agents_learning_cycles=1,
+                                environment="ExploreDiscrete", size=5, n_agents=A, numpy_seed=3, torch_seed=4,
+                                algo="AC")
+    monkeypatch.chdir(tmp_path)
+    rb = ref.Buffer(params, constrained=True, save_path=str(tmp_path / "ref"))
+    (tmp_path / "ref").mkdir()
+    mine = BatchedBuffer(params, constrained=True)            # default path: results/<name>_<i>
+    for b in range(batches):
+        rew = rng.normal(size=(T, bsz, A))
+        cost = rng.integers(0, 3, size=(T, bsz, K)).astype(np.float64)
+        lam = rng.random(K)
+        mod = rew - (cost @ lam)[:, :, None]
+        for e in range(bsz):
+            for t in range(T):
+                rb.append(list(rew[t, e]), list(mod[t, e]), list(cost[t, e]))
+            rb.step()
+        for t in range(T):                                     # compat path: per-step [E, A] / [E, K] tensors
+            mine.append(torch.from_numpy(rew[t]), torch.from_numpy(mod[t]), torch.from_numpy(cost[t]))
+        mine.step()
+        rb.append_lambdas(lam)
+        mine.append_lambdas(lam)
+    plt = mock.MagicMock()
+    with mock.patch.object(sys.modules[ref.Buffer.__module__], "plt", plt), mock.patch("builtins.print"):
+        rb.save_results()
+    out = mine.save_results()
+    assert out == "results/ExploreDiscrete_s5_n3_3-4_AC_0" and mine.save_results() == out
+    for name in ("constr3.npy", "scores3.npy", "lambdas.npy"):
+        np.testing.assert_allclose(np.load(tmp_path / out / name), np.load(tmp_path / "ref" / name), rtol=1e-13, atol=0)
+    assert json.load(open(tmp_path / out / "params.json")) == json.load(open(tmp_path / "ref" / "params.json"))
+    bs, bm = rb._get_batch_scores()
+    ms, mm = mine.batch_scores()
+    np.testing.assert_allclose(ms, np.array(bs), rtol=1e-13)
+    np.testing.assert_allclose(mm, np.array(bm), rtol=1e-13)
+    np.testing.assert_allclose(mine.batch_constraints(), np.array(rb._get_batch_constraints()), rtol=1e-13)
+    # unconstrained runs get their own directory stem and no lambdas file (buffer.py:56-57,152-153)
+    un = BatchedBuffer(params, constrained=False)
+    un.extend(torch.zeros(2, A), torch.zeros(2, A), torch.zeros(2, K))
+    p = un.save_results()
+    assert p.endswith("_AC_unconstr_0") and not (tmp_path / p / "lambdas.npy").exists()
