@@ -106,31 +106,40 @@ template <int A, int MODE>
 __global__ void __launch_bounds__(kCongThreads, cong_min_blocks(A)) congestion_step_kernel(const CongestionStepArgs a) {
   const int64_t g = (int64_t)blockIdx.x * kCongThreads + threadIdx.x;
   if (g >= a.n_groups) return;
-  const int64_t e0 = g * 4;
-  const int64_t ld = a.ld;
+  // 32-bit element offsets (the host checks (2A+1) * ld < 2^32): one add per row and one wide add per
+  // access instead of a 64-bit multiply-add chain (a sixth of the kernel's instructions before).
+  const uint32_t ld = (uint32_t)a.ld;
+  const uint32_t e0 = (uint32_t)g * 4u;
 
   uint32_t xw[A], yw[A], aw[A], mw[A];
+  {
+    uint32_t off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i) {
-    xw[i] = ld_stream_u32(a.pos_x + i * ld + e0);
-    yw[i] = ld_stream_u32(a.pos_y + i * ld + e0);
-    aw[i] = ld_stream_u32(a.actions + i * ld + e0);
-    if (MODE == 1) mw[i] = ld_stream_u32(a.moves + i * ld + e0);
-    if (MODE == 0) mw[i] = aw[i];
+    for (int i = 0; i < A; ++i, off += ld) {
+      xw[i] = ld_stream_u32(a.pos_x + off);
+      yw[i] = ld_stream_u32(a.pos_y + off);
+      aw[i] = ld_stream_u32(a.actions + off);
+      if (MODE == 1) mw[i] = ld_stream_u32(a.moves + off);
+      if (MODE == 0) mw[i] = aw[i];
+    }
   }
-  if (MODE == 2) congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + e0, (uint32_t)a.t);
+  if (MODE == 2)
+    congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + (int64_t)g * 4, (uint32_t)a.t);
 
   uint32_t dcw[A];
   congestion_transition<A>(xw, yw, mw, dcw, (uint32_t)a.size * 0x01010101u);
+  {
+    uint32_t off = e0, obs_off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i) {
-    st_stream_u32(a.pos_x + i * ld + e0, xw[i]);
-    st_stream_u32(a.pos_y + i * ld + e0, yw[i]);
-    if (MODE != 1 && a.moves) st_stream_u32(a.moves + i * ld + e0, mw[i]);
-    if (a.done) st_stream_u32(a.done + i * ld + e0, 0u);                 // congestion.py:103-104
-    if (a.obs) {
-      st_stream_f4(a.obs + (2 * i) * ld + e0, bytes_to_float4(xw[i]));
-      st_stream_f4(a.obs + (2 * i + 1) * ld + e0, bytes_to_float4(yw[i]));
+    for (int i = 0; i < A; ++i, off += ld, obs_off += 2u * ld) {
+      st_stream_u32(a.pos_x + off, xw[i]);
+      st_stream_u32(a.pos_y + off, yw[i]);
+      if (MODE != 1 && a.moves) st_stream_u32(a.moves + off, mw[i]);
+      if (a.done) st_stream_u32(a.done + off, 0u);                       // congestion.py:103-104
+      if (a.obs) {
+        st_stream_f4(a.obs + obs_off, bytes_to_float4(xw[i]));
+        st_stream_f4(a.obs + (obs_off + ld), bytes_to_float4(yw[i]));
+      }
     }
   }
 
@@ -154,14 +163,15 @@ __global__ void __launch_bounds__(kCongThreads, cong_min_blocks(A)) congestion_s
                                              (float)(lam * c3)));
   }
   const int W = a.size + 1;
+  uint32_t off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i) {
+  for (int i = 0; i < A; ++i, off += ld) {
     float r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       r[k] = congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
                                (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W, a.wait_reward);
-    st_stream_f4(a.reward + i * ld + e0, make_float4(r[0], r[1], r[2], r[3]));
+    st_stream_f4(a.reward + off, make_float4(r[0], r[1], r[2], r[3]));
   }
 }
 
@@ -398,6 +408,9 @@ extern "C" int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* po
   SMARL_REQUIRE(pos_x && pos_y && actions && reward && cost, "null required pointer");
   SMARL_REQUIRE(p->noise_mode != 1 || moves, "noise_mode 1 needs the recorded moves");
   SMARL_REQUIRE((lambdas == nullptr) == (penalty == nullptr), "lambdas and penalty go together");
+  SMARL_REQUIRE((2 * (int64_t)p->n_agents + 1) * ld < (1ll << 32),
+                "(2A+1)*ld = %lld exceeds 32-bit element offsets; split the env batch",
+                (long long)((2 * (int64_t)p->n_agents + 1) * ld));
   SMARL_REQUIRE(aligned16(pos_x) && aligned16(pos_y) && aligned16(actions) && aligned16(moves) &&
                     aligned16(obs) && aligned16(reward) && aligned16(cost) && aligned16(done) &&
                     aligned16(penalty), "pointers must be 16-byte aligned");
