@@ -222,11 +222,16 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
 
   for (int t = 0; t < T; ++t) {
     uint32_t aw[A], mw[A];
+    {
+      const uint8_t* act_t = a.actions + (int64_t)t * A * ld;            // uniform; per-thread offsets stay 32-bit
+      const uint8_t* mov_t = MODE == 1 ? a.moves + (int64_t)t * A * ld : nullptr;
+      uint32_t off = (uint32_t)e0;
 #pragma unroll
-    for (int i = 0; i < A; ++i) {
-      aw[i] = ld_stream_u32(a.actions + ((int64_t)t * A + i) * ld + e0);
-      if (MODE == 1) mw[i] = ld_stream_u32(a.moves + ((int64_t)t * A + i) * ld + e0);
-      if (MODE == 0) mw[i] = aw[i];
+      for (int i = 0; i < A; ++i, off += (uint32_t)ld) {
+        aw[i] = ld_stream_u32(act_t + off);
+        if (MODE == 1) mw[i] = ld_stream_u32(mov_t + off);
+        if (MODE == 0) mw[i] = aw[i];
+      }
     }
     if (MODE == 2) congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + e0, (uint32_t)t);
     uint32_t dcw[A], conw[A];
@@ -442,6 +447,8 @@ extern "C" int smarl_congestion_rollout(const SmarlCongestionParams* p, const Sm
   SMARL_REQUIRE(acc->g_mode == 0 || G, "g_mode != 0 needs G");
   SMARL_REQUIRE(acc->g_mode != 1 || g_scratch, "g_mode 1 needs g_scratch");
   SMARL_REQUIRE((stats == nullptr) == (stats_scratch == nullptr), "stats and stats_scratch go together");
+  SMARL_REQUIRE((int64_t)p->n_agents * ld < (1ll << 32), "A*ld = %lld exceeds 32-bit element offsets; split the env batch",
+                (long long)((int64_t)p->n_agents * ld));
   SMARL_REQUIRE(aligned16(start_x) && aligned16(start_y) && aligned16(actions) && aligned16(moves) &&
                     aligned16(final_x) && aligned16(final_y) && aligned16(R) && aligned16(modR) &&
                     aligned16(C) && aligned16(G) && aligned16(g_scratch), "pointers must be 16-byte aligned");
