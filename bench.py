@@ -415,6 +415,44 @@ def run_ours(a):
                               "same_results_as_u8": same}
         except Exception as ex:
             e2e["packed4"] = {"error": str(ex)[:200]}
+        # extra: the same call on the reference's env-major arrays ([T][E][A] actions, [E][A] results); the layout
+        # change runs on the device inside the pipeline
+        try:
+            del packed_h
+            act_em = torch.empty((T, E, A), dtype=torch.uint8, **pin)
+            act_em.copy_(actions[:, :, :E].permute(0, 2, 1))
+            st_em = torch.empty((E, A, 2), dtype=torch.uint8, **pin)
+            st_em.copy_(torch.stack([env.start_x[:, :E].t(), env.start_y[:, :E].t()], dim=2))
+            R_em = torch.empty((E, A), dtype=torch.float32, **pin)
+            M_em = torch.empty((E, A), dtype=torch.float32, **pin)
+            C_em = torch.empty((E, A), dtype=torch.int32, **pin)
+
+            def host_call_em():
+                _lib.check(lib.smarl_host_coverage_rollout_envmajor(sess, C.byref(hp), C.byref(hacc), st_em.data_ptr(),
+                                                                    act_em.data_ptr(), lam_h.data_ptr(), R_em.data_ptr(),
+                                                                    M_em.data_ptr(), C_em.data_ptr(), st_h.data_ptr()))
+            for _ in range(2):
+                host_call_em()
+            same = bool(torch.equal(R_em, R_ref[:, :E].t()))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_call_em()
+            el_em = time.perf_counter() - t0
+            tt = torch.tensor([el_em], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el_em = float(tt.item())
+            e2e["envmajor"] = {"value": world * agent_steps * e2e_steps / el_em, "unit": UNIT,
+                               "h2d_bytes_per_step": int(T * A * E + 2 * A * E), "d2h_bytes_per_step": int(3 * A * E * 4),
+                               "ms_per_step": 1e3 * el_em / e2e_steps,
+                               "api": "smarl_host_coverage_rollout_envmajor (reference orientation: actions [T][E][A], "
+                                      "results [E][A]; transposed on the device)",
+                               "same_results_as_agent_major": same}
+        except Exception as ex:
+            e2e["envmajor"] = {"error": str(ex)[:200]}
         lib.smarl_host_session_destroy(sess)
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------

@@ -357,6 +357,15 @@ int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const SmarlCoverage
                                         const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
                                         double* stats_h);
 
+/* Same for callers that keep the reference's env-major arrays (what np.array(actions) gives there): no
+ * padding, no ld.  starts_h u8 [E][A][2] (x, y per agent, coverage.py:45-49); actions_h u8 [T][E][A];
+ * R_h, modR_h f32 [E][A]; C_h i32 [E][A].  The layout change runs on the device inside the pipeline, so
+ * the PCIe traffic equals smarl_host_coverage_rollout's. */
+int smarl_host_coverage_rollout_envmajor(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                         const SmarlAccounting* acc, const uint8_t* starts_h,
+                                         const uint8_t* actions_h, const double* lambdas_h, float* R_h,
+                                         float* modR_h, int32_t* C_h, double* stats_h);
+
 /* Congestion episodes from host buffers.  p->demand is a HOST table; moves_h u8 [T][A][ld] only for
  * noise_mode 1; C_h i32 [1][ld]. */
 int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCongestionParams* p,

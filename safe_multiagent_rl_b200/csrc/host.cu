@@ -31,6 +31,8 @@ struct SmarlHostSession {
   double* d_thresholds;
   double* d_demand;
   double* h_stats;          // pinned [n_chunks][stats_len]
+  uint8_t* d_stage_in[2];   // env-major entry points: per-stream staging of one chunk's inputs / outputs,
+  uint8_t* d_stage_out[2];  // allocated on first use
 };
 
 using namespace smarl;
@@ -43,6 +45,7 @@ static void free_session(SmarlHostSession* s) {
   cudaFree(s->d_landmarks); cudaFree(s->d_R); cudaFree(s->d_modR); cudaFree(s->d_C); cudaFree(s->d_n_active);
   cudaFree(s->d_stats); cudaFree(s->d_scratch); cudaFree(s->d_lut); cudaFree(s->d_weights);
   cudaFree(s->d_lambdas); cudaFree(s->d_thresholds); cudaFree(s->d_demand);
+  for (int i = 0; i < 2; ++i) { cudaFree(s->d_stage_in[i]); cudaFree(s->d_stage_out[i]); }
   if (s->h_stats) cudaFreeHost(s->h_stats);
   delete s;
 }
@@ -125,6 +128,66 @@ __global__ void unpack4_kernel(const uint8_t* __restrict__ packed, uint8_t* __re
   uint4 o;
   o.x = spread(v.x & 0xFFFFu); o.y = spread(v.x >> 16); o.z = spread(v.y & 0xFFFFu); o.w = spread(v.y >> 16);
   *reinterpret_cast<uint4*>(actions + row * ld + e0 + col) = o;
+}
+
+// Layout converters for callers that keep the reference's env-major arrays ([.., env, agent], what
+// np.array(actions) gives there).  A CTA stages kTileEnvs envs x R rows in shared memory so that both the
+// env-major side (contiguous [env][R]) and the agent-major side ([R][ld], 128 consecutive envs of a row) are
+// read / written in full lines.  Rows r of an interleaved pair layout (x0,y0,x1,y1,..) go to out0 / out1.
+constexpr int kTileEnvs = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(256) envmajor_to_agentmajor(const T* __restrict__ in, T* __restrict__ out0,
+                                                              T* __restrict__ out1, int R, int64_t n, int64_t in_outer,
+                                                              int64_t out_outer, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);                    // [kTileEnvs][R + 1]
+  const int RP = R + 1;
+  const int64_t e_base = (int64_t)blockIdx.x * kTileEnvs;
+  const int m = (int)min((int64_t)kTileEnvs, n - e_base);
+  const T* src = in + (int64_t)blockIdx.y * in_outer + e_base * R;
+  for (int idx = threadIdx.x; idx < m * R; idx += 256) tile[(idx / R) * RP + idx % R] = src[idx];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < R * kTileEnvs; idx += 256) {
+    const int r = idx / kTileEnvs, e = idx % kTileEnvs;
+    if (e >= m) continue;
+    T* row = out1 ? ((r & 1) ? out1 : out0) + (int64_t)(r >> 1) * ld : out0 + (int64_t)r * ld;
+    row[(int64_t)blockIdx.y * out_outer + e_base + e] = tile[e * RP + r];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) agentmajor_to_envmajor(const T* __restrict__ in, T* __restrict__ out, int R,
+                                                              int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const int RP = R + 1;
+  const int64_t e_base = (int64_t)blockIdx.x * kTileEnvs;
+  const int m = (int)min((int64_t)kTileEnvs, n - e_base);
+  for (int idx = threadIdx.x; idx < R * kTileEnvs; idx += 256) {
+    const int r = idx / kTileEnvs, e = idx % kTileEnvs;
+    if (e < m) tile[e * RP + r] = in[(int64_t)r * ld + e_base + e];
+  }
+  __syncthreads();
+  T* dst = out + e_base * R;
+  for (int idx = threadIdx.x; idx < m * R; idx += 256) dst[idx] = tile[(idx / R) * RP + idx % R];
+}
+
+template <typename T>
+int to_agent_major(const T* in, T* out0, T* out1, int R, int64_t n, int64_t outer, int64_t in_outer, int64_t out_outer,
+                   int64_t ld, cudaStream_t st) {
+  dim3 grid((unsigned)((n + kTileEnvs - 1) / kTileEnvs), (unsigned)outer);
+  envmajor_to_agentmajor<T><<<grid, 256, sizeof(T) * kTileEnvs * (R + 1), st>>>(in, out0, out1, R, n, in_outer, out_outer, ld);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
+template <typename T>
+int to_env_major(const T* in, T* out, int R, int64_t n, int64_t ld, cudaStream_t st) {
+  agentmajor_to_envmajor<T><<<(unsigned)((n + kTileEnvs - 1) / kTileEnvs), 256, sizeof(T) * kTileEnvs * (R + 1), st>>>(
+      in, out, R, n, ld);
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
 }
 
 struct Chunk {
@@ -241,6 +304,63 @@ extern "C" int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const Sm
                                                    const double* lambdas_h, float* R_h, float* modR_h,
                                                    int32_t* C_h, double* stats_h) {
   return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions4_h, true, lambdas_h, R_h, modR_h, C_h, stats_h);
+}
+
+extern "C" int smarl_host_coverage_rollout_envmajor(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                                    const SmarlAccounting* acc, const uint8_t* starts_h,
+                                                    const uint8_t* actions_h, const double* lambdas_h, float* R_h,
+                                                    float* modR_h, int32_t* C_h, double* stats_h) {
+  SMARL_REQUIRE(s && p && acc, "null session / params");
+  SMARL_REQUIRE(s->kind == SMARL_ENV_COVERAGE && p->n_agents == s->A && acc->n_steps == s->T,
+                "session was created for kind=%d A=%d T=%d", s->kind, s->A, s->T);
+  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
+  SMARL_REQUIRE(p->lut_len >= 0 && p->lut_len <= 12287, "lut_len=%d outside 0..12287", p->lut_len);
+  SMARL_REQUIRE(starts_h && actions_h && R_h && modR_h && C_h, "null host buffer");
+  const int A = s->A, T = s->T, sl = stats_len(A, A);
+  const int64_t ld = s->ld, E = s->n_envs, chunk = s->chunk;
+  const size_t in_bytes = (size_t)(T + 2) * A * chunk, out_bytes = (size_t)3 * A * chunk * 4;
+  for (int i = 0; i < 2; ++i) {
+    if (!s->d_stage_in[i]) SMARL_CUDA(cudaMalloc(&s->d_stage_in[i], in_bytes));
+    if (!s->d_stage_out[i]) SMARL_CUDA(cudaMalloc(&s->d_stage_out[i], out_bytes));
+  }
+  cudaStream_t s0 = s->streams[0];
+  if (p->lut_len) SMARL_CUDA(cudaMemcpyAsync(s->d_lut, p->lut, sizeof(float) * p->lut_len, cudaMemcpyHostToDevice, s0));
+  if (p->weights) SMARL_CUDA(cudaMemcpyAsync(s->d_weights, p->weights, sizeof(float) * A, cudaMemcpyHostToDevice, s0));
+  if (int rc = upload_small(s, lambdas_h, acc->thresholds, A)) return rc;
+  SmarlCoverageParams dp = *p;
+  dp.lut = s->d_lut;
+  dp.weights = p->weights ? s->d_weights : nullptr;
+  SmarlAccounting dacc = *acc;
+  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+  uint8_t* dx = static_cast<uint8_t*>(s->d_start_x);
+  uint8_t* dy = static_cast<uint8_t*>(s->d_start_y);
+  uint8_t* da = static_cast<uint8_t*>(s->d_actions);
+  return pipeline(s, stats_h, [&](const Chunk& c) -> int {
+    uint8_t* st_in = s->d_stage_in[c.index & 1];
+    uint8_t* st_act = st_in + (size_t)2 * A * chunk;
+    float* st_R = reinterpret_cast<float*>(s->d_stage_out[c.index & 1]);
+    float* st_M = st_R + (size_t)A * chunk;
+    int32_t* st_C = reinterpret_cast<int32_t*>(st_M + (size_t)A * chunk);
+    // env-major host slabs of this chunk are contiguous per step: [e0, e0+n) x A
+    SMARL_CUDA(cudaMemcpyAsync(st_in, starts_h + c.e0 * 2 * A, (size_t)c.n * 2 * A, cudaMemcpyHostToDevice, c.st));
+    SMARL_CUDA(cudaMemcpy2DAsync(st_act, (size_t)chunk * A, actions_h + c.e0 * A, (size_t)E * A, (size_t)c.n * A, (size_t)T,
+                                 cudaMemcpyHostToDevice, c.st));
+    if (int rc = to_agent_major<uint8_t>(st_in, dx + c.e0, dy + c.e0, 2 * A, c.n, 1, 0, 0, ld, c.st)) return rc;
+    if (int rc = to_agent_major<uint8_t>(st_act, da + c.e0, nullptr, A, c.n, T, chunk * A, (int64_t)A * ld, ld, c.st)) return rc;
+    if (int rc = smarl_coverage_rollout(&dp, &dacc, dx + c.e0, dy + c.e0, da + c.e0, lambdas_h ? s->d_lambdas : nullptr,
+                                        nullptr, nullptr, s->d_R + c.e0, s->d_modR + c.e0, s->d_C + c.e0, nullptr,
+                                        nullptr, s->d_stats + (int64_t)c.index * sl,
+                                        s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
+      return rc;
+    if (int rc = to_env_major<float>(s->d_R + c.e0, st_R, A, c.n, ld, c.st)) return rc;
+    if (int rc = to_env_major<float>(s->d_modR + c.e0, st_M, A, c.n, ld, c.st)) return rc;
+    if (int rc = to_env_major<int32_t>(s->d_C + c.e0, st_C, A, c.n, ld, c.st)) return rc;
+    const size_t nb = (size_t)c.n * A * 4;
+    SMARL_CUDA(cudaMemcpyAsync(R_h + c.e0 * A, st_R, nb, cudaMemcpyDeviceToHost, c.st));
+    SMARL_CUDA(cudaMemcpyAsync(modR_h + c.e0 * A, st_M, nb, cudaMemcpyDeviceToHost, c.st));
+    SMARL_CUDA(cudaMemcpyAsync(C_h + c.e0 * A, st_C, nb, cudaMemcpyDeviceToHost, c.st));
+    return SMARL_OK;
+  });
 }
 
 extern "C" int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCongestionParams* p,

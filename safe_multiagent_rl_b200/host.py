@@ -56,24 +56,33 @@ class HostRollout:
     def coverage(self, size, starts, actions, weights=None, lambdas=None, gamma=0.99, thresholds=None,
                  fieldview_size=None, packed4=False):
         """starts [E, A, 2] ints, actions [T, E, A] ints 0..4 -> dict(R [E,A], modR [E,A], C [E,A], stats).
-        packed4: ship the actions as two 4-bit values per byte (half the PCIe traffic)."""
-        A, ld = self.A, self.ld
+        The arrays go to the library as they are (env-major, smarl_host_coverage_rollout_envmajor: the layout
+        change runs on the device).  packed4: ship the actions agent-major as two 4-bit values per byte
+        (half the PCIe traffic; the packing is done here on the CPU)."""
+        A, ld, E, T = self.A, self.ld, self.E, self.T
         _, table = penalty_table(size, A, fieldview_size)
         lut = np.ascontiguousarray(table if A > 1 else table[:0], dtype=np.float32)
         w = None if weights is None else np.ascontiguousarray(np.asarray(weights, np.float64)[:A], dtype=np.float32)
         lam = None if lambdas is None else np.ascontiguousarray(lambdas, dtype=np.float64)
         thr = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.float64)
+        p = _lib.CoverageParams(size, A, len(lut), 0, _p(lut) if len(lut) else None, _p(w))
+        acc = _lib.Accounting(gamma, T, 0, _p(thr))
+        st = np.zeros(self.lib.smarl_stats_len(A, self.K), np.float64)
+        if not packed4:
+            starts = np.ascontiguousarray(starts, dtype=np.uint8)
+            actions = np.ascontiguousarray(actions, dtype=np.uint8)
+            if starts.shape != (E, A, 2) or actions.shape != (T, E, A):
+                raise ValueError(f"expected starts {(E, A, 2)} and actions {(T, E, A)}, got {starts.shape}, {actions.shape}")
+            R, M, Cs = np.empty((E, A), np.float32), np.empty((E, A), np.float32), np.empty((E, A), np.int32)
+            _lib.check(self.lib.smarl_host_coverage_rollout_envmajor(self._sess, C.byref(p), C.byref(acc), _p(starts),
+                                                                     _p(actions), _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
+            return dict(R=R, modR=M, C=Cs, stats=st)
         sx, sy = _am(np.asarray(starts)[:, :, 0], ld, np.uint8), _am(np.asarray(starts)[:, :, 1], ld, np.uint8)
         act = _am(actions, ld, np.uint8)
+        act = np.ascontiguousarray(act[..., 0::2] | (act[..., 1::2] << 4))            # [T, A, ld/2]
         R, M, Cs, st = self._outputs()
-        p = _lib.CoverageParams(size, A, len(lut), 0, _p(lut) if len(lut) else None, _p(w))
-        acc = _lib.Accounting(gamma, self.T, 0, _p(thr))
-        fn = self.lib.smarl_host_coverage_rollout
-        if packed4:
-            act = np.ascontiguousarray(act[..., 0::2] | (act[..., 1::2] << 4))        # [T, A, ld/2]
-            fn = self.lib.smarl_host_coverage_rollout_packed4
-        _lib.check(fn(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act), _p(lam), _p(R), _p(M), _p(Cs),
-                      _p(st)))
+        _lib.check(self.lib.smarl_host_coverage_rollout_packed4(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy),
+                                                                _p(act), _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
         return self._result(R, M, Cs, st)
 
     def congestion(self, size, starts, actions, demand_rate, noise=0.0, seed=0, env_offset=0, moves=None, lambdas=None,

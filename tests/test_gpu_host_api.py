@@ -13,13 +13,18 @@ def close(got, want, scale, rtol=1e-5):
     np.testing.assert_allclose(np.asarray(got, np.float64), want, rtol=rtol, atol=rtol * scale)
 
 
-def test_host_coverage_rollout_multi_chunk():
+@pytest.mark.parametrize("size,A,E,T", [(7, 4, 150_001, 6),      # 3 chunks of 65536, ragged tail
+                                         (9, 16, 70_003, 3),      # the bench's agent count
+                                         (5, 3, 77, 5)])          # less than one transpose tile
+def test_host_coverage_rollout_multi_chunk(size, A, E, T):
+    """Default wrapper path = smarl_host_coverage_rollout_envmajor (env-major arrays as they are, layout change
+    on the device); packed4 = the agent-major entry point.  Both against the oracle / each other."""
     from safe_multiagent_rl_b200.host import HostRollout
-    size, A, E, T, gamma = 7, 4, 150_001, 6, 0.99            # 3 chunks of 65536
+    gamma = 0.99
     rng = np.random.default_rng(0)
     starts = rng.integers(0, size, (E, A, 2))
     actions = rng.integers(0, 5, (T, E, A))
-    w, lam, thr = [1.0, 2.0, 3.0, 1.0], np.array([0.1, 0.2, 0.3, 0.4]), [3.0] * A
+    w, lam, thr = [1.0 + (i % 3) for i in range(A)], np.linspace(0.1, 0.4, A), [3.0] * A
     lut = no.coverage_penalty_lut(size, no.coverage_fieldview(size, A))
     pos = starts.copy()
 
