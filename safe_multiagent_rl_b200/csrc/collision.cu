@@ -92,6 +92,17 @@ static __device__ __noinline__ int collisions_exact(const double* x, const doubl
   return n;
 }
 
+// Exact test of one pair (the f64 arithmetic of the pair loop below) for the f32-screened path.
+static __device__ __noinline__ int pair_collides(const double* x, const double* y, int i, int j, double lim2_lo,
+                                                 double lim2_hi, double lim) {
+  const double dx = __dadd_rn(x[i], -x[j]), dy = __dadd_rn(y[i], -y[j]);
+  const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+  if (q < lim2_lo) return 1;
+  return (q < lim2_hi && __dsqrt_rn(q) < lim) ? 1 : 0;
+}
+
+constexpr int kPairPrefilterA = 12;   // agent count from which the pair loop is screened in f32
+
 // One CollisionAvoidance.step for one env held in registers.  Returns the env reward (same for
 // every agent) and the collision count; updates px/py/done_mask in place.
 template <int A>
@@ -155,26 +166,58 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
   const double lim2 = lim * lim;
   const double lim2_lo = lim2 * 0.999999, lim2_hi = lim2 * 1.000001;
   const uint32_t alive = ~done_mask;
-  bool band = false;
-#pragma unroll
-  for (int i = 0; i < A; ++i) {
-#pragma unroll
-    for (int j = i + 1; j < A; ++j) {
-      const double dx = __dadd_rn(px[i], -px[j]), dy = __dadd_rn(py[i], -py[j]);
-      const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      const bool below_lo = q < lim2_lo, below_hi = q < lim2_hi;
-      n += (below_lo && ((alive >> i) & (alive >> j) & 1u)) ? 1 : 0;
-      band |= below_lo != below_hi;
-    }
-  }
-  if (band) {
+  if constexpr (A >= kPairPrefilterA) {
+    // Many agents: the A(A-1)/2 pair tests dominate and almost all pairs are far apart.  Screen them in f32
+    // (full-rate pipe, half the registers): coordinates <= 254 carry an absolute f32 error < 2e-5, so the f32
+    // squared distance of a pair with |d| ~ lim is off by < 1e-4 relative -- far inside the 1 % margin.  Only
+    // pairs that pass the screen are evaluated in f64, out of line, from a local-memory copy of the positions.
     double cx[A], cy[A];
+    float fx[A], fy[A];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       cx[i] = px[i];
       cy[i] = py[i];
+      fx[i] = (float)px[i];
+      fy[i] = (float)py[i];
     }
-    n = collisions_exact(cx, cy, A, alive, lim);
+    const float screen = (float)(lim2 * 1.01);
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      uint32_t near = 0u;
+#pragma unroll
+      for (int j = i + 1; j < A; ++j) {
+        const float dx = fx[i] - fx[j], dy = fy[i] - fy[j];
+        near |= (fmaf(dy, dy, dx * dx) < screen) ? (1u << j) : 0u;
+      }
+      near &= ((alive >> i) & 1u) ? alive : 0u;
+      while (near) {
+        const int j = __ffs((int)near) - 1;
+        near &= near - 1u;
+        n += pair_collides(cx, cy, i, j, lim2_lo, lim2_hi, lim);
+      }
+    }
+  } else {
+    bool band = false;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+#pragma unroll
+      for (int j = i + 1; j < A; ++j) {
+        const double dx = __dadd_rn(px[i], -px[j]), dy = __dadd_rn(py[i], -py[j]);
+        const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        const bool below_lo = q < lim2_lo, below_hi = q < lim2_hi;
+        n += (below_lo && ((alive >> i) & (alive >> j) & 1u)) ? 1 : 0;
+        band |= below_lo != below_hi;
+      }
+    }
+    if (band) {
+      double cx[A], cy[A];
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        cx[i] = px[i];
+        cy[i] = py[i];
+      }
+      n = collisions_exact(cx, cy, A, alive, lim);
+    }
   }
   collisions = n;
 }

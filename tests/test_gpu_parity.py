@@ -218,6 +218,8 @@ COLLISION_CASES = [
     (5, 8, 3, 100, 30, 2),
     (3, 12, 2, 64, 25, 3),
     (4, 32, 1, 48, 6, 4),             # maximum agents
+    (64, 16, 1, 300, 12, 5),          # large coordinates through the f32-screened pair loop (A >= 12)
+    (200, 13, 2, 200, 8, 6),
 ]
 
 
