@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput sweep over BASELINE.json configs[0..4] shapes (all three envs, grid 5-64, agents 3-32,
-envs 1K-4M) on one GPU: closed-loop (T step launches + returns kernel, captured in ONE CUDA graph so
+envs 1K-16M) on one GPU: closed-loop (T step launches + returns kernel, captured in ONE CUDA graph so
 small batches are not launch-bound) and fused open-loop rollout.  Prints a markdown table.
 
     python tools/sweep.py [--quick] > profiles/rNN/sweep.md
@@ -101,9 +101,9 @@ if __name__ == "__main__":
     elif not a.quick:                                # configs[4]: sweep
         for env_name in ("coverage", "congestion", "collision"):
             for S, A in [(5, 3), (8, 4), (16, 8), (32, 16), (64, 32)]:
-                for E in [1 << 10, 1 << 13, 1 << 16, 1 << 20, 1 << 22]:
-                    if env_name == "collision" and E * A > (1 << 25):
-                        continue
+                for E in [1 << 10, 1 << 13, 1 << 16, 1 << 20, 1 << 22, 1 << 24]:
+                    if env_name == "collision" and E * A > (1 << 26):
+                        continue                     # f64 state + f32 actions: keep the buffers under ~60 GB
                     if E * A * 50 > 4e9:
                         continue
                     cfgs.append((env_name, S, A, E, 50))
