@@ -80,7 +80,9 @@ int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaSt
 int launch_coverage_rollout(int A, const CoverageRolloutArgs& a, unsigned grid, cudaStream_t s);
 
 #if SMARL_TU_IS(0)
-template <int A>
+// KEEP: positions fit in L2 and are loaded / stored with an evict_last policy (a compile-time switch: as a
+// run-time branch inside the load loop it cost the reward_rows = 1 path 13 % of its bandwidth).
+template <int A, bool KEEP>
 __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const CoverageStepArgs a) {
   extern __shared__ float s_lut[];
   coverage_load_lut(s_lut, a.lut, a.lut_len);
@@ -91,12 +93,12 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
   const uint32_t e0 = (uint32_t)g * 4u;
 
   uint32_t xw[A], yw[A], aw[A];
-  const uint64_t keep = l2_keep_policy();
+  const uint64_t keep = KEEP ? l2_keep_policy() : 0ull;
   {
     uint32_t off = e0;
 #pragma unroll
     for (int i = 0; i < A; ++i, off += ld) {
-      if (a.keep_pos) {
+      if (KEEP) {
         xw[i] = ld_keep_u32(a.pos_x + off, keep);
         yw[i] = ld_keep_u32(a.pos_y + off, keep);
       } else {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
     for (int i = 0; i < A; ++i, off += ld, obs_off += 2u * ld) {
       grid_move4_s127(xw[i], yw[i], aw[i], ge_bias);       // coverage.py:174-189
       const uint32_t cw = move_cost4(aw[i]);               // coverage.py:191-196
-      if (a.keep_pos) {
+      if (KEEP) {
         st_keep_u32(a.pos_x + off, xw[i], keep);
         st_keep_u32(a.pos_y + off, yw[i], keep);
       } else {
@@ -167,7 +169,11 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
 
 int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaStream_t s) {
   const size_t smem = (size_t)(a.lut_len + 1) * sizeof(float);
-  SMARL_DISPATCH_A(A, coverage_step_kernel<kA><<<grid, kStepThreads, smem, s>>>(a));
+  if (a.keep_pos) {
+    SMARL_DISPATCH_A(A, coverage_step_kernel<kA, true><<<grid, kStepThreads, smem, s>>>(a));
+  } else {
+    SMARL_DISPATCH_A(A, coverage_step_kernel<kA, false><<<grid, kStepThreads, smem, s>>>(a));
+  }
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;
 }
