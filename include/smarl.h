@@ -382,6 +382,21 @@ int smarl_host_collision_rollout(SmarlHostSession* s, const SmarlCollisionParams
                                  const float* actions_h, const double* lambdas_h, float* R_h, float* modR_h,
                                  int32_t* C_h, int32_t* n_active_h, double* stats_h);
 
+/* Env-major forms of the two calls above (arrays as a user of the reference holds them, no padding):
+ * Congestion  starts_h u8 [E][A][2]; actions_h, moves_h u8 [T][E][A]; R_h, modR_h f32 [E][A]; C_h i32 [E].
+ * Collision   starts_h f64 [E][A][2]; landmarks_h f64 [E][L][2]; actions_h f32 [T][E][A][2];
+ *             R_h, modR_h f32 [E][A]; C_h, n_active_h i32 [E]. */
+int smarl_host_congestion_rollout_envmajor(SmarlHostSession* s, const SmarlCongestionParams* p,
+                                           const SmarlAccounting* acc, const uint8_t* starts_h,
+                                           const uint8_t* actions_h, const uint8_t* moves_h,
+                                           const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
+                                           double* stats_h);
+int smarl_host_collision_rollout_envmajor(SmarlHostSession* s, const SmarlCollisionParams* p,
+                                          const SmarlAccounting* acc, const double* starts_h,
+                                          const double* landmarks_h, const float* actions_h,
+                                          const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
+                                          int32_t* n_active_h, double* stats_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,10 @@ PROTOTYPES = {
                                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "smarl_host_coverage_rollout_envmajor": (C.c_int, [c_ptr, P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr,
                                                        c_ptr, c_ptr, c_ptr, c_ptr]),
+    "smarl_host_congestion_rollout_envmajor": (C.c_int, [c_ptr, P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr,
+                                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "smarl_host_collision_rollout_envmajor": (C.c_int, [c_ptr, P(CollisionParams), P(Accounting), c_ptr, c_ptr, c_ptr,
+                                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "smarl_host_congestion_rollout": (C.c_int, [c_ptr, P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr,
                                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "smarl_host_collision_rollout": (C.c_int, [c_ptr, P(CollisionParams), P(Accounting), c_ptr, c_ptr, c_ptr, c_ptr,

@@ -134,22 +134,29 @@ __global__ void unpack4_kernel(const uint8_t* __restrict__ packed, uint8_t* __re
 // np.array(actions) gives there).  A CTA stages kTileEnvs envs x R rows in shared memory so that both the
 // env-major side (contiguous [env][R]) and the agent-major side ([R][ld], 128 consecutive envs of a row) are
 // read / written in full lines.  Rows r of an interleaved pair layout (x0,y0,x1,y1,..) go to out0 / out1.
-constexpr int kTileEnvs = 128;
+constexpr int kTileEnvs = 128;   // envs per CTA tile; halved until the tile fits the default 48 KB of shared memory
+
+template <typename T>
+static int tile_envs(int R) {
+  int te = kTileEnvs;
+  while (sizeof(T) * (size_t)te * (R + 1) > 48 * 1024) te /= 2;
+  return te;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) envmajor_to_agentmajor(const T* __restrict__ in, T* __restrict__ out0,
                                                               T* __restrict__ out1, int R, int64_t n, int64_t in_outer,
-                                                              int64_t out_outer, int64_t ld) {
+                                                              int64_t out_outer, int64_t ld, int te) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);                    // [kTileEnvs][R + 1]
   const int RP = R + 1;
-  const int64_t e_base = (int64_t)blockIdx.x * kTileEnvs;
-  const int m = (int)min((int64_t)kTileEnvs, n - e_base);
+  const int64_t e_base = (int64_t)blockIdx.x * te;
+  const int m = (int)min((int64_t)te, n - e_base);
   const T* src = in + (int64_t)blockIdx.y * in_outer + e_base * R;
   for (int idx = threadIdx.x; idx < m * R; idx += 256) tile[(idx / R) * RP + idx % R] = src[idx];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < R * kTileEnvs; idx += 256) {
-    const int r = idx / kTileEnvs, e = idx % kTileEnvs;
+  for (int idx = threadIdx.x; idx < R * te; idx += 256) {
+    const int r = idx / te, e = idx % te;
     if (e >= m) continue;
     T* row = out1 ? ((r & 1) ? out1 : out0) + (int64_t)(r >> 1) * ld : out0 + (int64_t)r * ld;
     row[(int64_t)blockIdx.y * out_outer + e_base + e] = tile[e * RP + r];
@@ -158,14 +165,14 @@ __global__ void __launch_bounds__(256) envmajor_to_agentmajor(const T* __restric
 
 template <typename T>
 __global__ void __launch_bounds__(256) agentmajor_to_envmajor(const T* __restrict__ in, T* __restrict__ out, int R,
-                                                              int64_t n, int64_t ld) {
+                                                              int64_t n, int64_t ld, int te) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
   const int RP = R + 1;
-  const int64_t e_base = (int64_t)blockIdx.x * kTileEnvs;
-  const int m = (int)min((int64_t)kTileEnvs, n - e_base);
-  for (int idx = threadIdx.x; idx < R * kTileEnvs; idx += 256) {
-    const int r = idx / kTileEnvs, e = idx % kTileEnvs;
+  const int64_t e_base = (int64_t)blockIdx.x * te;
+  const int m = (int)min((int64_t)te, n - e_base);
+  for (int idx = threadIdx.x; idx < R * te; idx += 256) {
+    const int r = idx / te, e = idx % te;
     if (e < m) tile[e * RP + r] = in[(int64_t)r * ld + e_base + e];
   }
   __syncthreads();
@@ -176,16 +183,17 @@ __global__ void __launch_bounds__(256) agentmajor_to_envmajor(const T* __restric
 template <typename T>
 int to_agent_major(const T* in, T* out0, T* out1, int R, int64_t n, int64_t outer, int64_t in_outer, int64_t out_outer,
                    int64_t ld, cudaStream_t st) {
-  dim3 grid((unsigned)((n + kTileEnvs - 1) / kTileEnvs), (unsigned)outer);
-  envmajor_to_agentmajor<T><<<grid, 256, sizeof(T) * kTileEnvs * (R + 1), st>>>(in, out0, out1, R, n, in_outer, out_outer, ld);
+  const int te = tile_envs<T>(R);
+  dim3 grid((unsigned)((n + te - 1) / te), (unsigned)outer);
+  envmajor_to_agentmajor<T><<<grid, 256, sizeof(T) * te * (R + 1), st>>>(in, out0, out1, R, n, in_outer, out_outer, ld, te);
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;
 }
 
 template <typename T>
 int to_env_major(const T* in, T* out, int R, int64_t n, int64_t ld, cudaStream_t st) {
-  agentmajor_to_envmajor<T><<<(unsigned)((n + kTileEnvs - 1) / kTileEnvs), 256, sizeof(T) * kTileEnvs * (R + 1), st>>>(
-      in, out, R, n, ld);
+  const int te = tile_envs<T>(R);
+  agentmajor_to_envmajor<T><<<(unsigned)((n + te - 1) / te), 256, sizeof(T) * te * (R + 1), st>>>(in, out, R, n, ld, te);
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;
 }
@@ -306,6 +314,30 @@ extern "C" int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const Sm
   return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions4_h, true, lambdas_h, R_h, modR_h, C_h, stats_h);
 }
 
+// Per-stream staging of one chunk's env-major inputs / outputs (allocated on first use of an env-major entry).
+static int ensure_staging(SmarlHostSession* s, size_t in_bytes, size_t out_bytes) {
+  for (int i = 0; i < 2; ++i) {
+    if (!s->d_stage_in[i]) SMARL_CUDA(cudaMalloc(&s->d_stage_in[i], in_bytes));
+    if (!s->d_stage_out[i]) SMARL_CUDA(cudaMalloc(&s->d_stage_out[i], out_bytes));
+  }
+  return SMARL_OK;
+}
+
+// Episode products of one chunk back to env-major host arrays: R, modR [E][A] f32 and C [E][K] i32.
+static int download_env_major(SmarlHostSession* s, const Chunk& c, int A, int K, float* R_h, float* modR_h, int32_t* C_h) {
+  const int64_t ld = s->ld, chunk = s->chunk;
+  float* st_R = reinterpret_cast<float*>(s->d_stage_out[c.index & 1]);
+  float* st_M = st_R + (size_t)A * chunk;
+  int32_t* st_C = reinterpret_cast<int32_t*>(st_M + (size_t)A * chunk);
+  if (int rc = to_env_major<float>(s->d_R + c.e0, st_R, A, c.n, ld, c.st)) return rc;
+  if (int rc = to_env_major<float>(s->d_modR + c.e0, st_M, A, c.n, ld, c.st)) return rc;
+  if (int rc = to_env_major<int32_t>(s->d_C + c.e0, st_C, K, c.n, ld, c.st)) return rc;
+  SMARL_CUDA(cudaMemcpyAsync(R_h + c.e0 * A, st_R, (size_t)c.n * A * 4, cudaMemcpyDeviceToHost, c.st));
+  SMARL_CUDA(cudaMemcpyAsync(modR_h + c.e0 * A, st_M, (size_t)c.n * A * 4, cudaMemcpyDeviceToHost, c.st));
+  SMARL_CUDA(cudaMemcpyAsync(C_h + c.e0 * K, st_C, (size_t)c.n * K * 4, cudaMemcpyDeviceToHost, c.st));
+  return SMARL_OK;
+}
+
 extern "C" int smarl_host_coverage_rollout_envmajor(SmarlHostSession* s, const SmarlCoverageParams* p,
                                                     const SmarlAccounting* acc, const uint8_t* starts_h,
                                                     const uint8_t* actions_h, const double* lambdas_h, float* R_h,
@@ -318,11 +350,7 @@ extern "C" int smarl_host_coverage_rollout_envmajor(SmarlHostSession* s, const S
   SMARL_REQUIRE(starts_h && actions_h && R_h && modR_h && C_h, "null host buffer");
   const int A = s->A, T = s->T, sl = stats_len(A, A);
   const int64_t ld = s->ld, E = s->n_envs, chunk = s->chunk;
-  const size_t in_bytes = (size_t)(T + 2) * A * chunk, out_bytes = (size_t)3 * A * chunk * 4;
-  for (int i = 0; i < 2; ++i) {
-    if (!s->d_stage_in[i]) SMARL_CUDA(cudaMalloc(&s->d_stage_in[i], in_bytes));
-    if (!s->d_stage_out[i]) SMARL_CUDA(cudaMalloc(&s->d_stage_out[i], out_bytes));
-  }
+  if (int rc = ensure_staging(s, (size_t)(T + 2) * A * chunk, (size_t)3 * A * chunk * 4)) return rc;
   cudaStream_t s0 = s->streams[0];
   if (p->lut_len) SMARL_CUDA(cudaMemcpyAsync(s->d_lut, p->lut, sizeof(float) * p->lut_len, cudaMemcpyHostToDevice, s0));
   if (p->weights) SMARL_CUDA(cudaMemcpyAsync(s->d_weights, p->weights, sizeof(float) * A, cudaMemcpyHostToDevice, s0));
@@ -338,9 +366,6 @@ extern "C" int smarl_host_coverage_rollout_envmajor(SmarlHostSession* s, const S
   return pipeline(s, stats_h, [&](const Chunk& c) -> int {
     uint8_t* st_in = s->d_stage_in[c.index & 1];
     uint8_t* st_act = st_in + (size_t)2 * A * chunk;
-    float* st_R = reinterpret_cast<float*>(s->d_stage_out[c.index & 1]);
-    float* st_M = st_R + (size_t)A * chunk;
-    int32_t* st_C = reinterpret_cast<int32_t*>(st_M + (size_t)A * chunk);
     // env-major host slabs of this chunk are contiguous per step: [e0, e0+n) x A
     SMARL_CUDA(cudaMemcpyAsync(st_in, starts_h + c.e0 * 2 * A, (size_t)c.n * 2 * A, cudaMemcpyHostToDevice, c.st));
     SMARL_CUDA(cudaMemcpy2DAsync(st_act, (size_t)chunk * A, actions_h + c.e0 * A, (size_t)E * A, (size_t)c.n * A, (size_t)T,
@@ -352,14 +377,7 @@ extern "C" int smarl_host_coverage_rollout_envmajor(SmarlHostSession* s, const S
                                         nullptr, s->d_stats + (int64_t)c.index * sl,
                                         s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
       return rc;
-    if (int rc = to_env_major<float>(s->d_R + c.e0, st_R, A, c.n, ld, c.st)) return rc;
-    if (int rc = to_env_major<float>(s->d_modR + c.e0, st_M, A, c.n, ld, c.st)) return rc;
-    if (int rc = to_env_major<int32_t>(s->d_C + c.e0, st_C, A, c.n, ld, c.st)) return rc;
-    const size_t nb = (size_t)c.n * A * 4;
-    SMARL_CUDA(cudaMemcpyAsync(R_h + c.e0 * A, st_R, nb, cudaMemcpyDeviceToHost, c.st));
-    SMARL_CUDA(cudaMemcpyAsync(modR_h + c.e0 * A, st_M, nb, cudaMemcpyDeviceToHost, c.st));
-    SMARL_CUDA(cudaMemcpyAsync(C_h + c.e0 * A, st_C, nb, cudaMemcpyDeviceToHost, c.st));
-    return SMARL_OK;
+    return download_env_major(s, c, A, A, R_h, modR_h, C_h);
   });
 }
 
@@ -443,5 +461,103 @@ extern "C" int smarl_host_collision_rollout(SmarlHostSession* s, const SmarlColl
     if (n_active_h)
       if (int rc = copy_rows(n_active_h, s->d_n_active, 4, 1, ld, c, cudaMemcpyDeviceToHost)) return rc;
     return copy_rows(C_h, s->d_C, 4, 1, ld, c, cudaMemcpyDeviceToHost);
+  });
+}
+
+extern "C" int smarl_host_congestion_rollout_envmajor(SmarlHostSession* s, const SmarlCongestionParams* p,
+                                                      const SmarlAccounting* acc, const uint8_t* starts_h,
+                                                      const uint8_t* actions_h, const uint8_t* moves_h,
+                                                      const double* lambdas_h, float* R_h, float* modR_h,
+                                                      int32_t* C_h, double* stats_h) {
+  SMARL_REQUIRE(s && p && acc, "null session / params");
+  SMARL_REQUIRE(s->kind == SMARL_ENV_CONGESTION && p->n_agents == s->A && acc->n_steps == s->T,
+                "session was created for kind=%d A=%d T=%d", s->kind, s->A, s->T);
+  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
+  SMARL_REQUIRE(p->size >= 1 && p->size <= 254 && p->demand, "bad size or demand table");
+  SMARL_REQUIRE(starts_h && actions_h && R_h && modR_h && C_h, "null host buffer");
+  SMARL_REQUIRE(p->noise_mode != 1 || moves_h, "noise_mode 1 needs the recorded moves");
+  const int A = s->A, T = s->T, sl = stats_len(A, 1), W = p->size + 1;
+  const int64_t ld = s->ld, E = s->n_envs, chunk = s->chunk;
+  if (int rc = ensure_staging(s, (size_t)(2 * T + 2) * A * chunk, (size_t)3 * A * chunk * 4)) return rc;
+  cudaStream_t s0 = s->streams[0];
+  SMARL_CUDA(cudaMemcpyAsync(s->d_demand, p->demand, sizeof(double) * W * W, cudaMemcpyHostToDevice, s0));
+  if (int rc = upload_small(s, lambdas_h, acc->thresholds, 1)) return rc;
+  if (moves_h && !s->d_moves) SMARL_CUDA(cudaMalloc(&s->d_moves, (size_t)T * A * ld));
+  SmarlCongestionParams dp = *p;
+  dp.demand = s->d_demand;
+  dp.wait_reward = nullptr;
+  SmarlAccounting dacc = *acc;
+  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+  uint8_t* dx = static_cast<uint8_t*>(s->d_start_x);
+  uint8_t* dy = static_cast<uint8_t*>(s->d_start_y);
+  uint8_t* da = static_cast<uint8_t*>(s->d_actions);
+  return pipeline(s, stats_h, [&](const Chunk& c) -> int {
+    uint8_t* st_in = s->d_stage_in[c.index & 1];
+    uint8_t* st_act = st_in + (size_t)2 * A * chunk;
+    uint8_t* st_mov = st_act + (size_t)T * A * chunk;
+    SMARL_CUDA(cudaMemcpyAsync(st_in, starts_h + c.e0 * 2 * A, (size_t)c.n * 2 * A, cudaMemcpyHostToDevice, c.st));
+    SMARL_CUDA(cudaMemcpy2DAsync(st_act, (size_t)chunk * A, actions_h + c.e0 * A, (size_t)E * A, (size_t)c.n * A, (size_t)T,
+                                 cudaMemcpyHostToDevice, c.st));
+    if (int rc = to_agent_major<uint8_t>(st_in, dx + c.e0, dy + c.e0, 2 * A, c.n, 1, 0, 0, ld, c.st)) return rc;
+    if (int rc = to_agent_major<uint8_t>(st_act, da + c.e0, nullptr, A, c.n, T, chunk * A, (int64_t)A * ld, ld, c.st)) return rc;
+    if (moves_h) {
+      SMARL_CUDA(cudaMemcpy2DAsync(st_mov, (size_t)chunk * A, moves_h + c.e0 * A, (size_t)E * A, (size_t)c.n * A, (size_t)T,
+                                   cudaMemcpyHostToDevice, c.st));
+      if (int rc = to_agent_major<uint8_t>(st_mov, s->d_moves + c.e0, nullptr, A, c.n, T, chunk * A, (int64_t)A * ld, ld, c.st))
+        return rc;
+    }
+    SmarlCongestionParams cp = dp;
+    cp.env_offset = dp.env_offset + c.e0;                 // Philox streams are keyed by the global env id
+    if (int rc = smarl_congestion_rollout(&cp, &dacc, dx + c.e0, dy + c.e0, da + c.e0, moves_h ? s->d_moves + c.e0 : nullptr,
+                                          lambdas_h ? s->d_lambdas : nullptr, nullptr, nullptr, s->d_R + c.e0,
+                                          s->d_modR + c.e0, s->d_C + c.e0, nullptr, nullptr,
+                                          s->d_stats + (int64_t)c.index * sl,
+                                          s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
+      return rc;
+    return download_env_major(s, c, A, 1, R_h, modR_h, C_h);
+  });
+}
+
+extern "C" int smarl_host_collision_rollout_envmajor(SmarlHostSession* s, const SmarlCollisionParams* p,
+                                                     const SmarlAccounting* acc, const double* starts_h,
+                                                     const double* landmarks_h, const float* actions_h,
+                                                     const double* lambdas_h, float* R_h, float* modR_h,
+                                                     int32_t* C_h, int32_t* n_active_h, double* stats_h) {
+  SMARL_REQUIRE(s && p && acc, "null session / params");
+  SMARL_REQUIRE(s->kind == SMARL_ENV_COLLISION && p->n_agents == s->A && acc->n_steps == s->T &&
+                    p->n_landmarks == s->L, "session was created for kind=%d A=%d T=%d L=%d", s->kind, s->A, s->T, s->L);
+  SMARL_REQUIRE(acc->g_mode == 0, "host rollout returns episode products only (g_mode 0)");
+  SMARL_REQUIRE(starts_h && landmarks_h && actions_h && R_h && modR_h && C_h, "null host buffer");
+  const int A = s->A, T = s->T, L = s->L, sl = stats_len(A, 1);
+  const int64_t ld = s->ld, E = s->n_envs, chunk = s->chunk;
+  const size_t start_b = (size_t)16 * A * chunk, lm_b = (size_t)16 * L * chunk, act_b = (size_t)T * 2 * A * 4 * chunk;
+  if (int rc = ensure_staging(s, start_b + lm_b + act_b, (size_t)3 * A * chunk * 4)) return rc;
+  if (int rc = upload_small(s, lambdas_h, acc->thresholds, 1)) return rc;
+  SmarlAccounting dacc = *acc;
+  dacc.thresholds = acc->thresholds ? s->d_thresholds : nullptr;
+  double* dx = static_cast<double*>(s->d_start_x);
+  double* dy = static_cast<double*>(s->d_start_y);
+  float* da = static_cast<float*>(s->d_actions);
+  return pipeline(s, stats_h, [&](const Chunk& c) -> int {
+    double* st_start = reinterpret_cast<double*>(s->d_stage_in[c.index & 1]);
+    double* st_lm = st_start + (size_t)2 * A * chunk;
+    float* st_act = reinterpret_cast<float*>(st_lm + (size_t)2 * L * chunk);
+    SMARL_CUDA(cudaMemcpyAsync(st_start, starts_h + c.e0 * 2 * A, (size_t)c.n * 2 * A * 8, cudaMemcpyHostToDevice, c.st));
+    SMARL_CUDA(cudaMemcpyAsync(st_lm, landmarks_h + c.e0 * 2 * L, (size_t)c.n * 2 * L * 8, cudaMemcpyHostToDevice, c.st));
+    SMARL_CUDA(cudaMemcpy2DAsync(st_act, (size_t)chunk * 2 * A * 4, actions_h + c.e0 * 2 * A, (size_t)E * 2 * A * 4,
+                                 (size_t)c.n * 2 * A * 4, (size_t)T, cudaMemcpyHostToDevice, c.st));
+    if (int rc = to_agent_major<double>(st_start, dx + c.e0, dy + c.e0, 2 * A, c.n, 1, 0, 0, ld, c.st)) return rc;
+    if (int rc = to_agent_major<double>(st_lm, s->d_landmarks + c.e0, nullptr, 2 * L, c.n, 1, 0, 0, ld, c.st)) return rc;
+    if (int rc = to_agent_major<float>(st_act, da + c.e0, nullptr, 2 * A, c.n, T, chunk * 2 * A, (int64_t)2 * A * ld, ld, c.st))
+      return rc;
+    if (int rc = smarl_collision_rollout(p, &dacc, dx + c.e0, dy + c.e0, s->d_landmarks + c.e0, da + c.e0,
+                                         lambdas_h ? s->d_lambdas : nullptr, nullptr, nullptr, nullptr,
+                                         s->d_n_active + c.e0, s->d_R + c.e0, s->d_modR + c.e0, s->d_C + c.e0, nullptr,
+                                         nullptr, s->d_stats + (int64_t)c.index * sl,
+                                         s->d_scratch + (int64_t)c.index * s->scratch_per_chunk, c.n, ld, c.st))
+      return rc;
+    if (n_active_h)
+      SMARL_CUDA(cudaMemcpyAsync(n_active_h + c.e0, s->d_n_active + c.e0, (size_t)c.n * 4, cudaMemcpyDeviceToHost, c.st));
+    return download_env_major(s, c, A, 1, R_h, modR_h, C_h);
   });
 }

@@ -87,34 +87,44 @@ class HostRollout:
 
     def congestion(self, size, starts, actions, demand_rate, noise=0.0, seed=0, env_offset=0, moves=None, lambdas=None,
                    gamma=0.99, thresholds=None):
-        A, ld = self.A, self.ld
+        """starts [E, A, 2] ints, actions (and recorded moves) [T, E, A] ints -> dict(R [E,A], modR [E,A], C [E,1], stats);
+        the arrays go to smarl_host_congestion_rollout_envmajor as they are."""
+        A, E, T = self.A, self.E, self.T
         dem = np.ascontiguousarray(demand_rate, dtype=np.float64)
         assert dem.shape == (size + 1, size + 1)
         lam = None if lambdas is None else np.ascontiguousarray(lambdas, dtype=np.float64)
         thr = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.float64)
-        sx, sy = _am(np.asarray(starts)[:, :, 0], ld, np.uint8), _am(np.asarray(starts)[:, :, 1], ld, np.uint8)
-        act = _am(actions, ld, np.uint8)
-        mv = None if moves is None else _am(moves, ld, np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint8)
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        mv = None if moves is None else np.ascontiguousarray(moves, dtype=np.uint8)
+        if starts.shape != (E, A, 2) or actions.shape != (T, E, A) or (mv is not None and mv.shape != (T, E, A)):
+            raise ValueError(f"expected starts {(E, A, 2)} and actions / moves {(T, E, A)}")
         mode = 1 if moves is not None else (2 if noise > 0 else 0)
-        R, M, Cs, st = self._outputs()
+        R, M, Cs = np.empty((E, A), np.float32), np.empty((E, A), np.float32), np.empty((E, 1), np.int32)
+        st = np.zeros(self.lib.smarl_stats_len(A, 1), np.float64)
         p = _lib.CongestionParams(size, A, _p(dem), mode, 0, keep_threshold(noise), seed & (2 ** 64 - 1), env_offset, None)
-        acc = _lib.Accounting(gamma, self.T, 0, _p(thr))
-        _lib.check(self.lib.smarl_host_congestion_rollout(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act),
-                                                          _p(mv), _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
-        return self._result(R, M, Cs, st)
+        acc = _lib.Accounting(gamma, T, 0, _p(thr))
+        _lib.check(self.lib.smarl_host_congestion_rollout_envmajor(self._sess, C.byref(p), C.byref(acc), _p(starts),
+                                                                   _p(actions), _p(mv), _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
+        return dict(R=R, modR=M, C=Cs, stats=st)
 
     def collision(self, size, starts, landmarks, actions, lambdas=None, gamma=0.99, thresholds=None, agents_size=0.25):
-        """starts [E,A,2] f64, landmarks [E,L,2] f64, actions [T,E,A,2] f32."""
-        A, ld, L, T, E = self.A, self.ld, self.L, self.T, self.E
+        """starts [E,A,2] f64, landmarks [E,L,2] f64, actions [T,E,A,2] f32 -> dict(R, modR [E,A], C [E,1], n_active [E],
+        stats); the arrays go to smarl_host_collision_rollout_envmajor as they are."""
+        A, L, T, E = self.A, self.L, self.T, self.E
         lam = None if lambdas is None else np.ascontiguousarray(lambdas, dtype=np.float64)
         thr = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.float64)
-        sx, sy = _am(np.asarray(starts)[:, :, 0], ld, np.float64), _am(np.asarray(starts)[:, :, 1], ld, np.float64)
-        lm = _am(np.asarray(landmarks).reshape(E, 2 * L), ld, np.float64)
-        act = _am(np.asarray(actions).reshape(T, E, 2 * A), ld, np.float32)
-        n_active = np.zeros((1, ld), np.int32)
-        R, M, Cs, st = self._outputs()
+        starts = np.ascontiguousarray(starts, dtype=np.float64)
+        landmarks = np.ascontiguousarray(landmarks, dtype=np.float64)
+        actions = np.ascontiguousarray(actions, dtype=np.float32)
+        if starts.shape != (E, A, 2) or landmarks.shape != (E, L, 2) or actions.shape != (T, E, A, 2):
+            raise ValueError(f"expected starts {(E, A, 2)}, landmarks {(E, L, 2)}, actions {(T, E, A, 2)}")
+        n_active = np.zeros(E, np.int32)
+        R, M, Cs = np.empty((E, A), np.float32), np.empty((E, A), np.float32), np.empty((E, 1), np.int32)
+        st = np.zeros(self.lib.smarl_stats_len(A, 1), np.float64)
         p = _lib.CollisionParams(size, A, L, 0, agents_size, 0, 0)
         acc = _lib.Accounting(gamma, T, 0, _p(thr))
-        _lib.check(self.lib.smarl_host_collision_rollout(self._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(lm),
-                                                         _p(act), _p(lam), _p(R), _p(M), _p(Cs), _p(n_active), _p(st)))
-        return self._result(R, M, Cs, st, n_active=n_active[0, :E])
+        _lib.check(self.lib.smarl_host_collision_rollout_envmajor(self._sess, C.byref(p), C.byref(acc), _p(starts),
+                                                                  _p(landmarks), _p(actions), _p(lam), _p(R), _p(M), _p(Cs),
+                                                                  _p(n_active), _p(st)))
+        return dict(R=R, modR=M, C=Cs, stats=st, n_active=n_active)

@@ -100,3 +100,57 @@ def test_host_collision_rollout_multi_chunk():
     close(out["R"], want["R"], scale); close(out["modR"], want["modR"], scale)
     assert (n_active < T).any()
     h.close()
+
+
+def test_host_agent_major_entries_equal_env_major():
+    """The padded agent-major entry points (what bench.py's e2e binds) and the env-major ones the numpy wrapper
+    uses must produce identical arrays, for Congestion (Philox noise and recorded moves) and Collision."""
+    import ctypes as C
+    from safe_multiagent_rl_b200 import _lib
+    from safe_multiagent_rl_b200.envs.congestion import keep_threshold
+    from safe_multiagent_rl_b200.host import HostRollout, _am, _p
+    rng = np.random.default_rng(5)
+    # ---- Congestion
+    size, A, E, T, gamma, noise, seed, off = 7, 6, 66_001, 5, 0.95, 0.3, 9, 77
+    demand = rng.random((size + 1, size + 1)) * 8 + 2
+    starts = rng.integers(0, size, (E, A, 2)); starts[:, 0] = 0
+    actions = rng.integers(0, 5, (T, E, A))
+    moves = rng.integers(0, 5, (T, E, A))
+    h = HostRollout("congestion", A, T, E)
+    ld = h.ld
+    for mv in (None, moves):
+        em = h.congestion(size, starts, actions, demand, noise=noise, seed=seed, env_offset=off, moves=mv, lambdas=[0.4],
+                          gamma=gamma, thresholds=[2.0])
+        sx, sy = _am(starts[:, :, 0], ld, np.uint8), _am(starts[:, :, 1], ld, np.uint8)
+        act, mva = _am(actions, ld, np.uint8), (None if mv is None else _am(mv, ld, np.uint8))
+        R, M = np.zeros((A, ld), np.float32), np.zeros((A, ld), np.float32)
+        Cs, st = np.zeros((1, ld), np.int32), np.zeros(h.lib.smarl_stats_len(A, 1))
+        dem, lam, thr = np.ascontiguousarray(demand), np.array([0.4]), np.array([2.0])
+        p = _lib.CongestionParams(size, A, _p(dem), 1 if mv is not None else 2, 0, keep_threshold(noise), seed, off, None)
+        acc = _lib.Accounting(gamma, T, 0, _p(thr))
+        _lib.check(h.lib.smarl_host_congestion_rollout(h._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act), _p(mva),
+                                                       _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
+        assert np.array_equal(R[:, :E].T, em["R"]) and np.array_equal(M[:, :E].T, em["modR"])
+        assert np.array_equal(Cs[:, :E].T, em["C"]) and np.array_equal(st, em["stats"])
+    h.close()
+    # ---- Collision (A = 24: the f64 transpose tile has to shrink to fit shared memory)
+    size, A, L, E, T = 6, 24, 2, 65_600, 4
+    starts, lm = rng.random((E, A, 2)) * size, rng.random((E, L, 2)) * size
+    actions = rng.normal(0, 0.5, (T, E, A, 2)).astype(np.float32)
+    h = HostRollout("collision", A, T, E, n_landmarks=L)
+    ld = h.ld
+    em = h.collision(size, starts, lm, actions, lambdas=[0.5], gamma=0.99, thresholds=[1.0])
+    sx, sy = _am(starts[:, :, 0], ld, np.float64), _am(starts[:, :, 1], ld, np.float64)
+    lma = _am(lm.reshape(E, 2 * L), ld, np.float64)
+    act = _am(actions.reshape(T, E, 2 * A), ld, np.float32)
+    R, M = np.zeros((A, ld), np.float32), np.zeros((A, ld), np.float32)
+    Cs, na, st = np.zeros((1, ld), np.int32), np.zeros((1, ld), np.int32), np.zeros(h.lib.smarl_stats_len(A, 1))
+    lam, thr = np.array([0.5]), np.array([1.0])
+    p = _lib.CollisionParams(size, A, L, 0, 0.25, 0, 0)
+    acc = _lib.Accounting(0.99, T, 0, _p(thr))
+    _lib.check(h.lib.smarl_host_collision_rollout(h._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(lma), _p(act), _p(lam),
+                                                  _p(R), _p(M), _p(Cs), _p(na), _p(st)))
+    assert np.array_equal(R[:, :E].T, em["R"]) and np.array_equal(M[:, :E].T, em["modR"])
+    assert np.array_equal(Cs[:, :E].T, em["C"]) and np.array_equal(na[0, :E], em["n_active"])
+    assert np.array_equal(st, em["stats"])
+    h.close()
