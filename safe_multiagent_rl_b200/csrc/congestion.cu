@@ -144,18 +144,10 @@ __global__ void __launch_bounds__(kCongThreads, cong_min_blocks(A)) congestion_s
   }
 
   uint32_t conw[A];
-#pragma unroll
-  for (int i = 0; i < A; ++i) conw[i] = 0u;
-  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll 1
-  for (int k = 0; k < 4; ++k) {
-    const int at_origin = congestion_env<A>(xw, yw, dcw, aw, conw, k);
-    const int c = max(0, A / 3 - at_origin);                             // congestion.py:93-100
-    c0 = k == 0 ? c : c0;
-    c1 = k == 1 ? c : c1;
-    c2 = k == 2 ? c : c2;
-    c3 = k == 3 ? c : c3;
-  }
+  const uint32_t org = congestion_classes<A, kSimdClassAgentsStep>(xw, yw, dcw, aw, conw);
+  // congestion.py:93-100: cost = max(0, A // 3 - #agents on node (0,0)) per env lane
+  const int c0 = max(0, A / 3 - (int)(org & 0xFFu)), c1 = max(0, A / 3 - (int)((org >> 8) & 0xFFu)),
+            c2 = max(0, A / 3 - (int)((org >> 16) & 0xFFu)), c3 = max(0, A / 3 - (int)(org >> 24));
   st_stream_i4(a.cost + e0, make_int4(c0, c1, c2, c3));
   if (a.penalty) {                                                       // meta_agent.py:21-22
     const double lam = __ldg(a.lambdas);
@@ -236,18 +228,9 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
     if (MODE == 2) congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + e0, (uint32_t)t);
     uint32_t dcw[A], conw[A];
     congestion_transition<A>(xw, yw, mw, dcw, size4);
-#pragma unroll
-    for (int i = 0; i < A; ++i) conw[i] = 0u;
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-      const int c = max(0, A / 3 - congestion_env<A>(xw, yw, dcw, aw, conw, k));
-      c0 = k == 0 ? c : c0;
-      c1 = k == 1 ? c : c1;
-      c2 = k == 2 ? c : c2;
-      c3 = k == 3 ? c : c3;
-    }
-    const int cost[4] = {c0, c1, c2, c3};
+    const uint32_t org = congestion_classes<A, kSimdClassAgentsRollout>(xw, yw, dcw, aw, conw);
+    const int cost[4] = {max(0, A / 3 - (int)(org & 0xFFu)), max(0, A / 3 - (int)((org >> 8) & 0xFFu)),
+                         max(0, A / 3 - (int)((org >> 16) & 0xFFu)), max(0, A / 3 - (int)(org >> 24))};
     float pen[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -43,10 +43,61 @@ __device__ __forceinline__ void congestion_noise_moves(const uint32_t (&aw)[A], 
   }
 }
 
-// Congestion._congestions (congestion.py:113-137) for env lane k of the packed words, in the
-// closed form proved equivalent in tests/test_oracle_vs_reference.py: agents sharing the same
-// directed edge form a class; with L = lowest index in the class whose INTENDED action is a
-// move (<4), members >= L get (#members >= L) - 1, everything else 0.
+// 0x01 in every byte of v that is zero (carry-free: the low 7 bits are tested by an add that cannot leave the byte).
+__device__ __forceinline__ uint32_t zero_bytes01(uint32_t v) {
+  const uint32_t k7f = 0x7F7F7F7Fu;
+  return (~(((v & k7f) + k7f) | v) & 0x80808080u) >> 7;
+}
+
+// Congestion._congestions (congestion.py:113-137) for the four envs of the packed words at once, in the
+// closed form proved equivalent in tests/test_oracle_vs_reference.py: agents sharing the same directed edge
+// form a class; with L = lowest index in the class whose INTENDED action is a move (<4), members >= L
+// ("active") get (#members >= L) - 1, everything else 0.
+//   xw,yw  new positions   dcw  displacement code (nx-ox+1) | (ny-oy+1) << 2   aw intended (0..4)
+// The edge (ox,oy,nx,ny) is identified by the three bytes (nx, ny, dcode); every quantity below is a byte
+// per env lane (flags 0/1, counts <= 31), so one pass over the A(A-1)/2 pairs serves all four envs:
+//   e(i,j)  = [key_i == key_j]
+//   act_j   = mov_j | OR_{i<j} e(i,j) & mov_i          (some member k <= j of j's class intends to move)
+//   con_i   = act_i ? sum_{j != i} e(i,j) & act_j : 0
+// Row j's e(.,j) are kept in registers until act_j is final, then added to both counters.
+// Writes conw[i]; returns the per-lane number of agents standing on node (0,0) (congestion.py:97).
+template <int A>
+__device__ __forceinline__ uint32_t congestion_env4(const uint32_t (&xw)[A], const uint32_t (&yw)[A],
+                                                    const uint32_t (&dcw)[A], const uint32_t (&aw)[A],
+                                                    uint32_t (&conw)[A]) {
+  const uint32_t k01 = 0x01010101u;
+  uint32_t mov[A], act[A], cnt[A];
+  uint32_t at_origin = 0u;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    mov[i] = ((aw[i] >> 2) & k01) ^ k01;              // a < 4 for a in 0..4
+    at_origin += zero_bytes01(xw[i] | yw[i]);
+    cnt[i] = 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    uint32_t e[A];
+    uint32_t a_j = mov[j];
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      e[i] = zero_bytes01((xw[i] ^ xw[j]) | (yw[i] ^ yw[j]) | (dcw[i] ^ dcw[j]));
+      a_j |= e[i] & mov[i];
+    }
+    act[j] = a_j;
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      cnt[i] += e[i] & a_j;
+      cnt[j] += e[i] & act[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < A; ++i) conw[i] = cnt[i] & (act[i] * 0xFFu);
+  return at_origin;
+}
+
+// The same closed form for ONE env lane k of the packed words, with per-agent class bitmasks and popc.  Used
+// for larger agent counts (thresholds below), where the byte-SIMD form's unrolled pair loop over all four lanes runs out
+// of registers (measured: A = 16 -2 %, A = 32 -5 % with the SIMD form; A = 3..8 +12..26 %).
 //   xw,yw  new positions   dcw  displacement code (nx-ox+1) | (ny-oy+1) << 2   aw intended
 // The edge (ox,oy,nx,ny) is identified by the 3-byte key (nx, ny, dcode).
 // Writes byte k of conw[i]; returns the number of agents standing on node (0,0).
@@ -90,6 +141,28 @@ __device__ __forceinline__ int congestion_env(const uint32_t (&xw)[A], const uin
     conw[i] |= con << (8 * k);
   }
   return at_origin;
+}
+
+// Largest agent count served by the byte-SIMD form, per kernel (measured on 2^20 envs: the step kernel gains up to
+// A = 10 and loses 12 % at A = 12, where it needs 180 registers; the fused rollout still gains 9 % at A = 12).
+constexpr int kSimdClassAgentsStep = 10;
+constexpr int kSimdClassAgentsRollout = 12;
+
+// Congestions of the four envs of a thread + per-lane count of agents on node (0,0) (bytes of the result).
+template <int A, int MAX_SIMD_A>
+__device__ __forceinline__ uint32_t congestion_classes(const uint32_t (&xw)[A], const uint32_t (&yw)[A],
+                                                       const uint32_t (&dcw)[A], const uint32_t (&aw)[A],
+                                                       uint32_t (&conw)[A]) {
+  if constexpr (A <= MAX_SIMD_A) {
+    return congestion_env4<A>(xw, yw, dcw, aw, conw);
+  } else {
+#pragma unroll
+    for (int i = 0; i < A; ++i) conw[i] = 0u;
+    uint32_t org = 0u;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) org |= (uint32_t)congestion_env<A>(xw, yw, dcw, aw, conw, k) << (8 * k);
+    return org;
+  }
 }
 
 // Waiting-branch reward in f64, the reference's operation order (congestion.py:86-87).
