@@ -266,6 +266,13 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
   if (live) {
     st_stream_i4(a.C + e0, make_int4(csum[0], csum[1], csum[2], csum[3]));
   }
+  if (live) {   // unrolled: dynamic indices would push the position words into local memory for the whole episode
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      if (a.final_x) st_stream_u32(a.final_x + i * ld + e0, xw[i]);
+      if (a.final_y) st_stream_u32(a.final_y + i * ld + e0, yw[i]);
+    }
+  }
 #pragma unroll 1
   for (int i = 0; i < A; ++i) {
     double raw[4], mod[4];
@@ -275,8 +282,6 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
       mod[k] = raw[k] - s_pen[k];
     }
     if (live) {
-      if (a.final_x) st_stream_u32(a.final_x + i * ld + e0, xw[i]);
-      if (a.final_y) st_stream_u32(a.final_y + i * ld + e0, yw[i]);
       st_stream_f4(a.R + i * ld + e0, make_float4((float)raw[0], (float)raw[1], (float)raw[2], (float)raw[3]));
       st_stream_f4(a.modR + i * ld + e0, make_float4((float)mod[0], (float)mod[1], (float)mod[2], (float)mod[3]));
     }
