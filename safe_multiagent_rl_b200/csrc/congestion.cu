@@ -36,10 +36,12 @@ struct CongestionStepArgs {
 };
 
 constexpr int kCongThreads = 128;
-// Both Congestion kernels are issue / latency-bound, so up to 8 agents the register budget is capped
-// (64 per thread in the step kernel, 128 in the rollout kernel: no or a few bytes of spills) to run 8 CTAs
-// per SM; measured on config 2 (A=8): rollout 5.28 -> 4.39 ms, closed loop 6.53 -> 6.29 ms.  Larger
-// agent counts would spill hundreds of bytes and get slower, so they keep the compiler's choice.
+// Both Congestion kernels are issue / latency-bound, so up to 8 agents the register budget is capped for more
+// resident CTAs: 80 per thread in the step kernel (6 CTAs of 128; with the byte-SIMD class counting a tighter cap
+// spills more than the occupancy returns: config 2 closed loop 5.38 ms at 64 registers, 5.29 at 72, 5.18 at 80) and
+// 128 in the rollout kernel (8 CTAs of 64: rollout 5.28 -> 4.39 ms when introduced).  Larger agent counts would
+// spill hundreds of bytes and get slower, so they keep the compiler's choice.
+constexpr int cong_step_min_blocks(int A) { return A <= 8 ? 6 : 1; }
 constexpr int cong_min_blocks(int A) { return A <= 8 ? 8 : 1; }
 
 // One Congestion transition for four envs (congestion.py:49-75): applies the effective moves,
@@ -103,7 +105,7 @@ int launch_congestion_rollout_m2(int A, const CongestionRolloutArgs& a, unsigned
 
 #if SMARL_TU_IS(0) || SMARL_TU_IS(1) || SMARL_TU_IS(2)
 template <int A, int MODE>
-__global__ void __launch_bounds__(kCongThreads, cong_min_blocks(A)) congestion_step_kernel(const CongestionStepArgs a) {
+__global__ void __launch_bounds__(kCongThreads, cong_step_min_blocks(A)) congestion_step_kernel(const CongestionStepArgs a) {
   const int64_t g = (int64_t)blockIdx.x * kCongThreads + threadIdx.x;
   if (g >= a.n_groups) return;
   // 32-bit element offsets (the host checks (2A+1) * ld < 2^32): one add per row and one wide add per
