@@ -101,10 +101,13 @@ def test_config3_congestion_10x10_8_agents_1M_envs():
         close(o["modR"][:n].t().cpu().numpy(), ref["modR"], scale)
 
 
-def test_config2_collision_5x5_3_agents_65536_envs():
-    """configs[1]: CollisionAvoidance size 5, 3 agents, 65,536 envs, T=50."""
+@pytest.mark.parametrize("A,E,T", [(3, 65536, 50),          # configs[1]
+                                   (3, 1 << 18, 20),        # large batch: the register-capped A <= 4 kernels
+                                   (4, (1 << 18) + 40, 12)])
+def test_config2_collision_5x5_3_agents_65536_envs(A, E, T):
+    """configs[1]: CollisionAvoidance size 5, 3 agents, 65,536 envs, T=50 (and the kernels large batches select)."""
     import safe_multiagent_rl_b200 as s
-    S, A, L, E, T, gamma = 5, 3, 1, 65536, 50, 0.99
+    S, L, gamma = 5, 1, 0.99
     rng = np.random.default_rng(5)
     starts = rng.random((E, A, 2)) * S
     lm = rng.random((E, L, 2)) * S
