@@ -14,8 +14,10 @@ from tools.sweep import make  # noqa: E402
 env_name, S, A, E, T = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 env, K, _ = make(env_name, S, A, E, g)
-if env_name == "collision":
+if env_name in ("collision", "coverage_cont"):
     actions = torch.randn((T, 2 * A, env.ld), generator=g, device="cuda") * 0.5
+elif env_name == "coverage_disc":
+    actions = torch.randint(0, 9, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
 else:
     actions = torch.randint(0, 5, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
 lam = torch.full((K,), 0.1, dtype=torch.float64, device="cuda")

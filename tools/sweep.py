@@ -33,6 +33,21 @@ def make(env_name, S, A, E, g):
         env.start_x[1:, :E] = torch.randint(0, S, (A - 1, E), generator=g, device=dev, dtype=torch.uint8)
         env.start_y[1:, :E] = torch.randint(0, S, (A - 1, E), generator=g, device=dev, dtype=torch.uint8)
         K, bytes_step = 1, 19.0 + 8.0 / A            # incl. the effective-move row the step kernel publishes
+    elif env_name in ("coverage_cont", "coverage_disc"):       # the paper's Explore variants (f64 positions, coarseness 6)
+        starts = np.zeros((E, A, 2))
+        if env_name == "coverage_cont":
+            env = s.BatchedCoverageContinuous(S, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)], coarseness=6,
+                                              starts=starts)
+            pos = torch.rand((2, A, E), generator=g, device=dev, dtype=torch.float64) * S
+            bytes_step = 32.0 + 8.0 + 8.0 + 4.0 + 4.0 + 1.0 + 4.0 / A      # pos r/w, action, obs, reward, cost, done, penalty
+        else:
+            env = s.BatchedCoverageDiscretized(S, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)], coarseness=6,
+                                               starts=starts)
+            zoom = 6.0 / S
+            pos = torch.floor(torch.rand((2, A, E), generator=g, device=dev, dtype=torch.float64) * S * zoom) / zoom
+            bytes_step = 32.0 + 1.0 + 8.0 + 4.0 + 4.0 + 1.0 + 4.0 / A
+        env.start_x[:, :E], env.start_y[:, :E] = pos[0], pos[1]
+        K = A
     else:
         rng = np.random.default_rng(0)
         env = s.BatchedCollisionAvoidance(S, A, n_envs=E, starts=np.zeros((E, A, 2)), landmarks=np.zeros((E, 1, 2)))
@@ -59,8 +74,10 @@ def timed(fn, iters):
 def run(env_name, S, A, E, T):
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     env, K, bytes_step = make(env_name, S, A, E, g)
-    if env_name == "collision":
+    if env_name in ("collision", "coverage_cont"):
         actions = torch.randn((T, 2 * A, env.ld), generator=g, device="cuda") * 0.5
+    elif env_name == "coverage_disc":
+        actions = torch.randint(0, 9, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
     else:
         actions = torch.randint(0, 5, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
     lam = torch.full((K,), 0.1, dtype=torch.float64, device="cuda")
@@ -95,7 +112,9 @@ if __name__ == "__main__":
     cfgs = [("coverage", 5, 3, 50, 50),            # configs[0]
             ("collision", 5, 3, 65536, 50),        # configs[1]
             ("congestion", 10, 8, 1 << 20, 100),   # configs[2]
-            ("coverage", 32, 16, 1 << 22, 50)]     # configs[3] per GPU
+            ("coverage", 32, 16, 1 << 22, 50),     # configs[3] per GPU
+            ("coverage_cont", 5, 3, 1 << 20, 50),  # ExploreContinuous / ExploreDiscretized, the paper's runs (coarseness 6)
+            ("coverage_disc", 5, 3, 1 << 20, 50)]
     if a.cfg:
         cfgs = [(c.split(",")[0], *map(int, c.split(",")[1:])) for c in a.cfg]
     elif not a.quick:                                # configs[4]: sweep
