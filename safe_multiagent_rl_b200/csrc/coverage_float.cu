@@ -148,8 +148,10 @@ int launch_coverage_float_rollout_m1(int A, const CoverageFloatRolloutArgs& a, u
 #if SMARL_TU_IS(3) || SMARL_TU_IS(4)
 // Fused open-loop episode of the float-position Coverage envs: positions, per-agent cost sums and the
 // (S_rew, S_pen) discounted sums stay in registers; reward_a = w_a * rew, so one pair serves every agent.
-template <int A, int MODE>
-__global__ void __launch_bounds__(kCovFThreads) coverage_float_rollout_kernel(const CoverageFloatRolloutArgs r) {
+// CAP: 64 registers (8 CTAs per SM) for A <= 4 on batches >= 2^18 envs (2^20 envs: Continuous 1.69 -> 1.26 ms, Discretized
+// 2.34 -> 2.00 ms per batch); a one-wave batch of 65 536 envs is latency-bound per thread and loses 8 % to the spills.
+template <int A, int MODE, bool CAP>
+__global__ void __launch_bounds__(kCovFThreads, (CAP ? 8 : 1)) coverage_float_rollout_kernel(const CoverageFloatRolloutArgs r) {
   __shared__ double s_red[kCovFThreads / 32];
   const CoverageFloatArgs& a = r.env;
   const int64_t eg = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
@@ -239,7 +241,16 @@ __global__ void __launch_bounds__(kCovFThreads) coverage_float_rollout_kernel(co
 }
 #define SMARL_DEFINE_COVF_ROLLOUT(M)                                                                              \
   int launch_coverage_float_rollout_m##M(int A, const CoverageFloatRolloutArgs& a, unsigned grid, cudaStream_t s) { \
-    SMARL_DISPATCH_A(A, coverage_float_rollout_kernel<kA, M><<<grid, kCovFThreads, 0, s>>>(a));                   \
+    if (A <= 4 && a.env.n_envs >= (1 << 18)) {                                                                      \
+      switch (A) {                                                                                                  \
+        case 1: coverage_float_rollout_kernel<1, M, true><<<grid, kCovFThreads, 0, s>>>(a); break;                  \
+        case 2: coverage_float_rollout_kernel<2, M, true><<<grid, kCovFThreads, 0, s>>>(a); break;                  \
+        case 3: coverage_float_rollout_kernel<3, M, true><<<grid, kCovFThreads, 0, s>>>(a); break;                  \
+        default: coverage_float_rollout_kernel<4, M, true><<<grid, kCovFThreads, 0, s>>>(a); break;                 \
+      }                                                                                                             \
+    } else {                                                                                                        \
+      SMARL_DISPATCH_A(A, coverage_float_rollout_kernel<kA, M, false><<<grid, kCovFThreads, 0, s>>>(a));            \
+    }                                                                                                               \
     SMARL_CUDA(cudaGetLastError());                                                                               \
     return SMARL_OK;                                                                                              \
   }

@@ -681,7 +681,10 @@ def test_tiny_batches_all_envs(E):
 
 
 @pytest.mark.parametrize("kind,size,A,E,T,coarse,seed", [("continuous", 5, 3, 300, 40, 6, 1), ("continuous", 10, 8, 130, 15, None, 2),
-                                                          ("discretized", 5, 3, 300, 40, 20, 0), ("discretized", 3, 32, 33, 6, 3, 3)])
+                                                          ("discretized", 5, 3, 300, 40, 20, 0), ("discretized", 3, 32, 33, 6, 3, 3),
+                                                          # >= 2^18 envs with A <= 4: the register-capped kernel builds
+                                                          ("continuous", 5, 3, (1 << 18) + 8, 6, 6, 4),
+                                                          ("discretized", 5, 4, 1 << 18, 5, 6, 5)])
 @pytest.mark.parametrize("g_mode", [0, 1, 2])
 def test_coverage_float_fused_rollout(kind, size, A, E, T, coarse, seed, g_mode):
     s = smarl()
