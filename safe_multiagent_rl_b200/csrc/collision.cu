@@ -264,7 +264,7 @@ int launch_collision_rollout(int A, const CollisionRolloutArgs& a, unsigned grid
 // CAP: 64 registers (8 CTAs per SM) for A <= 4 on large batches, where occupancy pays (2^22 envs: closed loop +6.6 %,
 // fused +9 %); a one-wave batch like config 1 (65 536 envs) is latency-bound per thread and loses 3 % to the spills.
 template <int A, bool CAP>
-__global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 1)) collision_step_kernel(const CollisionStepArgs a) {
+__global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_kernel(const CollisionStepArgs a) {
   const int64_t e = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
   if (e >= a.n_envs) return;
   const int64_t ld = a.ld;
@@ -352,7 +352,9 @@ int launch_collision_step(int A, const CollisionStepArgs& a, unsigned grid, cuda
 
 #if SMARL_TU_IS(1)
 template <int A, bool CAP>
-__global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 1)) collision_rollout_kernel(const CollisionRolloutArgs a) {
+// (second launch bound: 0 = unspecified -- 1 would lift the compiler's register heuristic to 255 and cost A = 8 10 %;
+//  A = 5..8 is held to 5 CTAs per SM / 96 registers: fused A = 6 +13 %, A = 8 +7 % on 2^20..2^21 envs)
+__global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5 : 0))) collision_rollout_kernel(const CollisionRolloutArgs a) {
   __shared__ double s_red[kCollThreads / 32];
   const int64_t eg = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
   const bool live = eg < a.n_envs;

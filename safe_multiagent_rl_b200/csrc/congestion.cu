@@ -41,8 +41,8 @@ constexpr int kCongThreads = 128;
 // spills more than the occupancy returns: config 2 closed loop 5.38 ms at 64 registers, 5.29 at 72, 5.18 at 80) and
 // 128 in the rollout kernel (8 CTAs of 64: rollout 5.28 -> 4.39 ms when introduced).  Larger agent counts would
 // spill hundreds of bytes and get slower, so they keep the compiler's choice.
-constexpr int cong_step_min_blocks(int A) { return A <= 8 ? 6 : 1; }
-constexpr int cong_min_blocks(int A) { return A <= 8 ? 8 : 1; }
+constexpr int cong_step_min_blocks(int A) { return A <= 8 ? 6 : 0; }   // 0 = unspecified (1 would lift the register heuristic to 255)
+constexpr int cong_min_blocks(int A) { return A <= 8 ? 8 : 0; }
 
 // One Congestion transition for four envs (congestion.py:49-75): applies the effective moves,
 // leaves the new positions in xw/yw and the displacement codes in dcw.

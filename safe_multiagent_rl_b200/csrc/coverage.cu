@@ -183,7 +183,7 @@ int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaSt
 // Up to 4 agents the kernel is capped at 64 registers (8 CTAs per SM; A = 3 / 4 on 2^22 envs +4 % / +1.5 %); from A = 8 on a cap
 // was measured slower (A = 8 at 96 registers -3 %, A = 16 at 128 registers -13 %).
 template <int A>
-__global__ void __launch_bounds__(kRolloutThreads, (A <= 4 ? 8 : 1)) coverage_rollout_kernel(const CoverageRolloutArgs a) {
+__global__ void __launch_bounds__(kRolloutThreads, (A <= 4 ? 8 : 0)) coverage_rollout_kernel(const CoverageRolloutArgs a) {
   extern __shared__ float s_lut[];
   coverage_load_lut(s_lut, a.lut, a.lut_len);
   const int64_t g = (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;

@@ -151,7 +151,7 @@ int launch_coverage_float_rollout_m1(int A, const CoverageFloatRolloutArgs& a, u
 // CAP: 64 registers (8 CTAs per SM) for A <= 4 on batches >= 2^18 envs (2^20 envs: Continuous 1.69 -> 1.26 ms, Discretized
 // 2.34 -> 2.00 ms per batch); a one-wave batch of 65 536 envs is latency-bound per thread and loses 8 % to the spills.
 template <int A, int MODE, bool CAP>
-__global__ void __launch_bounds__(kCovFThreads, (CAP ? 8 : 1)) coverage_float_rollout_kernel(const CoverageFloatRolloutArgs r) {
+__global__ void __launch_bounds__(kCovFThreads, (CAP ? 8 : 0)) coverage_float_rollout_kernel(const CoverageFloatRolloutArgs r) {
   __shared__ double s_red[kCovFThreads / 32];
   const CoverageFloatArgs& a = r.env;
   const int64_t eg = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
