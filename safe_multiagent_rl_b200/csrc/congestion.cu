@@ -42,7 +42,7 @@ constexpr int kCongThreads = 128;
 // 128 in the rollout kernel (8 CTAs of 64: rollout 5.28 -> 4.39 ms when introduced).  Larger agent counts would
 // spill hundreds of bytes and get slower, so they keep the compiler's choice.
 constexpr int cong_step_min_blocks(int A) { return A <= 8 ? 6 : 0; }   // 0 = unspecified (1 would lift the register heuristic to 255)
-constexpr int cong_min_blocks(int A) { return A <= 8 ? 8 : 0; }
+constexpr int cong_min_blocks(int A) { return A <= 8 ? 8 : (A <= 12 ? 5 : 0); }   // A = 9..12: 168 registers (A = 12 fused +9 %)
 
 // One Congestion transition for four envs (congestion.py:49-75): applies the effective moves,
 // leaves the new positions in xw/yw and the displacement codes in dcw.
