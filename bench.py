@@ -302,7 +302,7 @@ def run_ours(a):
             if ev_b is not None:
                 ev_b.record()
             _lib.check(lib.smarl_rollout_returns_shared(C.byref(acc), P(lbuf.reward), P(env._weights), P(lbuf.cost),
-                                                        lbuf.cost_code, P(lbuf.penalty), P(lbuf.R), P(lbuf.modR),
+                                                        lbuf.cost_code, P(lbuf.penalty), None, P(lbuf.R), P(lbuf.modR),
                                                         P(lbuf.Csum), P(lbuf.G), P(lbuf.stats_vec),
                                                         P(lbuf.stats_scratch), A, K, E, ld, stream))
             sd.allreduce_stats(lbuf.stats_vec)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SMARL_ABI_VERSION 1
+#define SMARL_ABI_VERSION 2
 #define SMARL_MAX_AGENTS 32
 
 enum {
@@ -46,11 +46,19 @@ enum {
 };
 
 typedef void* smarl_stream_t;   /* cudaStream_t */
+enum { SMARL_ENV_COVERAGE = 0, SMARL_ENV_CONGESTION = 1, SMARL_ENV_COLLISION = 2 };
 
 int smarl_abi_version(void);
 const char* smarl_last_error(void);
 /* SM count and compute capability of the current device. */
 int smarl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Kernel-variant knob (profiling and tests; results never depend on it).  Large agent counts are served by
+ * lane-cooperative kernels that split one env over 2 or 4 lanes of a warp; by default the library picks the
+ * measured-fastest mapping per (env kind, n_agents).  lanes: -1 = automatic (default), 0 = one thread per env
+ * (Collision) / per four envs (grid envs), 2 or 4 = force the cooperative kernels where they exist (n_agents >= 9).
+ * env_kind is SMARL_ENV_COVERAGE / _CONGESTION / _COLLISION.  Process-wide; returns the previous setting. */
+int smarl_set_kernel_variant(int32_t env_kind, int32_t lanes);
 
 /* ------------------------------------------------------------------------------------
  * Grid envs share start/reset: replaces CoverageContinuous.reset/_restart
@@ -199,16 +207,20 @@ typedef struct {
   const double* demand;  /* [(size+1)*(size+1)] row-major [x][y], f64     congestion.py:28,86 */
   /* action noise (congestion.py:64-67): move = a if u1 < 1-noise else int(u2*5)              */
   int32_t noise_mode;    /* 0 = none, 1 = recorded effective moves, 2 = on-device Philox      */
-  int32_t reserved;
+  uint32_t episode;      /* mode 2: episode index mixed into the Philox counter (low 29 bits), so that every
+                            episode draws fresh noise like the reference's random(); see episode_dev   */
   uint64_t keep_threshold; /* mode 2: keep action iff w < keep_threshold, = ceil((1-noise)*2^32);
                               otherwise the move is w mod 5 (w = word a&3 of the Philox output)    */
   uint64_t seed;         /* mode 2: Philox4x32-10 key                                         */
-  int64_t env_offset;    /* mode 2: global id of env 0 (counter = (id, t, agent>>2)), so the
+  int64_t env_offset;    /* mode 2: global id of env 0 (counter = (id, t, agent>>2 | episode<<3)), so the
                             stream does not depend on how envs are sharded over GPUs          */
   const float* wait_reward; /* optional [A][(size+1)^2]: f32(-30*(con+1)/demand[x][y] + 7.5 - 4) for
                             con = 0..A-1, i.e. the waiting-branch reward (congestion.py:86-87)
                             evaluated in f64 on the host and rounded once; replaces a float64
                             division per agent-step in the kernels.  NULL = compute from demand.  */
+  const uint32_t* episode_dev; /* optional DEVICE scalar added to `episode` when the kernel runs: lets a captured
+                            CUDA graph draw fresh noise on every replay (bump it between replays).  NULL = 0;
+                            must be NULL in the smarl_host_* calls.                                    */
 } SmarlCongestionParams;
 
 /* One Congestion.step (congestion.py:106-111 = transition :49-75 + reward :77-90 with
@@ -308,9 +320,11 @@ int smarl_rollout_returns(const SmarlAccounting* acc, const float* reward, const
 /* Same accounting for a rollout buffer that stores ONE reward row per env and step (Coverage with
  * reward_rows = 1; Collision, whose reward is identical for all agents): reward_a[t] = w_a * reward_env[t].
  *   reward_env f32 [T][ld]   weights f32 [A] (NULL = 1)   everything else as smarl_rollout_returns
- *   (g_mode 0..3).  Reads 8/A instead of 4 + 4/A reward/penalty bytes per agent-step. */
+ *   (g_mode 0..3; n_active i32 [ld] episode lengths, NULL = T, honoured by g_mode 3 exactly as there).
+ *   Reads 8/A instead of 4 + 4/A reward/penalty bytes per agent-step. */
 int smarl_rollout_returns_shared(const SmarlAccounting* acc, const float* reward_env, const float* weights,
-                                 const void* cost, int32_t cost_dtype, const float* penalty, float* R,
+                                 const void* cost, int32_t cost_dtype, const float* penalty,
+                                 const int32_t* n_active, float* R,
                                  float* modR, int32_t* C, float* G, double* stats, double* stats_scratch,
                                  int32_t n_agents, int32_t n_constraints, int64_t n_envs, int64_t ld,
                                  smarl_stream_t stream);
@@ -329,7 +343,6 @@ int smarl_lambda_update(double* lambdas, const double* stats, const double* thre
  * products are in the host arrays.  Synchronous; one call at a time per session.
  * ---------------------------------------------------------------------------------- */
 typedef struct SmarlHostSession SmarlHostSession;   /* opaque: streams + device buffers */
-enum { SMARL_ENV_COVERAGE = 0, SMARL_ENV_CONGESTION = 1, SMARL_ENV_COLLISION = 2 };
 
 /* One session per (env kind, n_agents, n_steps, n_envs[, n_landmarks]); K follows the env. */
 int smarl_host_session_create(SmarlHostSession** out, int32_t env_kind, int32_t n_agents, int32_t n_steps,

@@ -5,7 +5,7 @@ The reference draws Congestion's action noise from Python's unseeded ``random``
 path uses a counter-based generator keyed by the *global* env id, so results do not
 depend on how envs are sharded over GPUs:
 
-    out = philox4x32_10(counter=(env_lo, env_hi, t, agent >> 2), key=(seed_lo, seed_hi))
+    out = philox4x32_10(counter=(env_lo, env_hi, t, agent >> 2 | episode << 3), key=(seed_lo, seed_hi))
     agent a uses the word w = out[a & 3]
     u1 = w * 2**-32,  u2 = (w mod 5 + 0.5) / 5     (both exact enough in f64: int(u2 * 5) == w mod 5)
     move = action if u1 < 1 - noise else int(u2 * 5)      (congestion.py:64-67)
@@ -44,15 +44,15 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def congestion_words(seed, env_ids, t, n_agents):
-    """uint32 word w, [E, A], for global env ids ``env_ids`` at step ``t``."""
+def congestion_words(seed, env_ids, t, n_agents, episode=0):
+    """uint32 word w, [E, A], for global env ids ``env_ids`` at step ``t`` of episode ``episode``."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     E = env_ids.shape[0]
     quads = (n_agents + 3) // 4
     c0 = (env_ids & MASK)[:, None]
     c1 = (env_ids >> np.uint64(32))[:, None]
     c2 = np.full((1, 1), t, dtype=np.uint64)
-    c3 = np.arange(quads, dtype=np.uint64)[None, :]
+    c3 = np.arange(quads, dtype=np.uint64)[None, :] | np.uint64((int(episode) << 3) & 0xFFFFFFFF)
     o = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)   # 4 x [E, quads]
     w = np.empty((E, 4 * quads), dtype=np.uint32)
     for q in range(4):
@@ -60,10 +60,10 @@ def congestion_words(seed, env_ids, t, n_agents):
     return w[:, :n_agents]
 
 
-def congestion_uniforms(seed, env_ids, t, n_agents):
+def congestion_uniforms(seed, env_ids, t, n_agents, episode=0):
     """The f64 uniforms (u1, u2) in [0,1) equivalent to the device's integer tests: feeding them to the
     reference's two ``random()`` calls (congestion.py:64,67) reproduces the device's moves."""
-    w = congestion_words(seed, env_ids, t, n_agents)
+    w = congestion_words(seed, env_ids, t, n_agents, episode)
     return w.astype(np.float64) * 2.0 ** -32, ((w % np.uint32(5)).astype(np.float64) + 0.5) / 5.0
 
 

@@ -28,9 +28,9 @@ class CoverageFloatParams(C.Structure):
 
 class CongestionParams(C.Structure):
     _fields_ = [("size", C.c_int32), ("n_agents", C.c_int32), ("demand", c_ptr),
-                ("noise_mode", C.c_int32), ("reserved", C.c_int32),
+                ("noise_mode", C.c_int32), ("episode", C.c_uint32),
                 ("keep_threshold", C.c_uint64), ("seed", C.c_uint64), ("env_offset", C.c_int64),
-                ("wait_reward", c_ptr)]
+                ("wait_reward", c_ptr), ("episode_dev", c_ptr)]
 
 
 class CollisionParams(C.Structure):
@@ -47,6 +47,7 @@ PROTOTYPES = {
     "smarl_abi_version": (C.c_int, []),
     "smarl_last_error": (C.c_char_p, []),
     "smarl_device_info": (C.c_int, [P(C.c_int), P(C.c_int), P(C.c_int)]),
+    "smarl_set_kernel_variant": (C.c_int, [i32, i32]),
     "smarl_grid_reset": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_random_starts_u8": (C.c_int, [i32, i32, C.c_uint64, i64, i64, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_random_starts_f64": (C.c_int, [i32, i32, f64, C.c_uint64, i64, i64, i32, c_ptr, c_ptr, i64, i32, i64, c_ptr]),
@@ -77,7 +78,7 @@ PROTOTYPES = {
     "smarl_rollout_penalty": (C.c_int, [c_ptr, i32, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_rollout_returns": (C.c_int, [P(Accounting), c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
-    "smarl_rollout_returns_shared": (C.c_int, [P(Accounting), c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr,
+    "smarl_rollout_returns_shared": (C.c_int, [P(Accounting), c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                                c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
     "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64, i32]),
@@ -126,10 +127,25 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.smarl_abi_version() != 1:
+    if lib.smarl_abi_version() != 2:
         raise SmarlError("libsmarl ABI version mismatch")
     _lib = lib
     return lib
+
+
+class kernel_variant:
+    """Context manager: force the thread mapping of one env kind's kernels (smarl_set_kernel_variant)."""
+
+    def __init__(self, env_kind: int, lanes: int):
+        self.env_kind, self.lanes = env_kind, lanes
+
+    def __enter__(self):
+        self.prev = load().smarl_set_kernel_variant(self.env_kind, self.lanes)
+        return self
+
+    def __exit__(self, *exc):
+        load().smarl_set_kernel_variant(self.env_kind, self.prev)
+        return False
 
 
 def check(rc: int) -> None:

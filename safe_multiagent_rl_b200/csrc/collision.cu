@@ -4,8 +4,9 @@
 // This file restates the reference's float64 arithmetic operation by operation so that
 // positions, done flags and collision counts are bit-exact; it is compiled with -fmad=false
 // and uses the _rn intrinsics wherever a contraction would change a rounding.
-#include "common.cuh"
-#include "stats.cuh"
+#include <stdlib.h>
+
+#include "collision.cuh"
 
 // Built as three translation units (build.py compiles this file once per SMARL_TU value):
 //   0 step kernel   1 fused rollout kernel   2 reset kernel + C entry points
@@ -15,94 +16,6 @@
 #define SMARL_TU_IS(k) (SMARL_TU == -1 || SMARL_TU == (k))
 
 namespace smarl {
-
-struct CollisionStepArgs {
-  double* pos_x;
-  double* pos_y;
-  uint8_t* done;
-  const float* actions;       // [2A][ld]
-  const double* landmarks;    // [2L][ld]
-  float* obs;
-  float* reward;
-  int32_t* cost;
-  uint8_t* done_out;
-  int32_t* episode_len;
-  const double* lambdas;
-  float* penalty;
-  int64_t n_envs;
-  int64_t ld;
-  double size;
-  double agents_size;
-  int32_t L;
-  int32_t obs_landmarks;
-  int32_t normalize;
-  int32_t reward_rows;
-};
-
-constexpr int kCollThreads = 128;
-constexpr int64_t kCollCapMinEnvs = 1 << 18;   // batches from which the A <= 4 kernels run register-capped (see below)
-
-// observation value of a coordinate: the state itself, or state / size with normalize_state
-// (collision_avoidance.py:164-165, a float64 division), rounded once to f32.
-__device__ __forceinline__ float obs_value(double v, double size, int normalize) {
-  return (float)(normalize ? __ddiv_rn(v, size) : v);
-}
-
-static __device__ __noinline__ float obs_normalized(double v, double size) { return (float)__ddiv_rn(v, size); }
-
-// numpy's pairwise float64 sum of n <= 128 contiguous values (what np.sum does to the A
-// per-agent minima at collision_avoidance.py:161): n < 8 sequential; otherwise 8 running
-// accumulators over blocks of 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail.
-template <int N>
-__device__ __forceinline__ double numpy_sum(const double (&v)[N]) {
-  if (N < 8) {
-    double s = 0.0;   // np.sum starts from the first element; 0.0 + v0 == v0 exactly (v0 >= 0)
-#pragma unroll
-    for (int i = 0; i < N; ++i) s = __dadd_rn(s, v[i]);
-    return s;
-  }
-  double r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = v[j < N ? j : 0];
-  constexpr int kFull = N - (N % 8);
-#pragma unroll
-  for (int i = 8; i < kFull; i += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], v[(i + j) < N ? (i + j) : 0]);
-  }
-  double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-#pragma unroll
-  for (int i = kFull; i < N; ++i) s = __dadd_rn(s, v[i]);
-  return s;
-}
-
-// sqrt_rn(q) < lim, out of line: only ever reached inside the 1e-9 / 1e-6 bands around lim^2 (practically
-// never), so the call sites stay three instructions instead of an inlined f64 square root each.
-static __device__ __noinline__ bool sqrt_below(double q, double lim) { return __dsqrt_rn(q) < lim; }
-
-// Exact recount of the colliding pairs (sqrt on every pair) for the rare env with a pair inside the
-// 1e-6 band around (2 agents_size)^2; rolled loops over a local-memory copy keep it out of the hot code.
-static __device__ __noinline__ int collisions_exact(const double* x, const double* y, int A, uint32_t alive,
-                                                    double lim) {
-  int n = 0;
-  for (int i = 0; i < A; ++i)
-    for (int j = i + 1; j < A; ++j) {
-      const double dx = __dadd_rn(x[i], -x[j]), dy = __dadd_rn(y[i], -y[j]);
-      const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      n += (__dsqrt_rn(q) < lim && ((alive >> i) & (alive >> j) & 1u)) ? 1 : 0;
-    }
-  return n;
-}
-
-// Exact test of one pair (the f64 arithmetic of the pair loop below) for the f32-screened path.
-static __device__ __noinline__ int pair_collides(const double* x, const double* y, int i, int j, double lim2_lo,
-                                                 double lim2_hi, double lim) {
-  const double dx = __dadd_rn(x[i], -x[j]), dy = __dadd_rn(y[i], -y[j]);
-  const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-  if (q < lim2_lo) return 1;
-  return (q < lim2_hi && __dsqrt_rn(q) < lim) ? 1 : 0;
-}
 
 constexpr int kPairPrefilterA = 12;   // agent count from which the pair loop is screened in f32
 
@@ -183,7 +96,7 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
       fx[i] = (float)px[i];
       fy[i] = (float)py[i];
     }
-    const float screen = (float)(lim2 * 1.01);
+    const float screen = collision_screen_q(lim, size);
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       uint32_t near = 0u;
@@ -225,40 +138,6 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
   collisions = n;
 }
 
-// ---------------------------------------------------------------------------------------
-// Fused open-loop episode: positions / done mask / discounted sums in registers for all T
-// steps (main.py:28-57 minus the policy nets, incl. the early break at :51).  The env reward
-// is shared by all agents, so one (S_rew, S_pen) pair per env serves every agent.
-// ---------------------------------------------------------------------------------------
-struct CollisionRolloutArgs {
-  const double* start_x;
-  const double* start_y;
-  const double* landmarks;
-  const float* actions;      // [T][2A][ld]
-  const double* lambdas;
-  double* final_x;
-  double* final_y;
-  uint8_t* final_done;
-  int32_t* n_active;
-  float* R;
-  float* modR;
-  int32_t* C;
-  float* G;
-  float* g_scratch;          // [2][T][ld]
-  double* partials;
-  const double* thresholds;
-  double gamma;
-  int64_t n_envs;
-  int64_t ld;
-  double size;
-  double agents_size;
-  int32_t L;
-  int32_t n_steps;
-  int32_t g_mode;
-};
-
-int launch_collision_step(int A, const CollisionStepArgs& a, unsigned grid, cudaStream_t s);
-int launch_collision_rollout(int A, const CollisionRolloutArgs& a, unsigned grid, cudaStream_t s);
 
 #if SMARL_TU_IS(0)
 // CAP: 64 registers (8 CTAs per SM) for A <= 4 on large batches, where occupancy pays (2^22 envs: closed loop +6.6 %,
@@ -482,6 +361,17 @@ __global__ void collision_reset_kernel(const double* __restrict__ start_x, const
     for (int l = 0; l < 2 * L; ++l) obs[(2 * A + l) * ld + e] = obs_value(landmarks[l * ld + e], size, normalize);
 }
 
+// Lanes per env: 0 = one thread per env (collision.cu), 2 / 4 = lane-cooperative kernels (collision_coop.cu).
+// Crossover measured on B200 (profiles/r02): see DESIGN.md section 3.3.  smarl_set_kernel_variant overrides it.
+int collision_coop_lanes(int A, int L, int64_t ld) {
+  if (A < 9) return 0;
+  if ((int64_t)(2 * A + 2 * L + 2) * ld >= (1ll << 32)) return 0;   // the cooperative kernels use 32-bit element offsets
+  const int forced = kernel_variant(SMARL_ENV_COLLISION);
+  if (forced >= 0) return forced;
+  if (A < 12) return 0;
+  return A <= 16 ? 2 : 4;
+}
+
 static int check_collision(const SmarlCollisionParams* p) {
   SMARL_REQUIRE(p != nullptr, "params is NULL");
   SMARL_REQUIRE(p->size >= 1, "size=%d must be >= 1", p->size);
@@ -531,6 +421,8 @@ extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x
   a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
   a.normalize = p->normalize_state;
   a.reward_rows = p->reward_rows == 1 ? 1 : 0;
+  if (const int lanes = collision_coop_lanes(p->n_agents, p->n_landmarks, ld))
+    return launch_collision_coop_step(p->n_agents, lanes, a, (cudaStream_t)stream);
   const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
   if (int rc = launch_collision_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;
@@ -560,8 +452,14 @@ extern "C" int smarl_collision_rollout(const SmarlCollisionParams* p, const Smar
   a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma; a.n_envs = n_envs;
   a.ld = ld; a.size = (double)p->size; a.agents_size = p->agents_size; a.L = p->n_landmarks;
   a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
-  const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
-  if (int rc = launch_collision_rollout(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
+  unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
+  if (const int lanes = collision_coop_lanes(p->n_agents, p->n_landmarks, ld)) {
+    const int64_t envs_per_cta = kCollThreads / lanes;     // the cooperative kernels run 128 / lanes envs per CTA
+    grid = (unsigned)((n_envs + envs_per_cta - 1) / envs_per_cta);
+    if (int rc = launch_collision_coop_rollout(p->n_agents, lanes, a, (cudaStream_t)stream)) return rc;
+  } else if (int rc = launch_collision_rollout(p->n_agents, a, grid, (cudaStream_t)stream)) {
+    return rc;
+  }
   if (stats)
     return launch_stats_finalize(stats_scratch, grid, p->n_agents, 1, n_envs, stats, (cudaStream_t)stream);
   return SMARL_OK;

@@ -34,6 +34,9 @@ void set_error(const char* fmt, ...);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// smarl_set_kernel_variant's current setting for an env kind (-1 = automatic).
+int kernel_variant(int env_kind);
+
 // Checks the shared layout contract of smarl.h for one call.
 int check_layout(int64_t n_envs, int64_t ld);
 

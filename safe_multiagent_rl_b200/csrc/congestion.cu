@@ -33,6 +33,8 @@ struct CongestionStepArgs {
   int64_t ld;
   int32_t size;
   int32_t t;
+  uint32_t episode;
+  const uint32_t* episode_dev;
 };
 
 constexpr int kCongThreads = 128;
@@ -92,6 +94,8 @@ struct CongestionRolloutArgs {
   int32_t size;
   int32_t n_steps;
   int32_t g_mode;
+  uint32_t episode;
+  const uint32_t* episode_dev;
 };
 
 constexpr int kCongRollThreads = 64;
@@ -126,7 +130,8 @@ __global__ void __launch_bounds__(kCongThreads, cong_step_min_blocks(A)) congest
     }
   }
   if (MODE == 2)
-    congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + (int64_t)g * 4, (uint32_t)a.t);
+    congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + (int64_t)g * 4, (uint32_t)a.t,
+                              a.episode + (a.episode_dev ? __ldg(a.episode_dev) : 0u));
 
   uint32_t dcw[A];
   congestion_transition<A>(xw, yw, mw, dcw, (uint32_t)a.size * 0x01010101u);
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
   const int W = a.size + 1;
   const uint32_t size4 = (uint32_t)a.size * 0x01010101u;
   const double lam = a.lambdas ? __ldg(a.lambdas) : 0.0;
+  const uint32_t episode = a.episode + ((MODE == 2 && a.episode_dev) ? __ldg(a.episode_dev) : 0u);
 
   uint32_t xw[A], yw[A];
 #pragma unroll
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
         if (MODE == 0) mw[i] = aw[i];
       }
     }
-    if (MODE == 2) congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + e0, (uint32_t)t);
+    if (MODE == 2) congestion_noise_moves<A>(aw, mw, a.seed, a.keep_threshold, a.env_offset + e0, (uint32_t)t, episode);
     uint32_t dcw[A], conw[A];
     congestion_transition<A>(xw, yw, mw, dcw, size4);
     const uint32_t org = congestion_classes<A, kSimdClassAgentsRollout>(xw, yw, dcw, aw, conw);
@@ -414,6 +420,7 @@ extern "C" int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* po
   a.reward = reward; a.cost = cost; a.done = done; a.lambdas = lambdas; a.penalty = penalty;
   a.demand = p->demand; a.wait_reward = p->wait_reward; a.keep_threshold = p->keep_threshold; a.seed = p->seed;
   a.env_offset = p->env_offset; a.n_groups = (n_envs + 3) / 4; a.ld = ld; a.size = p->size; a.t = t;
+  a.episode = p->episode; a.episode_dev = p->episode_dev;
   const unsigned grid = (unsigned)((a.n_groups + kCongThreads - 1) / kCongThreads);
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = launch_congestion_step(p->noise_mode, p->n_agents, a, grid, s)) return rc;
@@ -450,6 +457,7 @@ extern "C" int smarl_congestion_rollout(const SmarlCongestionParams* p, const Sm
   a.seed = p->seed;
   a.env_offset = p->env_offset; a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
   a.size = p->size; a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
+  a.episode = p->episode; a.episode_dev = p->episode_dev;
   const unsigned grid = (unsigned)((a.n_groups + kCongRollThreads - 1) / kCongRollThreads);
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = launch_congestion_rollout(p->noise_mode, p->n_agents, a, grid, s)) return rc;

@@ -11,16 +11,17 @@ namespace smarl {
 #define SMARL_CONGESTION_COST 2.0
 
 // Effective (post-noise) moves of four envs for every agent, from Philox4x32-10:
-//   counter = (env_id lo, env_id hi, t, agent >> 2), key = seed; agent a reads word w = out[a & 3];
+//   counter = (env_id lo, env_id hi, t, agent >> 2 | episode << 3), key = seed; agent a reads word w = out[a & 3];
 //   move = action if w < keep_threshold else w mod 5,
 // the integer form of congestion.py:64-67 (u1 < 1 - noise ? a : int(u2 * 5)) with u1 = w * 2^-32 and
 // u2 = (w mod 5 + 0.5) / 5.  Given w >= keep_threshold, w mod 5 is uniform on 0..4 up to one count in
 // 2^32 per outcome -- the same resolution as drawing a second 32-bit word -- so one generator call serves
-// four agents.
+// four agents.  The episode index (low 29 bits) sits above the agent-quad index, so every episode of every
+// env draws a fresh realisation, as the reference's random() does (congestion.py:64-67).
 template <int A>
 __device__ __forceinline__ void congestion_noise_moves(const uint32_t (&aw)[A], uint32_t (&mw)[A],
                                                        uint64_t seed, uint64_t keep_threshold,
-                                                       int64_t env0, uint32_t t) {
+                                                       int64_t env0, uint32_t t, uint32_t episode) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
   for (int i = 0; i < A; ++i) mw[i] = 0u;
@@ -29,7 +30,7 @@ __device__ __forceinline__ void congestion_noise_moves(const uint32_t (&aw)[A], 
     const uint64_t id = (uint64_t)(env0 + k);
 #pragma unroll
     for (int j = 0; j < (A + 3) / 4; ++j) {
-      const uint4 o = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), t, (uint32_t)j), key);
+      const uint4 o = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), t, (uint32_t)j | (episode << 3)), key);
       const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

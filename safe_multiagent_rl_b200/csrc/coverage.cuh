@@ -6,7 +6,8 @@ namespace smarl {
 
 // Coverage grids are limited to size <= 127 so that doubled coordinates fit a byte (see
 // coverage_pack2).  Largest penalty table kept in shared memory (entries): fv^2 <= this.
-constexpr int kCoverageMaxLut = 12287;
+// (the fused rollout kernel keeps a 32-byte static reduction buffer beside the table: (12279 + 1) * 4 + 32 = 48 KB)
+constexpr int kCoverageMaxLut = 12279;
 
 // Agents of env lane k packed for the pair loop: p[a] = (2x | 2y << 8), upper bytes zero.
 // One PRMT gathers (x_k, y_k) and zero-fills bytes 2,3 by replicating the (clear) sign bit of

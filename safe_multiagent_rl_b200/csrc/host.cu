@@ -406,6 +406,7 @@ extern "C" int smarl_host_congestion_rollout(SmarlHostSession* s, const SmarlCon
   if (int rc = upload_small(s, lambdas_h, acc->thresholds, 1)) return rc;
   if (moves_h && !s->d_moves) SMARL_CUDA(cudaMalloc(&s->d_moves, (size_t)T * A * ld));
   SmarlCongestionParams dp = *p;
+  dp.episode_dev = nullptr;                 // host callers pass the episode by value
   dp.demand = s->d_demand;
   dp.wait_reward = nullptr;             // host callers pass the demand table only; the kernel divides
   SmarlAccounting dacc = *acc;
@@ -490,6 +491,7 @@ extern "C" int smarl_host_congestion_rollout_envmajor(SmarlHostSession* s, const
   if (int rc = upload_small(s, lambdas_h, acc->thresholds, 1)) return rc;
   if (moves_h && !s->d_moves) SMARL_CUDA(cudaMalloc(&s->d_moves, (size_t)T * A * ld));
   SmarlCongestionParams dp = *p;
+  dp.episode_dev = nullptr;                 // host callers pass the episode by value
   dp.demand = s->d_demand;
   dp.wait_reward = nullptr;
   SmarlAccounting dacc = *acc;

@@ -20,6 +20,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_variant[3] = {-1, -1, -1};
+int kernel_variant(int env_kind) { return (env_kind >= 0 && env_kind < 3) ? g_variant[env_kind] : -1; }
+
 int check_layout(int64_t n_envs, int64_t ld) {
   SMARL_REQUIRE(n_envs >= 1, "n_envs=%lld must be >= 1", (long long)n_envs);
   SMARL_REQUIRE(ld >= n_envs && ld % 16 == 0, "ld=%lld must be a multiple of 16 and >= n_envs=%lld",
@@ -284,6 +287,14 @@ __global__ void __launch_bounds__(kAccThreads) returns_shared_kernel(const Retur
     //   sum x = w S_r - S_p,   sum x^2 = w^2 S_rr - 2 w S_rp + S_pp.
     double s_r[4] = {0, 0, 0, 0}, s_p[4] = {0, 0, 0, 0}, s_rr[4] = {0, 0, 0, 0}, s_rp[4] = {0, 0, 0, 0},
            s_pp[4] = {0, 0, 0, 0};
+    // episodes that ended early (Collision, main.py:51) standardise over their own T' steps; later steps get 0
+    int n_act[4] = {T, T, T, T};
+    if (a.n_active) {
+      int c[4];
+      CostVec<int32_t>::load(a.n_active + e0, c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) n_act[k] = min(max(c[k], 0), T);
+    }
     for (int t = T - 1; t >= 0; --t) {
       const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -293,14 +304,15 @@ __global__ void __launch_bounds__(kAccThreads) returns_shared_kernel(const Retur
       for (int k = 0; k < 4; ++k) {
         g_rew[k] = (double)rr[k] + gamma * g_rew[k];
         g_pen[k] = (double)pp[k] + gamma * g_pen[k];
-        s_r[k] += g_rew[k];
-        s_p[k] += g_pen[k];
-        s_rr[k] += g_rew[k] * g_rew[k];
-        s_rp[k] += g_rew[k] * g_pen[k];
-        s_pp[k] += g_pen[k] * g_pen[k];
+        if (t < n_act[k]) {
+          s_r[k] += g_rew[k];
+          s_p[k] += g_pen[k];
+          s_rr[k] += g_rew[k] * g_rew[k];
+          s_rp[k] += g_rew[k] * g_pen[k];
+          s_pp[k] += g_pen[k] * g_pen[k];
+        }
       }
     }
-    const double n = (double)T;
     double h_rew[4] = {0, 0, 0, 0}, h_pen[4] = {0, 0, 0, 0};
     for (int t = T - 1; t >= 0; --t) {
       const float4 r = ld_stream_f4(a.reward + (int64_t)t * ld + e0);
@@ -318,12 +330,13 @@ __global__ void __launch_bounds__(kAccThreads) returns_shared_kernel(const Retur
           float o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            const double n = (double)n_act[k];
             const double mean = (w * s_r[k] - s_p[k]) / n;
             const double sq = w * w * s_rr[k] - 2.0 * w * s_rp[k] + s_pp[k];
             const double var = (sq - n * mean * mean) / (n - 1.0);
             double inv = 1.0 / (sqrt(fmax(var, 0.0)) + 1e-7);
-            if (T < 2) inv = __longlong_as_double(0x7ff8000000000000ll);   // torch: std of one sample is nan
-            o[k] = (float)(((w * h_rew[k] - h_pen[k]) - mean) * inv);
+            if (n_act[k] < 2) inv = __longlong_as_double(0x7ff8000000000000ll);   // torch: std of one sample is nan
+            o[k] = t < n_act[k] ? (float)(((w * h_rew[k] - h_pen[k]) - mean) * inv) : 0.f;
           }
           st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0, make_float4(o[0], o[1], o[2], o[3]));
         }
@@ -445,6 +458,13 @@ using namespace smarl;
 extern "C" int smarl_abi_version(void) { return SMARL_ABI_VERSION; }
 extern "C" const char* smarl_last_error(void) { return g_error; }
 
+extern "C" int smarl_set_kernel_variant(int32_t env_kind, int32_t lanes) {
+  if (env_kind < 0 || env_kind >= 3) return -1;
+  const int prev = g_variant[env_kind];
+  g_variant[env_kind] = (lanes == 0 || lanes == 2 || lanes == 4) ? lanes : -1;
+  return prev;
+}
+
 extern "C" int smarl_device_info(int* sm, int* major, int* minor) {
   int dev = 0;
   SMARL_CUDA(cudaGetDevice(&dev));
@@ -459,8 +479,8 @@ extern "C" int32_t smarl_stats_len(int32_t n_agents, int32_t n_constraints) {
 }
 
 extern "C" int64_t smarl_stats_scratch_len(int32_t n_agents, int32_t n_constraints, int64_t n_envs) {
-  // one row of block partials per CTA; the smallest CTA any producer uses covers 64 envs
-  const int64_t n_chunks = (n_envs + 63) / 64;
+  // one row of block partials per CTA; the smallest CTA any producer uses covers 32 envs (cooperative kernels, 4 lanes per env)
+  const int64_t n_chunks = (n_envs + 31) / 32;
   return n_chunks * stats_len(n_agents, n_constraints);
 }
 
@@ -542,7 +562,8 @@ extern "C" int smarl_rollout_returns(const SmarlAccounting* acc, const float* re
 
 extern "C" int smarl_rollout_returns_shared(const SmarlAccounting* acc, const float* reward_env,
                                             const float* weights, const void* cost, int32_t cost_dtype,
-                                            const float* penalty, float* R, float* modR, int32_t* C, float* G,
+                                            const float* penalty, const int32_t* n_active, float* R, float* modR,
+                                            int32_t* C, float* G,
                                             double* stats, double* stats_scratch, int32_t n_agents,
                                             int32_t n_constraints, int64_t n_envs, int64_t ld,
                                             smarl_stream_t stream) {
@@ -559,7 +580,7 @@ extern "C" int smarl_rollout_returns_shared(const SmarlAccounting* acc, const fl
   SMARL_REQUIRE(aligned16(reward_env) && aligned16(cost) && aligned16(penalty) && aligned16(R) && aligned16(modR) &&
                     aligned16(C) && aligned16(G), "pointers must be 16-byte aligned");
   ReturnsArgs a;
-  a.reward = reward_env; a.cost = cost; a.penalty = penalty; a.n_active = nullptr; a.R = R; a.modR = modR; a.C = C;
+  a.reward = reward_env; a.cost = cost; a.penalty = penalty; a.n_active = n_active; a.R = R; a.modR = modR; a.C = C;
   a.G = G; a.partials = stats_scratch; a.thresholds = acc->thresholds; a.gamma = acc->gamma;
   a.n_groups = (n_envs + 3) / 4; a.n_envs = n_envs; a.ld = ld;
   a.A = n_agents; a.K = n_constraints; a.T = acc->n_steps; a.g_mode = acc->g_mode;

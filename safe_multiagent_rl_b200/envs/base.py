@@ -33,6 +33,7 @@ class BatchedEnv:
         self.shuffle = False
         self.seed = 0
         self._episode = 0          # shuffle=True: index of the next episode's start draw
+        self.validate_actions = False   # True: also range-check discrete actions handed over as DEVICE tensors (syncs)
 
     # ---- buffers --------------------------------------------------------------------------------
     def _alloc(self, rows, dtype, lead=()):
@@ -52,6 +53,13 @@ class BatchedEnv:
             self.action_buffer.copy_(actions)
             return self.action_buffer
         a = torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
+        if self.action_dtype == torch.uint8 and (not a.is_cuda or self.validate_actions) and a.numel():
+            # the reference indexes its direction / cost tables with the action (coverage.py:176-196,
+            # congestion.py:55-69) and raises IndexError beyond them; the kernels' bit tricks would decode such a
+            # byte as some other move.  Host arrays are checked for free; device tensors only on request (a sync).
+            lo, hi = int(a.min()), int(a.max())
+            if lo < 0 or hi >= self.action_space:
+                raise IndexError(f"discrete action outside 0..{self.action_space - 1} (got {lo if lo < 0 else hi})")
         a = a.to(self.device)
         if not agent_major:                                   # reference orientation: [E, A(, 2)]
             a = a.reshape(self.n_envs, rows).t()
@@ -134,17 +142,21 @@ class BatchedEnv:
         o = out if out is not None else {}
 
         def buf(name, rows, dtype, lead=()):
-            if name not in o:
+            # a buffer reused from a caller's dict must fit THIS call (a longer T or another g_mode than the call that
+            # created it would let the kernels write past its end): wrong shape or dtype => allocate afresh
+            want = tuple(lead) + (rows, self.ld)
+            have = o.get(name)
+            if have is None or tuple(have.shape) != want or have.dtype != dtype:
                 o[name] = self._alloc(rows, dtype, lead)
             return o[name]
         buf("R_", A, torch.float32), buf("modR_", A, torch.float32)
         buf("C_", K, torch.float32 if self.cost_dtype == torch.float32 else torch.int32)
         o["G_"] = buf("G_buf", A, torch.float32, (T,)) if g_mode != G_NONE else None
         o["gs_"] = buf("g_scratch", 1, torch.float32, (g_scratch_rows,)) if g_mode == G_REWARD_TO_GO else None
-        if "stats_vec" not in o:
-            o["stats_vec"] = torch.zeros(self.lib.smarl_stats_len(A, K), dtype=torch.float64, device=dev)
-            o["stats_scratch"] = torch.zeros(self.lib.smarl_stats_scratch_len(A, K, E), dtype=torch.float64,
-                                             device=dev)
+        n_stats, n_scratch = self.lib.smarl_stats_len(A, K), self.lib.smarl_stats_scratch_len(A, K, E)
+        if o.get("stats_vec") is None or o["stats_vec"].numel() != n_stats or o["stats_scratch"].numel() < n_scratch:
+            o["stats_vec"] = torch.zeros(n_stats, dtype=torch.float64, device=dev)
+            o["stats_scratch"] = torch.zeros(n_scratch, dtype=torch.float64, device=dev)
         return o
 
     def _rollout_result(self, o):

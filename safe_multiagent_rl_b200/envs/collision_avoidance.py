@@ -110,7 +110,7 @@ class BatchedCollisionAvoidance(BatchedEnv):
         o = self._rollout_outputs(T, g_mode, out, 2 * T)
         if "n_active_" not in o:
             o["n_active_"] = self._alloc(1, torch.int32)
-        thr = device_thresholds(thresholds, dev)
+        thr = device_thresholds(thresholds, dev, self.n_constraints)
         acc = make_accounting(gamma, T, g_mode, thr)
         self._maybe_shuffle()
         _lib.check(self.lib.smarl_collision_rollout(

@@ -35,8 +35,11 @@ class BatchedCongestion(BatchedEnv):
                  input, defaulting to the reference's when it fits.
     noise        action noise (congestion.py:64-67).  The reference draws it from Python's unseeded
                  ``random``; here ``seed`` keys an on-device Philox4x32-10 stream indexed by the
-                 global env id, step and agent, or recorded effective moves can be replayed with
-                 ``step(actions, moves=...)``.
+                 global env id, episode, step and agent, or recorded effective moves can be replayed
+                 with ``step(actions, moves=...)``.  The episode index lives in a device scalar that
+                 every ``reset()`` / ``rollout()`` after the first advances, so consecutive episodes
+                 (and consecutive replays of a captured CUDA graph) draw independent noise like the
+                 reference's ``random()``; ``set_noise_episode(n)`` pins it.
     starts       optional ``[n_envs, n_agents, 2]``; default as the reference: agent 0 at (0,0),
                  others ``floor(rand(2) * size)`` from the global np.random stream (:215-217).
     """
@@ -92,11 +95,24 @@ class BatchedCongestion(BatchedEnv):
         self.done = self._alloc(A, torch.uint8)
         self.penalty = self._alloc(1, torch.float32)[0]
         self._recorded = None
+        self._episode_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # noise episode index (read as u32)
+        self._noise_started = False
 
     def _params(self, mode):
         return _lib.CongestionParams(self.size, self.n_agents, _lib.ptr(self._demand), mode, 0,
                                      keep_threshold(self.noise), self.seed & (2 ** 64 - 1), self.env_offset,
-                                     _lib.ptr(self._wait_reward))
+                                     _lib.ptr(self._wait_reward), _lib.ptr(self._episode_dev))
+
+    def set_noise_episode(self, n):
+        """The next ``reset()`` / ``rollout()`` draws the noise of episode ``n`` (then counting on from there)."""
+        self._episode_dev.fill_(int(n))
+        self._noise_started = False
+
+    def _next_noise_episode(self):
+        # a device-side increment: capturable, so every replay of a CUDA graph that contains this reset advances too
+        if self._noise_started:
+            self._episode_dev.add_(1)
+        self._noise_started = True
 
     def _draw_starts(self, episode):
         self._draw_grid_starts(episode, 1)        # agent 0 restarts at (0,0), congestion.py:215-216
@@ -106,6 +122,7 @@ class BatchedCongestion(BatchedEnv):
         return torch.stack([self.pos_x[:, :E].t(), self.pos_y[:, :E].t()], dim=-1)
 
     def _reset_impl(self):
+        self._next_noise_episode()
         _lib.check(self.lib.smarl_grid_reset(_lib.ptr(self.start_x), _lib.ptr(self.start_y),
                                              _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(self.obs),
                                              self.n_agents, self.n_envs, self.ld, _lib.stream_ptr()))
@@ -140,10 +157,11 @@ class BatchedCongestion(BatchedEnv):
             assert moves.dtype == torch.uint8 and tuple(moves.shape) == (T, A, self.ld) and moves.is_contiguous()
         mode = NOISE_RECORDED if moves is not None else (NOISE_PHILOX if self.noise > 0 else NOISE_NONE)
         o = self._rollout_outputs(T, g_mode, out, T)
-        thr = device_thresholds(thresholds, dev)
+        thr = device_thresholds(thresholds, dev, self.n_constraints)
         acc = make_accounting(gamma, T, g_mode, thr)
         p = self._params(mode)
         self._maybe_shuffle()
+        self._next_noise_episode()
         _lib.check(self.lib.smarl_congestion_rollout(
             C.byref(p), C.byref(acc), _lib.ptr(self.start_x), _lib.ptr(self.start_y), _lib.ptr(actions),
             _lib.ptr(moves), _lib.ptr(lambdas), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(o["R_"]),

@@ -12,6 +12,9 @@ from ..rollout import G_NONE, device_thresholds, make_accounting
 from .base import BatchedEnv
 
 
+MAX_LUT = 12279      # kCoverageMaxLut (csrc/coverage.cuh): the table + the rollout kernel's reduction buffer fill 48 KB
+
+
 def penalty_table(size, n_agents, fieldview_size=None):
     """(fv, table) with table[q] = (fv - sqrt(q))**2 for integer squared distances q whose
     distance is inside the field of view, truncated after the last non-zero entry.
@@ -61,7 +64,7 @@ class BatchedCoverageDiscrete(BatchedEnv):
         self.fieldview_size, table = penalty_table(self.size, A, fieldview_size)
         if A == 1:
             table = table[:0]
-        if len(table) > 12287:
+        if len(table) > MAX_LUT:
             raise NotImplementedError("fieldview_size > 110 needs a penalty table larger than shared memory")
         self.weights = None if weights is None else list(weights)
         if self.weights is not None and len(self.weights) < A:
@@ -126,7 +129,7 @@ class BatchedCoverageDiscrete(BatchedEnv):
         A, E, dev = self.n_agents, self.n_envs, self.device
         assert actions.dtype == torch.uint8 and tuple(actions.shape) == (T, A, self.ld) and actions.is_contiguous()
         o = self._rollout_outputs(T, g_mode, out, 2 * T)
-        thr = device_thresholds(thresholds, dev)
+        thr = device_thresholds(thresholds, dev, self.n_constraints)
         acc = make_accounting(gamma, T, g_mode, thr)
         self._maybe_shuffle()
         _lib.check(self.lib.smarl_coverage_rollout(

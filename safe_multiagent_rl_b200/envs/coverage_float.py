@@ -68,7 +68,7 @@ class _CoverageFloat(BatchedEnv):
         assert actions.dtype == self.action_dtype and tuple(actions.shape) == (T, self.action_rows, self.ld) \
             and actions.is_contiguous()
         o = self._rollout_outputs(T, g_mode, out, 2 * T)
-        thr = device_thresholds(thresholds, dev)
+        thr = device_thresholds(thresholds, dev, self.n_constraints)
         acc = make_accounting(gamma, T, g_mode, thr)
         self._maybe_shuffle()
         _lib.check(self.lib.smarl_coverage_float_rollout(

@@ -86,9 +86,10 @@ class HostRollout:
         return self._result(R, M, Cs, st)
 
     def congestion(self, size, starts, actions, demand_rate, noise=0.0, seed=0, env_offset=0, moves=None, lambdas=None,
-                   gamma=0.99, thresholds=None):
+                   gamma=0.99, thresholds=None, episode=0):
         """starts [E, A, 2] ints, actions (and recorded moves) [T, E, A] ints -> dict(R [E,A], modR [E,A], C [E,1], stats);
-        the arrays go to smarl_host_congestion_rollout_envmajor as they are."""
+        the arrays go to smarl_host_congestion_rollout_envmajor as they are.  ``episode`` indexes the Philox noise realisation
+        (pass a running episode counter to get fresh noise per call, as the reference's random() gives)."""
         A, E, T = self.A, self.E, self.T
         dem = np.ascontiguousarray(demand_rate, dtype=np.float64)
         assert dem.shape == (size + 1, size + 1)
@@ -102,7 +103,8 @@ class HostRollout:
         mode = 1 if moves is not None else (2 if noise > 0 else 0)
         R, M, Cs = np.empty((E, A), np.float32), np.empty((E, A), np.float32), np.empty((E, 1), np.int32)
         st = np.zeros(self.lib.smarl_stats_len(A, 1), np.float64)
-        p = _lib.CongestionParams(size, A, _p(dem), mode, 0, keep_threshold(noise), seed & (2 ** 64 - 1), env_offset, None)
+        p = _lib.CongestionParams(size, A, _p(dem), mode, int(episode) & 0x1FFFFFFF, keep_threshold(noise), seed & (2 ** 64 - 1),
+                                  env_offset, None, None)
         acc = _lib.Accounting(gamma, T, 0, _p(thr))
         _lib.check(self.lib.smarl_host_congestion_rollout_envmajor(self._sess, C.byref(p), C.byref(acc), _p(starts),
                                                                    _p(actions), _p(mv), _p(lam), _p(R), _p(M), _p(Cs), _p(st)))

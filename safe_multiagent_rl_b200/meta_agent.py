@@ -40,15 +40,32 @@ class BatchedMetaAgent:
         self.lib = _lib.load()
         self._acc = torch.zeros(self.lib.smarl_stats_len(self.A, self.K), dtype=torch.float64, device=self.device)
         self._recorded = False
+        self._pending = None       # compat path: per-env cost sums of the episode batch in flight, [E, K]
 
     def act(self, constraint, reward):
         """meta_agent.py:18-23 on tensors: ``[E, K]``, ``[E, A]`` -> modified reward ``[E, A]``.
-        (Compatibility path; the fused path never materialises this.)"""
-        pen = constraint.to(torch.float64) @ self.lambdas
+        (Compatibility path; the fused path never materialises this.)  Like the reference, the step's
+        constraints are recorded while the gate ``learning_cycle >= start_learning_cycle`` is open
+        (meta_agent.py:19-20); a following ``step()`` without arguments folds them into the episode sums."""
+        c = constraint.to(torch.float64)
+        if self.learning_cycle >= self.start_learning_cycle:
+            self._pending = c.clone() if self._pending is None else self._pending + c
+        pen = c @ self.lambdas
         return reward.to(torch.float64) - pen[:, None]
 
-    def step(self, stats):
-        """Record a finished batch of episodes (its stats vector) if the gate is open."""
+    def step(self, stats=None):
+        """End of an episode batch (meta_agent.py:25-30).  With ``stats`` (the vector of a finished batch from
+        RolloutBuffer.finish / env.rollout) it is recorded if the gate is open; without, the constraints that
+        ``act`` recorded since the last call become one episode per env (nothing recorded -> no-op, :26-27)."""
+        if stats is None:
+            if self._pending is not None:
+                K, A = self.K, self.A
+                self._acc[:K] += self._pending.sum(0)                       # sum_e sum_t c[t, e, k]
+                self._acc[K:2 * K] += (self._pending > self.thresholds).to(torch.float64).sum(0)
+                self._acc[2 * K + 2 * A] += self._pending.shape[0]          # episodes
+                self._pending = None
+                self._recorded = True
+            return
         if self.learning_cycle >= self.start_learning_cycle:
             vec = stats.vec if hasattr(stats, "vec") else stats
             self._acc += vec
@@ -70,6 +87,7 @@ class BatchedMetaAgent:
         self.lr = self.lr / self.decay
         self._acc.zero_()
         self._recorded = False
+        self._pending = None
         self.learning_cycle = 0
 
     def increment_learning_cycle(self):

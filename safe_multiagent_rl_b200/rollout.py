@@ -50,11 +50,16 @@ class Stats:
 _THR_CACHE = {}
 
 
-def device_thresholds(thresholds, device):
+def device_thresholds(thresholds, device, n_constraints=None):
     """f64 device tensor for a thresholds list; cached by value so repeated calls (and calls made
-    while a CUDA graph is being captured, after one warm-up call) do no host->device copy."""
+    while a CUDA graph is being captured, after one warm-up call) do no host->device copy.
+    ``n_constraints``: the kernels read exactly K thresholds, so any other count is rejected (the reference's
+    CLI default ``[2]`` with CoverageDiscrete's K = n_agents would otherwise be read out of bounds)."""
     if thresholds is None:
         return None
+    n = thresholds.numel() if isinstance(thresholds, torch.Tensor) else np.asarray(thresholds).size
+    if n_constraints is not None and n != n_constraints:
+        raise ValueError(f"need one threshold per constraint: got {n}, the env has {n_constraints}")
     if isinstance(thresholds, torch.Tensor) and thresholds.is_cuda and thresholds.dtype == torch.float64:
         return thresholds
     key = (str(device), tuple(float(x) for x in np.asarray(
@@ -134,12 +139,12 @@ class RolloutBuffer:
         g_mode = self.g_mode if g_mode is None else g_mode
         if g_mode != G_NONE and self.G is None:
             raise ValueError("buffer was created without G storage")
-        thr = device_thresholds(thresholds, self.device)
+        thr = device_thresholds(thresholds, self.device, self.K)
         acc = make_accounting(gamma, self.T, g_mode, thr)
         if self.shared_reward:
             _lib.check(lib.smarl_rollout_returns_shared(
                 C.byref(acc), _lib.ptr(self.reward), _lib.ptr(self.weights), _lib.ptr(self.cost), self.cost_code,
-                _lib.ptr(self.penalty), _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum),
+                _lib.ptr(self.penalty), _lib.ptr(n_active), _lib.ptr(self.R), _lib.ptr(self.modR), _lib.ptr(self.Csum),
                 _lib.ptr(self.G if g_mode else None), _lib.ptr(self.stats_vec), _lib.ptr(self.stats_scratch), self.A,
                 self.K, self.E, self.ld, _lib.stream_ptr()))
             return dict(R=env_major(self.R, self.E), modR=env_major(self.modR, self.E), C=env_major(self.Csum, self.E),

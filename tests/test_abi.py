@@ -47,7 +47,7 @@ def test_abi_struct_sizes():
     from safe_multiagent_rl_b200 import _lib
     assert C.sizeof(_lib.CoverageParams) == 32
     assert C.sizeof(_lib.Accounting) == 24
-    assert C.sizeof(_lib.CongestionParams) == 56
+    assert C.sizeof(_lib.CongestionParams) == 64      # ABI v2: + episode_dev
     assert C.sizeof(_lib.CollisionParams) == 32
 
 
@@ -67,7 +67,7 @@ def test_validation_errors_before_any_cuda_work(lib):
     with pytest.raises(_lib.SmarlError):
         _lib.check(rc)
     assert lib.smarl_stats_len(16, 16) == 65
-    assert lib.smarl_stats_scratch_len(3, 3, 50) == 13
+    assert lib.smarl_stats_scratch_len(3, 3, 50) == 26      # one row of partials per 32 envs
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -79,7 +79,7 @@ def test_coverage_step_rollout_returns_stay_in_bounds(A, E):
                                            P(cost[t * A:]), None, P(lam), P(pen[t:]), E, ld, st))
     for g_mode in (0, 1, 2):
         acc = _lib.Accounting(0.99, T, g_mode, P(thr))
-        _lib.check(lib.smarl_rollout_returns_shared(C.byref(acc), P(renv), P(w), P(cost), 0, P(pen), P(R), P(M), P(Cs),
+        _lib.check(lib.smarl_rollout_returns_shared(C.byref(acc), P(renv), P(w), P(cost), 0, P(pen), None, P(R), P(M), P(Cs),
                                                     P(G) if g_mode else None, P(stats), P(scratch), A, A, E, ld, st))
     _lib.check(lib.smarl_lambda_update(P(lam), P(stats), P(thr), 0.01, A, A, st))
     torch.cuda.synchronize()
@@ -113,7 +113,7 @@ def test_congestion_and_collision_stay_in_bounds(A, E):
     scratch = ar.make(1, max(1, lib.smarl_stats_scratch_len(A, 1, E)), f64)
     _lib.check(lib.smarl_grid_reset(P(sx), P(sy), P(px), P(py), P(obs), A, E, ld, st))
     for mode in (0, 2, 1):
-        cp = _lib.CongestionParams(S, A, P(dem), mode, 0, 3865470567, 7, 123456789012, None)
+        cp = _lib.CongestionParams(S, A, P(dem), mode, 0, 3865470567, 7, 123456789012, None, None)
         _lib.check(lib.smarl_congestion_step(C.byref(cp), P(px), P(py), P(acts), P(mv), P(obs), P(rew), P(cost), P(done),
                                              P(lam), P(pen), 3, E, ld, st))
         for g_mode in (0, 1, 2):

@@ -1,0 +1,58 @@
+"""Lane-cooperative kernels (one env split over 2 / 4 lanes of a warp, csrc/*_coop.cu) against the
+oracle: the parity checks of test_gpu_parity.py re-run with every thread mapping forced through
+smarl_set_kernel_variant, over agent counts that do and do not divide by the lane count (padding
+agents), ragged env counts and both step-API and fused-rollout kernels.  Same bars as the base tests:
+integer / f64 state bit-exact, f32 sums within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import test_gpu_parity as tp
+from safe_multiagent_rl_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+AGENTS = [9, 12, 13, 16, 17, 22, 24, 27, 30, 31, 32]
+
+
+@pytest.mark.parametrize("lanes", [2, 4])
+@pytest.mark.parametrize("A", AGENTS)
+def test_collision_coop_step(lanes, A):
+    with _lib.kernel_variant(_lib.ENV_COLLISION, lanes):
+        tp.test_collision_step_matches_oracle(3 + A % 4, A, 1 + A % 3, 70 + A, 10, 100 + A)
+
+
+@pytest.mark.parametrize("lanes", [2, 4])
+@pytest.mark.parametrize("A", AGENTS)
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+def test_collision_coop_rollout(lanes, A, g_mode):
+    with _lib.kernel_variant(_lib.ENV_COLLISION, lanes):
+        tp.test_collision_fused_rollout(3 + A % 4, A, 1 + A % 3, 70 + A, 12, 200 + A, g_mode)
+
+
+@pytest.mark.parametrize("lanes", [0, 2, 4])
+def test_collision_variants_agree_on_large_fields(lanes):
+    """Coordinates up to 200 through the f32 screen, tiny agents (the screen margin scales with the field)."""
+    s = tp.smarl()
+    size, A, L, E, T = 200, 16, 2, 333, 6
+    rng = np.random.default_rng(7)
+    starts = rng.random((E, A, 2)) * size
+    starts[:, 1::2] = starts[:, 0::2] + rng.normal(0, 0.004, size=(E, A // 2, 2))      # pairs right at the collision distance
+    starts = np.clip(starts, 0, size)
+    landmarks = rng.random((E, L, 2)) * size
+    actions = rng.normal(0, 0.002, size=(T, E, A, 2)).astype(np.float32)
+    with _lib.kernel_variant(_lib.ENV_COLLISION, lanes):
+        env = s.BatchedCollisionAvoidance(size, A, n_envs=E, n_landmarks=L, starts=starts, landmarks=landmarks,
+                                          agents_size=0.002)
+        env.reset()
+        pos, done = starts.copy(), np.zeros((E, A), dtype=bool)
+        total = 0
+        for t in range(T):
+            _, r, c, d = env.step(actions[t])
+            pos, r_o, c_o, done, _ = tp.no.collision_step(pos, done, actions[t].astype(np.float64), landmarks, size,
+                                                          agents_size=0.002)
+            assert np.array_equal(env.state().cpu().numpy(), pos)
+            assert np.array_equal(c.cpu().numpy(), c_o.astype(np.int64))
+            assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))
+            total += int(c_o.sum())
+        assert total > 0

@@ -126,7 +126,7 @@ def test_host_agent_major_entries_equal_env_major():
         R, M = np.zeros((A, ld), np.float32), np.zeros((A, ld), np.float32)
         Cs, st = np.zeros((1, ld), np.int32), np.zeros(h.lib.smarl_stats_len(A, 1))
         dem, lam, thr = np.ascontiguousarray(demand), np.array([0.4]), np.array([2.0])
-        p = _lib.CongestionParams(size, A, _p(dem), 1 if mv is not None else 2, 0, keep_threshold(noise), seed, off, None)
+        p = _lib.CongestionParams(size, A, _p(dem), 1 if mv is not None else 2, 0, keep_threshold(noise), seed, off, None, None)
         acc = _lib.Accounting(gamma, T, 0, _p(thr))
         _lib.check(h.lib.smarl_host_congestion_rollout(h._sess, C.byref(p), C.byref(acc), _p(sx), _p(sy), _p(act), _p(mva),
                                                        _p(lam), _p(R), _p(M), _p(Cs), _p(st)))
