@@ -13,30 +13,6 @@
 
 namespace smarl {
 
-struct CongestionStepArgs {
-  uint8_t* pos_x;
-  uint8_t* pos_y;
-  const uint8_t* actions;
-  uint8_t* moves;
-  float* obs;
-  float* reward;
-  int32_t* cost;
-  uint8_t* done;
-  const double* lambdas;
-  float* penalty;
-  const double* demand;
-  const float* wait_reward;
-  uint64_t keep_threshold;
-  uint64_t seed;
-  int64_t env_offset;
-  int64_t n_groups;
-  int64_t ld;
-  int32_t size;
-  int32_t t;
-  uint32_t episode;
-  const uint32_t* episode_dev;
-};
-
 constexpr int kCongThreads = 128;
 // Both Congestion kernels are issue / latency-bound, so up to 8 agents the register budget is capped for more
 // resident CTAs: 80 per thread in the step kernel (6 CTAs of 128; with the byte-SIMD class counting a tighter cap
@@ -356,7 +332,7 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
     const size_t smem = sizeof(double) * 4 * kCongRollThreads * (size_t)A;                                   \
     SMARL_DISPATCH_A(A, {                                                                                    \
       auto kern = congestion_rollout_kernel<kA, M>;                                                          \
-      if (smem > 48 * 1024)                                                                                  \
+      if (smem + 64 > 48 * 1024)   /* + the static reduction buffer */                                       \
         SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
       kern<<<grid, kCongRollThreads, smem, s>>>(a);                                                          \
     });                                                                                                      \
@@ -382,6 +358,15 @@ static int launch_congestion_step(int mode, int A, const CongestionStepArgs& a, 
 static int launch_congestion_rollout(int mode, int A, const CongestionRolloutArgs& a, unsigned grid, cudaStream_t s) {
   return mode == 0 ? launch_congestion_rollout_m0(A, a, grid, s)
        : mode == 1 ? launch_congestion_rollout_m1(A, a, grid, s) : launch_congestion_rollout_m2(A, a, grid, s);
+}
+
+// Lanes per env quad of the step kernel: 0 = one thread per four envs (this file), 2 / 4 = lane-cooperative
+// scan kernel (congestion_coop.cu).  Crossover measured on B200 (profiles/r02); smarl_set_kernel_variant overrides.
+static int congestion_coop_lanes(int A) {
+  if (A < 9) return 0;
+  const int forced = kernel_variant(SMARL_ENV_CONGESTION);
+  if (forced >= 0) return forced;
+  return A >= 12 ? 4 : 0;       // closed loop, of the HBM peak: A = 12 0.63 -> 0.68, 16 0.56 -> 0.65, 20 0.38 -> 0.60, 32 0.30 -> 0.48
 }
 
 static int check_congestion(const SmarlCongestionParams* p) {
@@ -423,6 +408,11 @@ extern "C" int smarl_congestion_step(const SmarlCongestionParams* p, uint8_t* po
   a.episode = p->episode; a.episode_dev = p->episode_dev;
   const unsigned grid = (unsigned)((a.n_groups + kCongThreads - 1) / kCongThreads);
   cudaStream_t s = (cudaStream_t)stream;
+  if (const int lanes = congestion_coop_lanes(p->n_agents)) {
+    return p->noise_mode == 0 ? launch_congestion_coop_step_m0(p->n_agents, lanes, a, s)
+         : p->noise_mode == 1 ? launch_congestion_coop_step_m1(p->n_agents, lanes, a, s)
+                              : launch_congestion_coop_step_m2(p->n_agents, lanes, a, s);
+  }
   if (int rc = launch_congestion_step(p->noise_mode, p->n_agents, a, grid, s)) return rc;
   return SMARL_OK;
 }

@@ -166,6 +166,34 @@ __device__ __forceinline__ uint32_t congestion_classes(const uint32_t (&xw)[A], 
   }
 }
 
+struct CongestionStepArgs {
+  uint8_t* pos_x;
+  uint8_t* pos_y;
+  const uint8_t* actions;
+  uint8_t* moves;
+  float* obs;
+  float* reward;
+  int32_t* cost;
+  uint8_t* done;
+  const double* lambdas;
+  float* penalty;
+  const double* demand;
+  const float* wait_reward;
+  uint64_t keep_threshold;
+  uint64_t seed;
+  int64_t env_offset;
+  int64_t n_groups;
+  int64_t ld;
+  int32_t size;
+  int32_t t;
+  uint32_t episode;
+  const uint32_t* episode_dev;
+};
+
+int launch_congestion_coop_step_m0(int A, int S, const CongestionStepArgs& a, cudaStream_t st);
+int launch_congestion_coop_step_m1(int A, int S, const CongestionStepArgs& a, cudaStream_t st);
+int launch_congestion_coop_step_m2(int A, int S, const CongestionStepArgs& a, cudaStream_t st);
+
 // Waiting-branch reward in f64, the reference's operation order (congestion.py:86-87).
 __device__ __forceinline__ double congestion_reward_f64(uint32_t con, uint32_t nx, uint32_t ny,
                                                         const double* __restrict__ demand, int W) {

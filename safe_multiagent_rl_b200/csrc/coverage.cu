@@ -77,6 +77,10 @@ struct CoverageRolloutArgs {
 constexpr int kRolloutThreads = 128;
 
 int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaStream_t s);
+int launch_coverage_coop_step(int A, int S, uint8_t* pos_x, uint8_t* pos_y, const uint8_t* actions, float* obs,
+                              float* reward, uint8_t* cost, uint8_t* done, const double* lambdas, float* penalty,
+                              const float* lut, const float* weights, int64_t n_groups, int64_t ld, int size,
+                              int lut_len, int reward_rows, cudaStream_t st);
 int launch_coverage_rollout(int A, const CoverageRolloutArgs& a, unsigned grid, cudaStream_t s);
 
 #if SMARL_TU_IS(0)
@@ -366,6 +370,15 @@ __global__ void grid_reset_kernel(const uint8_t* __restrict__ start_x, const uin
 // ---------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------
+// Lanes per env quad of the step kernel: 0 = one thread per four envs (this file), 2 / 4 = lane-cooperative
+// kernel (coverage_coop.cu).  Crossover measured on B200 (profiles/r02); smarl_set_kernel_variant overrides it.
+static int coverage_coop_lanes(int A) {
+  if (A < 9) return 0;
+  const int forced = kernel_variant(SMARL_ENV_COVERAGE);
+  if (forced >= 0) return forced;
+  return A >= 22 ? 2 : 0;       // A = 20: 0.76 vs 0.75 (tie), A = 24: 0.66 -> 0.71, A = 32: 0.58 -> 0.65 of the HBM peak, closed loop
+}
+
 static int check_coverage(const SmarlCoverageParams* p) {
   SMARL_REQUIRE(p != nullptr, "params is NULL");
   SMARL_REQUIRE(p->size >= 1 && p->size <= 127, "size=%d outside 1..127", p->size);
@@ -427,6 +440,10 @@ extern "C" int smarl_coverage_step(const SmarlCoverageParams* p, uint8_t* pos_x,
     set_error("(2A+1)*ld = %lld exceeds 32-bit element offsets; split the env batch", (long long)((2 * p->n_agents + 1) * ld));
     return SMARL_EUNSUPPORTED;
   }
+  if (const int lanes = coverage_coop_lanes(p->n_agents))
+    return launch_coverage_coop_step(p->n_agents, lanes, pos_x, pos_y, actions, obs, reward, cost, done, lambdas, penalty,
+                                     p->lut, p->weights, a.n_groups, ld, p->size, p->lut_len, a.reward_rows,
+                                     (cudaStream_t)stream);
   const unsigned grid = (unsigned)((a.n_groups + kStepThreads - 1) / kStepThreads);
   if (int rc = launch_coverage_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
   return SMARL_OK;

@@ -56,3 +56,36 @@ def test_collision_variants_agree_on_large_fields(lanes):
             assert np.array_equal(r.cpu().numpy(), r_o.astype(np.float32))
             total += int(c_o.sum())
         assert total > 0
+
+
+# ----------------------------------------------------------------------------- Coverage
+@pytest.mark.parametrize("lanes", [2, 4])
+@pytest.mark.parametrize("A", AGENTS)
+def test_coverage_coop_step(lanes, A):
+    with _lib.kernel_variant(_lib.ENV_COVERAGE, lanes):
+        tp.test_coverage_step_matches_oracle(2 * A, A, 150 + A, 6, None, 300 + A)
+        tp.test_coverage_step_matches_oracle(3, A, 37, 5, 10.0, 400 + A)          # every pair overlaps, ragged E
+
+
+@pytest.mark.parametrize("lanes", [2, 4])
+@pytest.mark.parametrize("A", [12, 17, 32])
+def test_coverage_coop_closed_loop_and_lean_buffer(lanes, A):
+    with _lib.kernel_variant(_lib.ENV_COVERAGE, lanes):
+        tp.test_coverage_rollouts_match_oracle(2 * A, A, 120, 8, None, 500 + A, 1)   # closed loop vs fused vs oracle
+        tp.test_coverage_lean_rollout_buffer(2 * A, A, 120, 8, None, 600 + A, 1)     # reward_rows = 1 path
+
+
+# ----------------------------------------------------------------------------- Congestion
+@pytest.mark.parametrize("lanes", [2, 4])
+@pytest.mark.parametrize("A", AGENTS)
+@pytest.mark.parametrize("mode", ["philox", "recorded"])
+def test_congestion_coop_step(lanes, A, mode):
+    with _lib.kernel_variant(_lib.ENV_CONGESTION, lanes):
+        tp.test_congestion_step_matches_oracle(2 + A % 5, A, 90 + A, 8, 0.3, 700 + A, mode)   # tiny grids: heavy edge sharing
+
+
+@pytest.mark.parametrize("lanes", [2, 4])
+def test_congestion_coop_no_noise_and_closed_loop(lanes):
+    with _lib.kernel_variant(_lib.ENV_CONGESTION, lanes):
+        tp.test_congestion_step_matches_oracle(3, 16, 64, 10, 0.0, 0, "philox")    # noise 0: mode 0 kernel
+        tp.test_congestion_closed_loop_returns()
