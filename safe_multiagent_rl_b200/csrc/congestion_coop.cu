@@ -123,7 +123,7 @@ __device__ __forceinline__ float congestion_reward_coop(uint32_t act, uint32_t c
 }
 
 template <int A, int S, int MODE>
-__global__ void __launch_bounds__(kCongCoopThreads, (A > 24 ? 5 : 4)) congestion_coop_step_kernel(const CongestionStepArgs a) {
+__global__ void __launch_bounds__(kCongCoopThreads, 4) congestion_coop_step_kernel(const CongestionStepArgs a) {
   using C = CongCoop<A, S>;
   constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC, NQ = C::NQ;
   extern __shared__ uint4 s_rec[];                                 // [EPC][PQ]: Philox blocks (MODE 2), then the

@@ -104,7 +104,9 @@ class BatchedCongestion(BatchedEnv):
                                      _lib.ptr(self._wait_reward), _lib.ptr(self._episode_dev))
 
     def set_noise_episode(self, n):
-        """The next ``reset()`` / ``rollout()`` draws the noise of episode ``n`` (then counting on from there)."""
+        """The next ``reset()`` / ``rollout()`` draws the noise of episode ``n`` (then counting on from there).
+        A captured CUDA graph that contains the reset advances the device counter before it draws, so pin
+        ``n - 1`` before replaying it for episode ``n``."""
         self._episode_dev.fill_(int(n))
         self._noise_started = False
 

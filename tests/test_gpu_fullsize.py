@@ -81,6 +81,7 @@ def test_config3_congestion_10x10_8_agents_1M_envs():
     thr = [150.0]
     out = env.rollout_closed_loop(lambda obs, t: actions[t], T, lam, gamma, thresholds=thr)
     pos_closed = (env.pos_x.clone(), env.pos_y.clone())
+    env.set_noise_episode(0)            # replay episode 0's noise: a second episode would draw a fresh realisation
     fused = env.rollout(actions, lambdas=lam, gamma=gamma, thresholds=thr, g_mode=1)
     assert torch.equal(env.pos_x, pos_closed[0]) and torch.equal(env.pos_y, pos_closed[1])   # same Philox stream
     assert torch.equal(fused["C"], out["C"])

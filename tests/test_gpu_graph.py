@@ -47,6 +47,10 @@ def test_closed_loop_in_one_cuda_graph(env_name):
         closed()
     for buf_t in (buf.R, buf.modR, buf.Csum, buf.G, env.pos_x, env.pos_y):
         buf_t.zero_()
+    if env_name == "congestion":
+        # the captured reset advances the noise episode before it draws (fresh noise per replay, as the reference's
+        # random() gives); pin the counter one below to replay the eager episode 0
+        env.set_noise_episode(-1)
     graph.replay()
     torch.cuda.synchronize()
     got = dict(R=buf.R, modR=buf.modR, C=buf.Csum, G=buf.G)
