@@ -336,6 +336,26 @@ int smarl_lambda_update(double* lambdas, const double* stats, const double* thre
                         int32_t n_agents, int32_t n_constraints, smarl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Multi-GPU: env instances are independent (envs/coverage.py:19, congestion.py:22,
+ * collision_avoidance.py:60), so ranks own contiguous ranges of global env ids and the data path has no
+ * collective.  The only exchange is the sum of the stats vectors before MetaAgent.update
+ * (meta_agent.py:32-39, called once per meta cycle at main.py:65-68).  NCCL is loaded at run time
+ * (libnccl.so.2); single-GPU hosts never need it.
+ *   rank 0: smarl_comm_get_unique_id(id)  ->  ship the SMARL_COMM_ID_BYTES bytes to every rank by any means
+ *   all ranks, current device set: smarl_comm_init_from_unique_id(&comm, id, rank, world)   (collective)
+ *   per batch:  smarl_stats_allreduce(comm, stats, smarl_stats_len(A, K), stream)  then  smarl_lambda_update
+ * The all-reduce is enqueued on `stream` (no host sync, CUDA-graph capturable) and works in place.
+ * ---------------------------------------------------------------------------------- */
+#define SMARL_COMM_ID_BYTES 128
+typedef struct SmarlComm SmarlComm;   /* opaque: one NCCL communicator */
+int smarl_comm_get_unique_id(void* id_out /* [SMARL_COMM_ID_BYTES] host */);
+int smarl_comm_init_from_unique_id(SmarlComm** out, const void* id, int32_t rank, int32_t world_size);
+void smarl_comm_destroy(SmarlComm* comm);
+/* NCCL version code of the library in use (e.g. 22809), 0 if NCCL cannot be loaded. */
+int smarl_comm_nccl_version(void);
+int smarl_stats_allreduce(SmarlComm* comm, double* stats, int32_t n, smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Host-buffer entry points (what a host-side caller with numpy arrays binds).  Inputs are
  * HOST arrays (pageable, or pinned for full PCIe speed) in the same agent-major layout with
  * ld = smarl_host_session_ld(); the call pipelines env chunks over two streams (H2D copy,

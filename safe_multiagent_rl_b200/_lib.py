@@ -81,6 +81,11 @@ PROTOTYPES = {
     "smarl_rollout_returns_shared": (C.c_int, [P(Accounting), c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                                c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
+    "smarl_comm_get_unique_id": (C.c_int, [c_ptr]),
+    "smarl_comm_init_from_unique_id": (C.c_int, [P(c_ptr), c_ptr, i32, i32]),
+    "smarl_comm_destroy": (None, [c_ptr]),
+    "smarl_comm_nccl_version": (C.c_int, []),
+    "smarl_stats_allreduce": (C.c_int, [c_ptr, c_ptr, i32, c_ptr]),
     "smarl_host_session_create": (C.c_int, [P(c_ptr), i32, i32, i32, i64, i32]),
     "smarl_host_session_destroy": (None, [c_ptr]),
     "smarl_host_session_ld": (i64, [c_ptr]),

@@ -83,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {cmd[-3]}: " + r.stderr[-2000:])
     if jobs or not os.path.exists(LIB_PATH):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs]
+        cmd = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -57,10 +57,66 @@ def shard_range(n_envs_total: int, rank: int, world: int):
     return offset, count
 
 
-def allreduce_stats(vec: torch.Tensor, group=None) -> torch.Tensor:
+class StatsComm:
+    """The C-ABI communicator (include/smarl.h: smarl_comm_* / smarl_stats_allreduce): NCCL bound by libsmarl
+    itself, so the whole closed-loop batch -- steps, accounting, the all-reduce, the lambda update -- is one
+    capturable sequence of C-ABI calls and a host without PyTorch can shard the same way.  The 128-byte unique
+    id travels over whatever the caller has; here that is torch.distributed's existing process group."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes):
+        import ctypes as C
+
+        from . import _lib
+        self.lib, self.rank, self.world = _lib.load(), int(rank), int(world)
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _lib.check(self.lib.smarl_comm_init_from_unique_id(C.byref(self._h), buf, self.rank, self.world))
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        import ctypes as C
+
+        from . import _lib
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().smarl_comm_get_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_process_group(cls, group=None):
+        """Collective over ``group``: rank 0 creates the id, everyone joins.  Single-process runs get a
+        one-rank communicator (the all-reduce is then the identity, through the same code path)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            box = [cls.new_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            return cls(rank, world, box[0])
+        return cls(0, 1, cls.new_unique_id())
+
+    def allreduce(self, vec: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+        assert vec.is_cuda and vec.dtype == torch.float64 and vec.is_contiguous()
+        _lib.check(self.lib.smarl_stats_allreduce(self._h, vec.data_ptr(), vec.numel(), _lib.stream_ptr()))
+        return vec
+
+    def close(self):
+        if self._h:
+            self.lib.smarl_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def allreduce_stats(vec: torch.Tensor, group=None, comm: "StatsComm | None" = None) -> torch.Tensor:
     """Sum the additive stats vector over ranks (in place).  Every slot is a sum over envs
     (integer-valued cost sums / counts are exact in f64), so the result equals the
-    single-GPU vector over all envs."""
+    single-GPU vector over all envs.  With ``comm`` the reduction goes through the C ABI
+    (smarl_stats_allreduce), otherwise through torch.distributed."""
+    if comm is not None:
+        return comm.allreduce(vec)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     return vec

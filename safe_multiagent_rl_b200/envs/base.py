@@ -34,6 +34,9 @@ class BatchedEnv:
         self.seed = 0
         self._episode = 0          # shuffle=True: index of the next episode's start draw
         self.validate_actions = False   # True: also range-check discrete actions handed over as DEVICE tensors (syncs)
+        self.emit_obs = True            # False: the step kernels skip the float observation rows (8 of Coverage's 19
+                                        # bytes per agent-step); for consumers that read the u8 position rows pos_x /
+                                        # pos_y directly, e.g. a fused policy kernel.  env.step then returns obs=None.
 
     # ---- buffers --------------------------------------------------------------------------------
     def _alloc(self, rows, dtype, lead=()):
@@ -125,6 +128,8 @@ class BatchedEnv:
             done_v = self.__dict__.get("_done_zeros_v")
             if done_v is None:
                 done_v = self._done_zeros_v = env_major(self._zero_done(), self.n_envs)
+        if not self.emit_obs:
+            return None, reward_v, cost_v, done_v
         obs_v = self.__dict__.get("_obs_v")
         if obs_v is None:
             obs_v = self._obs_v = env_major(self.obs, self.n_envs)
@@ -166,16 +171,20 @@ class BatchedEnv:
                  G=None if o["G_"] is None else env_major(o["G_"], E), stats=Stats(o["stats_vec"], A, K))
         return o
 
-    def new_rollout_buffer(self, n_steps, g_mode=G_REWARD_TO_GO, lean=False):
-        """Device slabs for one batch of episodes.  ``lean=True`` (envs that support it) stores only what
-        the accounting needs: one env-reward row instead of n_agents weighted rows, and no per-step done
-        flags when agents never finish -- fewer HBM bytes per step; ``env.step`` then returns the
-        ``[E, 1]`` env reward and per-agent rewards are ``buffer.rewards()``."""
+    def new_rollout_buffer(self, n_steps, g_mode=G_REWARD_TO_GO, lean=False, store_done=None):
+        """Device slabs for one batch of episodes.  Envs whose agents never finish (check_done is constant
+        False: coverage.py:97-98, congestion.py:103-104) do not store per-step done flags unless
+        ``store_done=True``: ``env.step`` still returns the all-False done array (one cached zero view), but the
+        step kernel writes one byte per agent-step less.  ``lean=True`` (envs that support it) also replaces the
+        n_agents weighted reward rows by one env-reward row; ``env.step`` then returns the ``[E, 1]`` env reward
+        and per-agent rewards are ``buffer.rewards()``."""
         if lean and not getattr(self, "supports_lean", False):
             raise ValueError(f"{type(self).__name__} has no lean rollout buffer")
+        if store_done is None:
+            store_done = not getattr(self, "never_done", False)
         return RolloutBuffer(n_steps, self.n_agents, self.n_constraints, self.n_envs, self.cost_dtype,
                              self.device, g_mode, shared_reward=lean, weights=getattr(self, "_weights", None) if lean else None,
-                             store_done=not (lean and getattr(self, "never_done", False)))
+                             store_done=store_done)
 
     def rollout_closed_loop(self, policy, n_steps, lambdas, gamma, thresholds=None, buffer=None,
                             g_mode=G_REWARD_TO_GO):

@@ -47,6 +47,7 @@ class BatchedCongestion(BatchedEnv):
     action_space = 5
     cost_dtype = torch.int32
     action_dtype = torch.uint8
+    never_done = True          # check_done is all-False (congestion.py:103-104)
 
     def __init__(self, size, n_agents, n_envs=1, noise=0.1, shuffle=False, device="cuda", starts=None,
                  demand_rate=None, seed=0, env_offset=0):
@@ -145,7 +146,7 @@ class BatchedCongestion(BatchedEnv):
         p = self._params(mode)
         _lib.check(self.lib.smarl_congestion_step(
             C.byref(p), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(act), _lib.ptr(self.moves),
-            _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
+            _lib.ptr(self.obs if self.emit_obs else None), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
             _lib.ptr(penalty), self.t, self.n_envs, self.ld, _lib.stream_ptr()))
 
     def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None, moves=None):

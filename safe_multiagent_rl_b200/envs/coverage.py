@@ -116,7 +116,7 @@ class BatchedCoverageDiscrete(BatchedEnv):
             params = self._params_shared
         _lib.check(self.lib.smarl_coverage_step(
             C.byref(params), _lib.ptr(self.pos_x), _lib.ptr(self.pos_y), _lib.ptr(act),
-            _lib.ptr(self.obs), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
+            _lib.ptr(self.obs if self.emit_obs else None), _lib.ptr(reward), _lib.ptr(cost), _lib.ptr(done), _lib.ptr(lambdas),
             _lib.ptr(penalty), self.n_envs, self.ld, _lib.stream_ptr()))
 
     def rollout(self, actions, lambdas=None, gamma=0.99, thresholds=None, g_mode=G_NONE, out=None):

@@ -20,7 +20,7 @@ from . import _lib
 
 class BatchedMetaAgent:
     def __init__(self, constraint_space, gamma, lr, thresholds, leq=True, start_learning_cycle=10, decay=1.0,
-                 lambda_0=0, n_agents=None, device="cuda", process_group=None):
+                 lambda_0=0, n_agents=None, device="cuda", process_group=None, comm=None):
         if not leq:
             raise NotImplementedError("only leq=True constraints (the reference's only use) are built")
         self.constraint_space = constraint_space
@@ -37,6 +37,7 @@ class BatchedMetaAgent:
         self.start_learning_cycle = start_learning_cycle
         self.decay = decay
         self.process_group = process_group
+        self.comm = comm           # optional dist.StatsComm: all-reduce through libsmarl's own NCCL binding
         self.lib = _lib.load()
         self._acc = torch.zeros(self.lib.smarl_stats_len(self.A, self.K), dtype=torch.float64, device=self.device)
         self._recorded = False
@@ -72,9 +73,12 @@ class BatchedMetaAgent:
             self._recorded = True
 
     def global_stats(self):
-        """Recorded sums over all ranks (sum_e C_k, violations, return sums, episode count)."""
+        """Recorded sums over all ranks (sum_e C_k, violations, return sums, episode count): through the C-ABI
+        communicator when one was given (``comm=StatsComm...``), else through torch.distributed."""
         acc = self._acc.clone()
-        if dist.is_available() and dist.is_initialized():
+        if self.comm is not None:
+            self.comm.allreduce(acc)
+        elif dist.is_available() and dist.is_initialized():
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.process_group)
         return acc
 

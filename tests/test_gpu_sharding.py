@@ -76,7 +76,7 @@ def test_congestion_philox_shard_invariance():
         assert np.array_equal(p2, pos[lo:hi]) and np.array_equal(r2, r[:, lo:hi]) and np.array_equal(c2, c[:, lo:hi])
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, abi_comm=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -89,7 +89,9 @@ def _nccl_worker(rank, world, port, q):
     actions = rng.integers(0, 5, size=(T, E, A)).astype(np.uint8)
     off, n = sd.shard_range(E, rank, world)
     env = s.BatchedCoverageDiscrete(5, A, n_envs=n, weights=[1.0, 2.0, 3.0], starts=starts[off:off + n], env_offset=off)
-    meta = s.BatchedMetaAgent([1] * A, 0.999, 0.05, [10.0] * A, start_learning_cycle=0, lambda_0=0.2, n_agents=A)
+    comm = sd.StatsComm.from_process_group() if abi_comm else None     # smarl_comm_* / smarl_stats_allreduce
+    meta = s.BatchedMetaAgent([1] * A, 0.999, 0.05, [10.0] * A, start_learning_cycle=0, lambda_0=0.2, n_agents=A,
+                              comm=comm)
     act = torch.as_tensor(actions[:, off:off + n], device="cuda")
     out = env.rollout_closed_loop(lambda obs, t: act[t], T, meta.lambdas, 0.999, thresholds=[10.0] * A)
     meta.step(out["stats"])
@@ -100,14 +102,35 @@ def _nccl_worker(rank, world, port, q):
     torch.distributed.destroy_process_group()
 
 
+def test_abi_communicator_single_rank_is_the_identity():
+    """smarl_comm_get_unique_id / _init_from_unique_id / smarl_stats_allreduce on one GPU: NCCL is loaded by
+    libsmarl itself (dlopen) and a one-rank all-reduce leaves the vector as it is."""
+    from safe_multiagent_rl_b200 import _lib
+    from safe_multiagent_rl_b200 import dist as sd
+    assert _lib.load().smarl_comm_nccl_version() >= 20000
+    comm = sd.StatsComm.from_process_group()
+    v = torch.arange(13, dtype=torch.float64, device="cuda") * 1.5
+    want = v.clone()
+    sd.allreduce_stats(v, comm=comm)
+    graph = torch.cuda.CUDAGraph()                      # the call is capturable: no host sync
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        comm.allreduce(v)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(v, want)
+    comm.close()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpu_nccl_lambda_update_matches_oracle():
+@pytest.mark.parametrize("abi_comm", [False, True])
+def test_two_gpu_nccl_lambda_update_matches_oracle(abi_comm):
     import torch.multiprocessing as mp
     from oracle import numpy_oracle as no
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 2000
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 2000 + (7 if abi_comm else 0)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, abi_comm)) for r in range(2)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in procs]
