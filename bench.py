@@ -310,7 +310,8 @@ def bench_policy_loop(s, a, dev):
     E = min(a.n_envs, 1 << 18)                 # the stacked forward materialises [A, E, 16] / [A, E, 5] f32 per step
     env = s.BatchedCoverageDiscrete(S, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)], device=dev,
                                     starts=np.random.default_rng(0).integers(0, S, (E, A, 2)))
-    pol = s.BatchedDiscretePolicy(env)
+    from safe_multiagent_rl_b200.policy import BatchedDiscretePolicy
+    pol = BatchedDiscretePolicy(env)
     lam = torch.full((A,), 0.1, dtype=torch.float64, device=dev)
     buf = env.new_rollout_buffer(T)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(T)]
@@ -346,7 +347,7 @@ def bench_policy_loop(s, a, dev):
     # BASELINE configs[0] (50 envs) with the policy in the loop, replayed from one CUDA graph
     env1 = s.BatchedCoverageDiscrete(5, 3, n_envs=50, weights=[1.0, 2.0, 3.0], device=dev,
                                      starts=np.random.default_rng(1).integers(0, 5, (50, 3, 2)))
-    pol1 = s.BatchedDiscretePolicy(env1)
+    pol1 = BatchedDiscretePolicy(env1)
     lam1 = torch.full((3,), 0.1, dtype=torch.float64, device=dev)
     loop = s.GraphedClosedLoop(env1, 50, lambda obs, t: pol1.act(obs), lam1, 0.999, thresholds=[25.0] * 3)
     ms1 = _event_ms(loop.replay, 50)

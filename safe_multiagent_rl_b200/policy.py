@@ -44,7 +44,7 @@ class BatchedDiscretePolicy(nn.Module):
         return self.fc2(F.relu(self.fc1(obs)))
 
     def dist(self, obs):
-        return torch.distributions.Categorical(logits=self.logits(obs))
+        return torch.distributions.Categorical(logits=self.logits(obs), validate_args=False)   # no host sync: graph-capturable
 
     @torch.no_grad()
     def act(self, obs):
@@ -73,7 +73,8 @@ class BatchedGaussianPolicy(nn.Module):
     def dist(self, obs):
         h = F.relu(self.fc1(obs))
         mu, var = self.fc2(h), F.relu(self.fc2_(h)) + 1e-4
-        return torch.distributions.Independent(torch.distributions.Normal(mu, var.sqrt()), 1)
+        return torch.distributions.Independent(torch.distributions.Normal(mu, var.sqrt(), validate_args=False), 1,
+                                              validate_args=False)
 
     @torch.no_grad()
     def act(self, obs):
