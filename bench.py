@@ -584,12 +584,24 @@ def run_ours(a):
         _lib.check(lib.smarl_host_session_create(C.byref(sess), _lib.ENV_COVERAGE, A, T, E, 0))
         assert lib.smarl_host_session_ld(sess) == ld
         pin = dict(pin_memory=True)
-        actions_h = torch.empty((T, A, ld), dtype=torch.uint8, **pin).copy_(actions)
-        sx_h = torch.empty((A, ld), dtype=torch.uint8, **pin).copy_(env.start_x)
-        sy_h = torch.empty((A, ld), dtype=torch.uint8, **pin).copy_(env.start_y)
-        R_h = torch.empty((A, ld), dtype=torch.float32, **pin)
-        M_h = torch.empty((A, ld), dtype=torch.float32, **pin)
-        C_h = torch.empty((K, ld), dtype=torch.int32, **pin)
+        pinned_nodes, pinned_raw = [], []
+
+        def pinned(shape, dtype):
+            """Pinned host array from smarl_host_alloc_pinned: placed on the NUMA node of this rank's GPU when the
+            kernel allows it (matters once several ranks share the box)."""
+            n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            raw, node = C.c_void_p(), C.c_int32(-1)
+            _lib.check(lib.smarl_host_alloc_pinned(C.byref(raw), n, C.byref(node)))
+            pinned_raw.append(raw)
+            pinned_nodes.append(int(node.value))
+            arr = np.ctypeslib.as_array((C.c_uint8 * n).from_address(raw.value))
+            return torch.from_numpy(arr).view(dtype).reshape(shape)
+        actions_h = pinned((T, A, ld), torch.uint8).copy_(actions)
+        sx_h = pinned((A, ld), torch.uint8).copy_(env.start_x)
+        sy_h = pinned((A, ld), torch.uint8).copy_(env.start_y)
+        R_h = pinned((A, ld), torch.float32)
+        M_h = pinned((A, ld), torch.float32)
+        C_h = pinned((K, ld), torch.int32)
         st_h = torch.zeros(lib.smarl_stats_len(A, K), dtype=torch.float64)
         lut_h = env._lut.cpu()
         w_h = torch.tensor(weights, dtype=torch.float32)
@@ -613,11 +625,19 @@ def run_ours(a):
         for _ in range(e2e_steps):
             host_call()                                         # synchronous: returns with host results ready
         el = time.perf_counter() - t0
+        el_local = el
         tt = torch.tensor([el], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         el = float(tt.item())
+        h2d_b, d2h_b = int(T * A * ld + 2 * A * ld), int(3 * A * ld * 4 + 8 * lib.smarl_stats_len(A, K))
+        mine = torch.tensor([h2d_b * e2e_steps / el_local / 1e9], dtype=torch.float64, device=dev)
+        per_rank = [mine.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, mine)
         e2e = {"value": world * agent_steps * e2e_steps / el, "unit": UNIT,
+               "per_rank_h2d_gbs": [round(float(x.item()), 2) for x in per_rank],
+               "pinned_numa_node": sorted(set(pinned_nodes)),
                "h2d_bytes_per_step": int(T * A * ld + 2 * A * ld),
                "d2h_bytes_per_step": int(3 * A * ld * 4 + 8 * lib.smarl_stats_len(A, K)),
                "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps,
@@ -654,6 +674,40 @@ def run_ours(a):
                               "same_results_as_u8": same}
         except Exception as ex:
             e2e["packed4"] = {"error": str(ex)[:200]}
+        # extra: base-5 packed actions, three per byte (a third of the action bytes on PCIe; expanded on the device)
+        try:
+            pitch5 = int(lib.smarl_host_session_pitch5(sess))
+            pad = torch.zeros((T, A, 3 * pitch5), dtype=torch.uint8, device=dev)
+            pad[:, :, :ld] = actions
+            packed5_h = pinned((T, A, pitch5), torch.uint8)
+            packed5_h.copy_(pad[:, :, 0::3] + 5 * pad[:, :, 1::3] + 25 * pad[:, :, 2::3])
+            del pad
+
+            def host_call5():
+                _lib.check(lib.smarl_host_coverage_rollout_packed5(sess, C.byref(hp), C.byref(hacc), sx_h.data_ptr(),
+                                                                   sy_h.data_ptr(), packed5_h.data_ptr(), lam_h.data_ptr(),
+                                                                   R_h.data_ptr(), M_h.data_ptr(), C_h.data_ptr(),
+                                                                   st_h.data_ptr()))
+            for _ in range(2):
+                host_call5()
+            same5 = bool(torch.equal(R_h, R_ref))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_call5()
+            el5 = time.perf_counter() - t0
+            tt = torch.tensor([el5], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el5 = float(tt.item())
+            e2e["packed5"] = {"value": world * agent_steps * e2e_steps / el5, "unit": UNIT,
+                              "h2d_bytes_per_step": int(T * A * pitch5 + 2 * A * ld), "ms_per_step": 1e3 * el5 / e2e_steps,
+                              "api": "smarl_host_coverage_rollout_packed5 (three base-5 actions per byte)",
+                              "same_results_as_u8": same5}
+        except Exception as ex:
+            e2e["packed5"] = {"error": str(ex)[:200]}
         # extra: the same call on the reference's env-major arrays ([T][E][A] actions, [E][A] results); the layout
         # change runs on the device inside the pipeline
         try:

@@ -390,6 +390,22 @@ int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const SmarlCoverage
                                         const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
                                         double* stats_h);
 
+/* Same with base-5 packed actions, three per byte: byte j of a row holds envs 3j, 3j+1, 3j+2 as a0 + 5 a1 + 25 a2
+ * (0.33 B per action); actions5_h u8 [T][A][smarl_host_session_pitch5()].  A third of the action bytes on PCIe. */
+int64_t smarl_host_session_pitch5(const SmarlHostSession* s);
+int smarl_host_coverage_rollout_packed5(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                        const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                        const uint8_t* start_y_h, const uint8_t* actions5_h,
+                                        const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
+                                        double* stats_h);
+
+/* Pinned (page-locked) host memory for the arrays of the smarl_host_* calls, placed on the NUMA node the current
+ * GPU is attached to (sysfs numa_node of its PCI address, set_mempolicy(MPOL_PREFERRED) around the first touch) when
+ * the kernel allows it; *numa_node_out (may be NULL) receives that node, or -1 if no binding was applied.  With one
+ * rank per GPU this keeps every rank's PCIe traffic on its own socket.  Free with smarl_host_free_pinned. */
+int smarl_host_alloc_pinned(void** out, size_t bytes, int32_t* numa_node_out);
+void smarl_host_free_pinned(void* p);
+
 /* Same for callers that keep the reference's env-major arrays (what np.array(actions) gives there): no
  * padding, no ld.  starts_h u8 [E][A][2] (x, y per agent, coverage.py:45-49); actions_h u8 [T][E][A];
  * R_h, modR_h f32 [E][A]; C_h i32 [E][A].  The layout change runs on the device inside the pipeline, so

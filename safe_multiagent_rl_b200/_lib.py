@@ -93,6 +93,11 @@ PROTOTYPES = {
                                               c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "smarl_host_coverage_rollout_packed4": (C.c_int, [c_ptr, P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr,
                                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "smarl_host_session_pitch5": (i64, [c_ptr]),
+    "smarl_host_coverage_rollout_packed5": (C.c_int, [c_ptr, P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr,
+                                                      c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "smarl_host_alloc_pinned": (C.c_int, [P(c_ptr), C.c_size_t, P(i32)]),
+    "smarl_host_free_pinned": (None, [c_ptr]),
     "smarl_host_coverage_rollout_envmajor": (C.c_int, [c_ptr, P(CoverageParams), P(Accounting), c_ptr, c_ptr, c_ptr,
                                                        c_ptr, c_ptr, c_ptr, c_ptr]),
     "smarl_host_congestion_rollout_envmajor": (C.c_int, [c_ptr, P(CongestionParams), P(Accounting), c_ptr, c_ptr, c_ptr,

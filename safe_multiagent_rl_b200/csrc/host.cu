@@ -3,6 +3,9 @@
 // host->device copy of chunk c+1, the fused rollout of chunk c and the device->host copy of
 // chunk c-1 overlap (PCIe is full duplex; the kernel is far shorter than either copy).
 #include <stdlib.h>
+#include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <new>
 
@@ -18,6 +21,8 @@ struct SmarlHostSession {
   void* d_start_y;
   void* d_actions;          // u8 [T][A][ld] or f32 [T][2A][ld]
   uint8_t* d_packed;        // Coverage 4-bit packed actions [T][A][ld/2], allocated on first use
+  uint8_t* d_packed5;       // Coverage base-5 packed actions [T][A][pitch5], allocated on first use
+  int64_t pitch5;           // bytes per base-5 packed row
   uint8_t* d_moves;         // Congestion recorded moves, allocated on first use
   double* d_landmarks;      // Collision f64 [2L][ld]
   float* d_R;
@@ -43,7 +48,7 @@ static void free_session(SmarlHostSession* s) {
   if (!s) return;
   for (auto st : s->streams)
     if (st) cudaStreamDestroy(st);
-  cudaFree(s->d_start_x); cudaFree(s->d_start_y); cudaFree(s->d_actions); cudaFree(s->d_moves); cudaFree(s->d_packed);
+  cudaFree(s->d_start_x); cudaFree(s->d_start_y); cudaFree(s->d_actions); cudaFree(s->d_moves); cudaFree(s->d_packed); cudaFree(s->d_packed5);
   cudaFree(s->d_landmarks); cudaFree(s->d_R); cudaFree(s->d_modR); cudaFree(s->d_C); cudaFree(s->d_n_active);
   cudaFree(s->d_stats); cudaFree(s->d_scratch); cudaFree(s->d_lut); cudaFree(s->d_weights);
   cudaFree(s->d_lambdas); cudaFree(s->d_thresholds); cudaFree(s->d_demand);
@@ -70,9 +75,10 @@ extern "C" int smarl_host_session_create(SmarlHostSession** out, int32_t kind, i
   // chunks, 66.7 with 16, 66.1 with 32, 65.8 with 64.
   const char* env_chunks = getenv("SMARL_HOST_CHUNKS");
   const int64_t n_target = env_chunks && atoll(env_chunks) > 0 ? atoll(env_chunks) : 32;
-  int64_t chunk = (s->ld / n_target + 15) / 16 * 16;
-  if (chunk < 65536) chunk = 65536;
+  int64_t chunk = (s->ld / n_target + 47) / 48 * 48;     // multiple of 16 (vector width) and of 3 (base-5 action triples)
+  if (chunk < 65520) chunk = 65520;
   if (chunk > s->ld) chunk = s->ld;
+  s->pitch5 = ((s->ld + 2) / 3 + 15) / 16 * 16;
   s->chunk = chunk;
   s->n_chunks = (int)((n_envs + chunk - 1) / chunk);
   const int sl = stats_len(A, s->K);
@@ -134,6 +140,38 @@ __global__ void unpack4_kernel(const uint8_t* __restrict__ packed, uint8_t* __re
   uint4 o;
   o.x = spread(v.x & 0xFFFFu); o.y = spread(v.x >> 16); o.z = spread(v.y & 0xFFFFu); o.w = spread(v.y >> 16);
   *reinterpret_cast<uint4*>(actions + row * ld + e0 + col) = o;
+}
+
+// Base-5 packed actions (actions are 0..4, so three fit one byte: b = a0 + 5 a1 + 25 a2 for envs 3j, 3j+1, 3j+2)
+// -> one byte per action.  A thread expands 16 packed bytes into 48 action bytes (three 16-byte stores); e0 is a
+// multiple of 48, so every access is aligned.  Stores beyond the row's ld (last chunk) are dropped.
+__global__ void unpack5_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ actions, int64_t rows,
+                               int64_t ld, int64_t pitch5, int64_t e0, int64_t groups) {
+  __shared__ uint32_t s_dec[256];
+  for (int b = threadIdx.x; b < 256; b += blockDim.x) s_dec[b] = (uint32_t)(b % 5) | ((uint32_t)((b / 5) % 5) << 8) | ((uint32_t)(b / 25) << 16);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * groups) return;
+  const int64_t row = i / groups, g = i % groups;
+  const uint4 v = *reinterpret_cast<const uint4*>(packed + row * pitch5 + e0 / 3 + g * 16);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint8_t out[48];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t d = s_dec[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+    out[3 * k] = (uint8_t)d;
+    out[3 * k + 1] = (uint8_t)(d >> 8);
+    out[3 * k + 2] = (uint8_t)(d >> 16);
+  }
+  const int64_t col = e0 + g * 48;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (col + 16 * q < ld) {
+      uint4 o;
+      memcpy(&o, out + 16 * q, 16);
+      *reinterpret_cast<uint4*>(actions + row * ld + col + 16 * q) = o;
+    }
+  }
 }
 
 // Layout converters for callers that keep the reference's env-major arrays ([.., env, agent], what
@@ -257,8 +295,9 @@ int pipeline(SmarlHostSession* s, double* stats_h, Body body) {
 
 static int host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams* p, const SmarlAccounting* acc,
                                  const uint8_t* start_x_h, const uint8_t* start_y_h, const uint8_t* actions_h,
-                                 bool packed4, const double* lambdas_h, float* R_h, float* modR_h, int32_t* C_h,
-                                 double* stats_h) {
+                                 int packing /* 0 bytes, 4 nibbles, 5 base-5 triples */, const double* lambdas_h, float* R_h,
+                                 float* modR_h, int32_t* C_h, double* stats_h) {
+  const bool packed4 = packing == 4, packed5 = packing == 5;
   SMARL_REQUIRE(s && p && acc, "null session / params");
   SMARL_REQUIRE(s->kind == SMARL_ENV_COVERAGE && p->n_agents == s->A && acc->n_steps == s->T,
                 "session was created for kind=%d A=%d T=%d", s->kind, s->A, s->T);
@@ -280,6 +319,7 @@ static int host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams*
   uint8_t* dy = static_cast<uint8_t*>(s->d_start_y);
   uint8_t* da = static_cast<uint8_t*>(s->d_actions);
   if (packed4 && !s->d_packed) SMARL_CUDA(cudaMalloc(&s->d_packed, (size_t)T * A * ld / 2));
+  if (packed5 && !s->d_packed5) SMARL_CUDA(cudaMalloc(&s->d_packed5, (size_t)T * A * s->pitch5));
   return pipeline(s, stats_h, [&](const Chunk& c) -> int {
     if (int rc = copy_rows(dx, start_x_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
     if (int rc = copy_rows(dy, start_y_h, 1, A, ld, c, cudaMemcpyHostToDevice)) return rc;
@@ -289,6 +329,15 @@ static int host_coverage_rollout(SmarlHostSession* s, const SmarlCoverageParams*
                                    cudaMemcpyHostToDevice, c.st));
       const int64_t n = rows * (c.w / 16);
       unpack4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(s->d_packed, da, rows, ld, c.e0, c.w);
+      SMARL_CUDA(cudaGetLastError());
+    } else if (packed5) {               // a third of the PCIe bytes: copy base-5 triples, expand on the device
+      const int64_t rows = (int64_t)T * A, groups = (c.w + 47) / 48;       // 16 packed bytes = 48 envs per group
+      int64_t w5 = groups * 16;
+      if (c.e0 / 3 + w5 > s->pitch5) w5 = s->pitch5 - c.e0 / 3;
+      SMARL_CUDA(cudaMemcpy2DAsync(s->d_packed5 + c.e0 / 3, s->pitch5, actions_h + c.e0 / 3, s->pitch5, (size_t)w5,
+                                   (size_t)rows, cudaMemcpyHostToDevice, c.st));
+      const int64_t n = rows * groups;
+      unpack5_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(s->d_packed5, da, rows, ld, s->pitch5, c.e0, groups);
       SMARL_CUDA(cudaGetLastError());
     } else if (int rc = copy_rows(da, actions_h, 1, (int64_t)T * A, ld, c, cudaMemcpyHostToDevice)) {
       return rc;
@@ -309,7 +358,7 @@ extern "C" int smarl_host_coverage_rollout(SmarlHostSession* s, const SmarlCover
                                            const uint8_t* start_y_h, const uint8_t* actions_h,
                                            const double* lambdas_h, float* R_h, float* modR_h,
                                            int32_t* C_h, double* stats_h) {
-  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions_h, false, lambdas_h, R_h, modR_h, C_h, stats_h);
+  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions_h, 0, lambdas_h, R_h, modR_h, C_h, stats_h);
 }
 
 extern "C" int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const SmarlCoverageParams* p,
@@ -317,7 +366,69 @@ extern "C" int smarl_host_coverage_rollout_packed4(SmarlHostSession* s, const Sm
                                                    const uint8_t* start_y_h, const uint8_t* actions4_h,
                                                    const double* lambdas_h, float* R_h, float* modR_h,
                                                    int32_t* C_h, double* stats_h) {
-  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions4_h, true, lambdas_h, R_h, modR_h, C_h, stats_h);
+  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions4_h, 4, lambdas_h, R_h, modR_h, C_h, stats_h);
+}
+
+extern "C" int64_t smarl_host_session_pitch5(const SmarlHostSession* s) { return s ? s->pitch5 : 0; }
+
+extern "C" int smarl_host_coverage_rollout_packed5(SmarlHostSession* s, const SmarlCoverageParams* p,
+                                                   const SmarlAccounting* acc, const uint8_t* start_x_h,
+                                                   const uint8_t* start_y_h, const uint8_t* actions5_h,
+                                                   const double* lambdas_h, float* R_h, float* modR_h,
+                                                   int32_t* C_h, double* stats_h) {
+  return host_coverage_rollout(s, p, acc, start_x_h, start_y_h, actions5_h, 5, lambdas_h, R_h, modR_h, C_h, stats_h);
+}
+
+// ---------------------------------------------------------------------------------------
+// Pinned host staging on the NUMA node the current GPU hangs off.  With several ranks on one box, pinned buffers
+// that all sit on one node make every GPU of the other socket pull its PCIe traffic across the inter-socket link;
+// this binds the allocation (first touch) to the GPU's own node when the kernel lets it.
+// ---------------------------------------------------------------------------------------
+static int gpu_numa_node() {
+  int dev = 0;
+  char bus[32] = "";
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) return -1;
+  for (char* c = bus; *c; ++c)
+    if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');     // sysfs spells the address in lower case
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+extern "C" int smarl_host_alloc_pinned(void** out, size_t bytes, int32_t* numa_node_out) {
+  SMARL_REQUIRE(out != nullptr && bytes > 0, "bad arguments");
+  const int node = gpu_numa_node();
+  bool bound = false;
+#ifdef SYS_set_mempolicy
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    // MPOL_PREFERRED = 1: fall back to other nodes instead of failing when the node is full or not in cpuset.mems
+    bound = syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(8 * sizeof(mask) + 1)) == 0;
+  }
+#endif
+  void* p = nullptr;
+  cudaError_t err = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (err == cudaSuccess) memset(p, 0, bytes);                   // first touch under the policy
+#ifdef SYS_set_mempolicy
+  if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+  if (err != cudaSuccess) {
+    set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+    return SMARL_ECUDA;
+  }
+  if (numa_node_out) *numa_node_out = bound ? node : -1;
+  *out = p;
+  return SMARL_OK;
+}
+
+extern "C" void smarl_host_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 // Per-stream staging of one chunk's env-major inputs / outputs (allocated on first use of an env-major entry).
