@@ -74,10 +74,24 @@ def workload_name(a):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's execution model (one env per process, Python loop) on all host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_rate(a, seconds):
+def cpu_impl():
+    """(module, kind): the unmodified reference classes when their copy travelled with the repo (oracle/_ref, made
+    by __graft_entry__.build() from /root/reference) or the tree is mounted, else the pinned port."""
+    from oracle import ref_timing as rt
+    if rt.root() is not None:
+        try:
+            rt.load()
+            return rt, "reference"
+        except Exception as ex:                     # e.g. a dependency of the reference missing on this box
+            sys.stderr.write(f"reference arm: falling back to the port ({ex})\n")
     from oracle import scalar_port as sp
-    procs = os.cpu_count() or 1
-    rate, used = sp.time_all_cores("coverage", a.size, a.n_agents, a.max_t, a.gamma, seconds, procs)
+    return sp, "port"
+
+
+def cpu_rate(a, seconds):
+    mod, _ = cpu_impl()
+    procs = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rate, used = mod.time_all_cores("coverage", a.size, a.n_agents, a.max_t, a.gamma, seconds, procs)
     return rate, used
 
 
@@ -95,14 +109,17 @@ def run_reference(a):
         rates.append(r)
     wall = time.perf_counter() - t0
     v = statistics.mean(rates)
+    kind = cpu_impl()[1]
+    what = ("the unmodified reference classes (oracle/_ref copy of envs/ + safe_multi_agent_RL/)" if kind == "reference"
+            else "oracle/scalar_port.py (reference-structured port; the reference copy is absent)")
     sample = (f"{a.steps} x {per_step:.1f}s of whole episodes (env.step + MetaAgent.act + Buffer.append/step + "
-              f"reward-to-go) on {cores} processes, one env each, recorded random actions")
+              f"reward-to-go) of {what} on {cores} processes, one env each, recorded random actions")
     emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "note": "CPU arm ignores n_envs: it steps one env per core"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -752,11 +769,12 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, cores = cpu_rate(a, a.cpu_seconds)
-        from oracle import scalar_port as sp
-        one_steps, one_el = sp.time_episodes("coverage", a.size, a.n_agents, a.max_t, a.gamma, 2.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "one_core": one_steps / one_el,
+        cmod, ckind = cpu_impl()
+        one_steps, one_el = cmod.time_episodes("coverage", a.size, a.n_agents, a.max_t, a.gamma, 2.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": ckind, "one_core": one_steps / one_el,
                "sample": f"{a.cpu_seconds:.0f}s of whole episodes of the same env config, one env per process on "
-                         f"{cores} processes (oracle/scalar_port.py: env.step + MetaAgent.act + Buffer + reward-to-go)"}
+                         f"{cores} processes ({'the unmodified reference classes, oracle/_ref' if ckind == 'reference' else 'oracle/scalar_port.py'}"
+                         f": env.step + MetaAgent.act + Buffer + reward-to-go)"}
         try:                                       # extra: the plain-C oracle (pthreads) on a 2^16-env slice
             from oracle import c_oracle as co
             from oracle import numpy_oracle as no

@@ -14,6 +14,14 @@ from ..rollout import G_NONE, device_thresholds, make_accounting
 from .base import BatchedEnv
 
 
+def default_starts(size, n_agents, n_envs, n_landmarks=1):
+    """(starts [n_envs, n_agents, 2], landmarks [n_envs, n_landmarks, 2]) in the reference ctor's RNG order
+    (collision_avoidance.py:60-62): per env the agents' ``rand(2) * size`` in index order, then the landmark(s).
+    The ctor itself draws a single landmark; with shuffle every reset redraws n_landmarks (:100-101)."""
+    draws = np.random.rand(n_envs, n_agents + n_landmarks, 2) * size
+    return draws[:, :n_agents], draws[:, n_agents:]
+
+
 class BatchedCollisionAvoidance(BatchedEnv):
     """Constructor mirrors ``CollisionAvoidance(size, n_agents, n_landmarks, shuffle, agents_size,
     normalize_state)`` (collision_avoidance.py:49) plus ``n_envs`` / ``device``.
@@ -42,13 +50,11 @@ class BatchedCollisionAvoidance(BatchedEnv):
         self.n_constraints = 1
         self.action_rows = 2 * A
         if starts is None or landmarks is None:
-            # the ctor draws a single landmark (:62); with shuffle every reset redraws n_landmarks (:100-101)
-            L0 = self.n_landmarks if self.shuffle else 1
-            draws = np.random.rand(E, A + L0, 2) * self.size
+            d_starts, d_landmarks = default_starts(self.size, A, E, self.n_landmarks if self.shuffle else 1)
             if starts is None:
-                starts = draws[:, :A]
+                starts = d_starts
             if landmarks is None:
-                landmarks = draws[:, A:]
+                landmarks = d_landmarks
         starts = np.asarray(starts, dtype=np.float64)
         landmarks = np.asarray(landmarks, dtype=np.float64)
         assert starts.shape == (E, A, 2) and landmarks.shape[0] == E and landmarks.shape[2] == 2

@@ -26,6 +26,15 @@ def keep_threshold(noise: float) -> int:
     return min(1 << 32, max(0, math.ceil(lim)))
 
 
+def default_starts(size, n_agents, n_envs):
+    """Start positions [n_envs, n_agents, 2] in the reference ctor's RNG order (congestion.py:22, :215-217): agent 0
+    sits at (0, 0) and draws nothing, agents 1.. draw ``floor(rand(2) * size)`` in index order, env after env."""
+    starts = np.zeros((n_envs, n_agents, 2))
+    if n_agents > 1:
+        starts[:, 1:, :] = np.floor(np.random.rand(n_envs, n_agents - 1, 2) * size)
+    return starts
+
+
 class BatchedCongestion(BatchedEnv):
     """Constructor mirrors ``Congestion(size, n_agents, noise, shuffle)`` (congestion.py:19) plus
     ``n_envs`` / ``device``.
@@ -77,9 +86,7 @@ class BatchedCongestion(BatchedEnv):
         wait = -30.0 * (con + 1) / demand_rate[None] + 7.5 - 4.0
         self._wait_reward = torch.as_tensor(np.ascontiguousarray(wait.astype(np.float32))).to(dev)
         if starts is None:
-            starts = np.zeros((E, A, 2))
-            if A > 1:
-                starts[:, 1:, :] = np.floor(np.random.rand(E, A - 1, 2) * self.size)
+            starts = default_starts(self.size, A, E)
         starts = np.asarray(starts)
         assert starts.shape == (E, A, 2)
         if starts.min() < 0 or starts.max() > self.size:

@@ -33,6 +33,15 @@ def penalty_table(size, n_agents, fieldview_size=None):
     return fv, np.asarray(vals, dtype=np.float64)
 
 
+def default_starts(size, n_agents, n_envs):
+    """Start positions [n_envs, n_agents, 2] drawn from the global ``np.random`` stream exactly as constructing
+    n_envs reference ``CoverageDiscrete`` envs one after another does: each ctor first builds and discards
+    n_agents continuous agents (coverage.py:19 via super().__init__, 2 rand values each), then draws the kept ones
+    as ``floor(rand(2) * size)`` in agent order (:170, :267-269)."""
+    draws = np.random.rand(n_envs, 2 * n_agents, 2)
+    return np.floor(draws[:, n_agents:, :] * size)
+
+
 class BatchedCoverageDiscrete(BatchedEnv):
     """Constructor mirrors ``CoverageDiscrete(size, n_agents, shuffle, agents_size, fieldview_size,
     weights)`` (coverage.py:167) plus ``n_envs`` / ``device``.
@@ -80,8 +89,7 @@ class BatchedCoverageDiscrete(BatchedEnv):
         self._params_shared = _lib.CoverageParams(self.size, A, len(table), 1, _lib.ptr(self._lut),
                                                   _lib.ptr(self._weights))
         if starts is None:
-            draws = np.random.rand(E, 2 * A, 2)
-            starts = np.floor(draws[:, A:, :] * self.size)
+            starts = default_starts(self.size, A, E)
         starts = np.asarray(starts)
         assert starts.shape == (E, A, 2)
         if starts.min() < 0 or starts.max() > self.size:

@@ -126,6 +126,12 @@ if __name__ == "__main__":
                     if E * A * 50 > 4e9:
                         continue
                     cfgs.append((env_name, S, A, E, 50))
+    print("Envelope of the kernels behind this table: n_agents <= 32; grid size <= 127 (Coverage: doubled u8 coordinates index the "
+          "penalty table, fieldview^2 <= 12279 table entries) / <= 254 (Congestion); fused Coverage rollout T <= 255 (byte cost "
+          "counters); per call (2 * n_agents + 1) * ld < 2^32 (32-bit element offsets: n_agents = 32 caps a call at ~6.6e7 envs; "
+          "larger batches are split by the caller); Collision n_landmarks <= 64.  Outside it the entry points return "
+          "SMARL_EUNSUPPORTED / the ctors raise.  Thread mapping per row: automatic (one thread per env / per four envs up to the "
+          "measured crossover, lane-cooperative kernels above it; DESIGN.md section 3).\n")
     print("| env | size | agents | envs | T | closed-loop agent-steps/s (CUDA graph) | ms | closed-loop algorithmic GB/s "
           "(fraction of the 6551 GB/s HBM peak) | fused agent-steps/s | ms |")
     print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
