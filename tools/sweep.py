@@ -25,27 +25,27 @@ def make(env_name, S, A, E, g):
                                         starts=np.zeros((E, A, 2), np.uint8))
         env.start_x[:, :E] = torch.randint(0, S, (A, E), generator=g, device=dev, dtype=torch.uint8)
         env.start_y[:, :E] = torch.randint(0, S, (A, E), generator=g, device=dev, dtype=torch.uint8)
-        K, bytes_step = A, 19.0 + 4.0 / A
+        K, bytes_step = A, 18.0 + 4.0 / A            # pos r/w 4, action 1, obs 8, reward 4, cost 1 (+ penalty 4/A); done not stored
     elif env_name == "congestion":
         rng = np.random.default_rng(0)
         env = s.BatchedCongestion(S, A, n_envs=E, noise=0.1, starts=np.zeros((E, A, 2), np.uint8),
                                   demand_rate=rng.random((S + 1, S + 1)) * 8 + 2, seed=1)
         env.start_x[1:, :E] = torch.randint(0, S, (A - 1, E), generator=g, device=dev, dtype=torch.uint8)
         env.start_y[1:, :E] = torch.randint(0, S, (A - 1, E), generator=g, device=dev, dtype=torch.uint8)
-        K, bytes_step = 1, 19.0 + 8.0 / A            # incl. the effective-move row the step kernel publishes
+        K, bytes_step = 1, 18.0 + 8.0 / A            # pos r/w 4, action 1, effective move 1, obs 8, reward 4 (+ cost, penalty 8/A)
     elif env_name in ("coverage_cont", "coverage_disc"):       # the paper's Explore variants (f64 positions, coarseness 6)
         starts = np.zeros((E, A, 2))
         if env_name == "coverage_cont":
             env = s.BatchedCoverageContinuous(S, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)], coarseness=6,
                                               starts=starts)
             pos = torch.rand((2, A, E), generator=g, device=dev, dtype=torch.float64) * S
-            bytes_step = 32.0 + 8.0 + 8.0 + 4.0 + 4.0 + 1.0 + 4.0 / A      # pos r/w, action, obs, reward, cost, done, penalty
+            bytes_step = 32.0 + 8.0 + 8.0 + 4.0 + 4.0 + 4.0 / A            # pos r/w, action, obs, reward, cost, penalty
         else:
             env = s.BatchedCoverageDiscretized(S, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)], coarseness=6,
                                                starts=starts)
             zoom = 6.0 / S
             pos = torch.floor(torch.rand((2, A, E), generator=g, device=dev, dtype=torch.float64) * S * zoom) / zoom
-            bytes_step = 32.0 + 1.0 + 8.0 + 4.0 + 4.0 + 1.0 + 4.0 / A
+            bytes_step = 32.0 + 1.0 + 8.0 + 4.0 + 4.0 + 4.0 / A
         env.start_x[:, :E], env.start_y[:, :E] = pos[0], pos[1]
         K = A
     else:
