@@ -20,6 +20,8 @@
 //
 // Bit-exactness: the per-agent arithmetic is shared with collision.cu (collision.cuh); the reward uses the very
 // association numpy_sum<A> uses; the collision count is an integer.  Compiled with -fmad=false.
+#include <stdlib.h>
+
 #include "collision.cuh"
 
 // Built as two translation units (build.py compiles this file once per SMARL_TU value): 0 step, 1 rollout.
@@ -33,6 +35,8 @@ namespace smarl {
 constexpr int kCoopThreads = 128;
 constexpr int kCoopMinA = 9;          // smallest agent count the cooperative kernels are instantiated for
 
+constexpr int kClipSlots = 64;        // compacted action clips per warp and step (two rounds of 32 lanes)
+
 template <int A, int S>
 struct CollCoop {
   static constexpr int B = (A + S - 1) / S;          // agents per lane
@@ -41,10 +45,24 @@ struct CollCoop {
   static constexpr int H = A / 2;                    // circular partner window (the last offset halved for even A)
   static constexpr bool kGhost = (A % S) != 0;       // some lanes own a padding agent at j = B-1
   static constexpr int PA = A | 1;                   // double2 stride per env: odd => conflict-free STS.128 / LDS.128
-  static constexpr int FS = S == 2 ? ((2 * A) | 1) : ((((2 * A) + 3) & ~3) | 2);   // float2 stride per env (LDS.64)
-  static constexpr int NS = (2 * A) | 1;             // float stride per env of the squared norms (LDS.32)
-  static constexpr size_t kSmem = (size_t)EPC * (PA * sizeof(double2) + FS * sizeof(float2) + NS * sizeof(float));
+  static constexpr int FS = S == 2 ? (A | 1) : (((A + 3) & ~3) | 2);   // float2 stride per env (LDS.64)
+  static constexpr int NS = A | 1;                   // float stride per env of the squared norms (LDS.32)
+  static constexpr size_t kSmem = (size_t)EPC * (PA * sizeof(double2) + FS * sizeof(float2) + NS * sizeof(float)) +
+                                  (size_t)(kCoopThreads / 32) * kClipSlots * sizeof(double2);
 };
+
+// The action clip of collision_move_agent (collision.cuh; collision_avoidance.py:113-117) for one agent whose squared
+// norm exceeds 1, out of line: norm = sqrt(dx^2 + dy^2); if norm > 1 both components are divided by it.
+static __device__ __noinline__ double2 clip_action(float adx, float ady) {
+  double dx = (double)adx, dy = (double)ady;
+  const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+  const double norm = __dsqrt_rn(q);
+  if (norm > 1.0) {
+    dx = __ddiv_rn(dx, norm);
+    dy = __ddiv_rn(dy, norm);
+  }
+  return make_double2(dx, dy);
+}
 
 // Exact test of one pair (the arithmetic of pair_collides in collision.cuh) on values instead of arrays.
 static __device__ __noinline__ int pair_collides_xy(double xi, double yi, double xj, double yj, double lim2_lo,
@@ -95,21 +113,61 @@ __device__ __forceinline__ double coop_numpy_sum(const double (&v)[CollCoop<A, S
 // One CollisionAvoidance.step of the group's env.  px/py/done_bits (bit j = own agent j) are updated in place;
 // reward (identical on every lane of the group) and the group's collision count are returned.  Must be called by
 // all 32 lanes (shuffles, __syncwarp); envs past their episode end simply have all agents done.
-template <int A, int S>
+template <int A, int S, bool COMPACT>
 __device__ __forceinline__ void collision_coop_env_step(double (&px)[CollCoop<A, S>::B], double (&py)[CollCoop<A, S>::B],
                                                         uint32_t& done_bits, const float (&adx)[CollCoop<A, S>::B],
                                                         const float (&ady)[CollCoop<A, S>::B],
                                                         const double* __restrict__ lm, int64_t ld, int L, double size,
                                                         double agents_size, int s, int q, double2* __restrict__ sp,
-                                                        float2* __restrict__ sf, float* __restrict__ sn, double& reward,
-                                                        int& collisions) {
+                                                        float2* __restrict__ sf, float* __restrict__ sn,
+                                                        double2* __restrict__ clip, double& reward, int& collisions) {
   using C = CollCoop<A, S>;
   constexpr int B = C::B, H = C::H, EPW = C::EPW;
-  // transition (collision_avoidance.py:103-121); padding agents carry a set done bit
+  // transition (collision_avoidance.py:103-121); padding agents carry a set done bit.
+  // The clip to unit norm (:113-117) costs an f64 sqrt and two f64 divisions (~100 instructions) for the agents whose
+  // action is longer than 1 -- a minority, but in practice some lane of every warp has one for every agent slot j, so
+  // inlined per slot the whole warp pays it B times.  Instead the clips of a warp are COMPACTED: every agent that
+  // needs one gets a rank (ballot + popc), posts its f32 action to shared memory, the lanes work the posted list
+  // off round-robin (ceil(n / 32) rounds instead of B) and the owners pick their f64 result up.  Ranks beyond the
+  // kClipSlots slots (an unusually clip-heavy warp) are evaluated in place.  Same arithmetic, same bits.
+  if constexpr (!COMPACT) {
 #pragma unroll
-  for (int j = 0; j < B; ++j) {
-    if ((done_bits >> j) & 1u) continue;
-    collision_move_agent(px[j], py[j], adx[j], ady[j], size);
+    for (int j = 0; j < B; ++j) {
+      if ((done_bits >> j) & 1u) continue;
+      collision_move_agent(px[j], py[j], adx[j], ady[j], size);
+    }
+  } else {
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    uint32_t need = 0u;
+    int rank[B];
+    int n_clip = 0;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const double dx = (double)adx[j], dy = (double)ady[j];
+      const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));   // :113 (dx**2 == dx*dx for fp32-origin values)
+      const bool nd = !((done_bits >> j) & 1u) && q > 1.0;     // sqrt_rn is monotonic with sqrt_rn(1) == 1: norm > 1 needs q > 1
+      const unsigned b = __ballot_sync(0xffffffffu, nd);
+      rank[j] = n_clip + __popc(b & lt);
+      n_clip += __popc(b);
+      need |= nd ? (1u << j) : 0u;
+      if (nd && rank[j] < kClipSlots) *reinterpret_cast<float2*>(clip + rank[j]) = make_float2(adx[j], ady[j]);
+    }
+    __syncwarp();
+    for (int r = (int)lane; r < min(n_clip, kClipSlots); r += 32) {
+      const float2 in = *reinterpret_cast<const float2*>(clip + r);
+      clip[r] = clip_action(in.x, in.y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      double2 d = make_double2((double)adx[j], (double)ady[j]);
+      if ((need >> j) & 1u) d = rank[j] < kClipSlots ? clip[rank[j]] : clip_action(adx[j], ady[j]);
+      if (!((done_bits >> j) & 1u)) {
+        px[j] = fmax(0.0, fmin(size, __dadd_rn(px[j], d.x)));      // :118
+        py[j] = fmax(0.0, fmin(size, __dadd_rn(py[j], d.y)));      // :119
+      }
+    }
+    __syncwarp();                       // the slots are reused by the next step
   }
   // landmark reach (:122-124) and per-agent minimum landmark distance (:158-161)
   double minq[B];
@@ -159,9 +217,7 @@ __device__ __forceinline__ void collision_coop_env_step(double (&px)[CollCoop<A,
     if (!C::kGhost || j < B - 1 || i < A) {
       sp[i] = make_double2(px[j], py[j]);
       sf[i] = make_float2(fx, fy);
-      sf[i + A] = make_float2(fx, fy);
       sn[i] = n;
-      sn[i + A] = n;
     }
   }
   __syncwarp();
@@ -176,8 +232,10 @@ __device__ __forceinline__ void collision_coop_env_step(double (&px)[CollCoop<A,
   const float* sns = sn + s;
 #pragma unroll
   for (int c = 1; c <= (B - 1) * S + H; ++c) {
-    const float2 p = sfs[c];
-    const float pn = sns[c];
+    // partner index (s + c) mod A: known at compile time except for the S-1 offsets around the wrap
+    const int cw = (c + S - 1 < A) ? c : (c >= A ? c - A : ((s + c >= A) ? c - A : c));
+    const float2 p = sfs[cw];
+    const float pn = sns[cw];
 #pragma unroll
     for (int j = 0; j < B; ++j) {
       const int k = c - j * S;
@@ -213,13 +271,15 @@ __device__ __forceinline__ void collision_coop_env_step(double (&px)[CollCoop<A,
 }
 
 #if SMARL_TU_IS(0)
-template <int A, int S>
+template <int A, int S, bool COMPACT>
 __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_step_kernel(const CollisionStepArgs a) {
   using C = CollCoop<A, S>;
   constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC;
   extern __shared__ double2 s_pos[];                                  // [EPC][PA]
   float2* s_f = reinterpret_cast<float2*>(s_pos + EPC * C::PA);       // [EPC][FS]
   float* s_n = reinterpret_cast<float*>(s_f + EPC * C::FS);           // [EPC][NS]
+  double2* s_clip = reinterpret_cast<double2*>(reinterpret_cast<char*>(s_pos) + C::kSmem) - (kCoopThreads / 32) * kClipSlots +
+                    (threadIdx.x >> 5) * kClipSlots;                   // [warps][kClipSlots]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane % EPW, s = lane / EPW;
   const int el = warp * EPW + q;
@@ -258,8 +318,8 @@ __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_step_kernel(co
 
   double reward = 0.0;
   int collisions = 0;
-  collision_coop_env_step<A, S>(px, py, done_bits, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size, s, q,
-                                s_pos + el * C::PA, s_f + el * C::FS, s_n + el * C::NS, reward, collisions);
+  collision_coop_env_step<A, S, COMPACT>(px, py, done_bits, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size, s, q,
+                                s_pos + el * C::PA, s_f + el * C::FS, s_n + el * C::NS, s_clip, reward, collisions);
   if (!live) return;
   const float rf = active ? (float)reward : 0.f;
   const bool all_rows = a.reward_rows != 1;
@@ -304,13 +364,13 @@ __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_step_kernel(co
   }
 }
 
-template <int S>
+template <int S, bool COMPACT>
 static int launch_step_s(int A, const CollisionStepArgs& a, cudaStream_t st) {
   switch (A) {
 #define SMARL_COOP_CASE(N)                                                                              \
   case N: {                                                                                             \
     using C = CollCoop<N, S>;                                                                           \
-    auto kern = collision_coop_step_kernel<N, S>;                                                       \
+    auto kern = collision_coop_step_kernel<N, S, COMPACT>;                                                     \
     if (C::kSmem > 48 * 1024)                                                                           \
       SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem)); \
     const unsigned grid = (unsigned)((a.n_envs + C::EPC - 1) / C::EPC);                                 \
@@ -331,20 +391,27 @@ static int launch_step_s(int A, const CollisionStepArgs& a, cudaStream_t st) {
 }
 
 int launch_collision_coop_step(int A, int S, const CollisionStepArgs& a, cudaStream_t st) {
-  return S == 2 ? launch_step_s<2>(A, a, st) : launch_step_s<4>(A, a, st);
+  // compacting the action clips pays in the fused rollout (-7..17 %) but not in the one-step kernel, whose front of
+  // global loads the ballots serialise (measured: A = 32 closed loop 14.4 -> 17.4 ms); SMARL_COLL_COMPACT=1 forces it
+  static const char* env = getenv("SMARL_COLL_COMPACT");
+  const bool compact = env && atoi(env) != 0;
+  if (compact) return S == 2 ? launch_step_s<2, true>(A, a, st) : launch_step_s<4, true>(A, a, st);
+  return S == 2 ? launch_step_s<2, false>(A, a, st) : launch_step_s<4, false>(A, a, st);
 }
 #endif
 
 #if SMARL_TU_IS(1)
 // Fused open-loop episode (main.py:28-57 minus the policy nets, incl. the early break at :51): the group's
 // positions / done bits / discounted sums stay in registers for all T steps.
-template <int A, int S>
+template <int A, int S, bool COMPACT>
 __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_rollout_kernel(const CollisionRolloutArgs a) {
   using C = CollCoop<A, S>;
   constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC;
   extern __shared__ double2 s_pos[];
   float2* s_f = reinterpret_cast<float2*>(s_pos + EPC * C::PA);
   float* s_n = reinterpret_cast<float*>(s_f + EPC * C::FS);
+  double2* s_clip = reinterpret_cast<double2*>(reinterpret_cast<char*>(s_pos) + C::kSmem) - (kCoopThreads / 32) * kClipSlots +
+                    (threadIdx.x >> 5) * kClipSlots;
   __shared__ double s_red[kCoopThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane % EPW, s = lane / EPW;
@@ -384,8 +451,8 @@ __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_rollout_kernel
     }
     double reward = 0.0;
     int collisions = 0;
-    collision_coop_env_step<A, S>(px, py, done_bits, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size, s, q,
-                                  s_pos + el * C::PA, s_f + el * C::FS, s_n + el * C::NS, reward, collisions);
+    collision_coop_env_step<A, S, COMPACT>(px, py, done_bits, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size, s, q,
+                                  s_pos + el * C::PA, s_f + el * C::FS, s_n + el * C::NS, s_clip, reward, collisions);
     if (!active) reward = 0.0;                 // collisions is 0 by itself: every agent is on its sentinel
     steps += active ? 1 : 0;
     const float rf = (float)reward;
@@ -452,13 +519,13 @@ __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_rollout_kernel
   }
 }
 
-template <int S>
+template <int S, bool COMPACT>
 static int launch_rollout_s(int A, const CollisionRolloutArgs& a, cudaStream_t st) {
   switch (A) {
 #define SMARL_COOP_CASE(N)                                                                              \
   case N: {                                                                                             \
     using C = CollCoop<N, S>;                                                                           \
-    auto kern = collision_coop_rollout_kernel<N, S>;                                                    \
+    auto kern = collision_coop_rollout_kernel<N, S, COMPACT>;                                                  \
     if (C::kSmem + 64 > 48 * 1024)                                                                      \
       SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem)); \
     const unsigned grid = (unsigned)((a.n_envs + C::EPC - 1) / C::EPC);                                 \
@@ -479,7 +546,10 @@ static int launch_rollout_s(int A, const CollisionRolloutArgs& a, cudaStream_t s
 }
 
 int launch_collision_coop_rollout(int A, int S, const CollisionRolloutArgs& a, cudaStream_t st) {
-  return S == 2 ? launch_rollout_s<2>(A, a, st) : launch_rollout_s<4>(A, a, st);
+  static const char* env = getenv("SMARL_COLL_COMPACT");
+  const bool compact = !env || atoi(env) != 0;
+  if (compact) return S == 2 ? launch_rollout_s<2, true>(A, a, st) : launch_rollout_s<4, true>(A, a, st);
+  return S == 2 ? launch_rollout_s<2, false>(A, a, st) : launch_rollout_s<4, false>(A, a, st);
 }
 #endif
 
