@@ -138,15 +138,16 @@ __global__ void __launch_bounds__(kCongThreads, cong_step_min_blocks(A)) congest
                                              (float)(lam * c3)));
   }
   const int W = a.size + 1;
-  uint32_t off = e0;
+  if (a.wait_reward) {
+    uint32_t off = e0;
 #pragma unroll
-  for (int i = 0; i < A; ++i, off += ld) {
-    float r[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      r[k] = congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
-                               (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W, a.wait_reward);
-    st_stream_f4(a.reward + off, make_float4(r[0], r[1], r[2], r[3]));
+    for (int i = 0; i < A; ++i, off += ld)
+      st_stream_f4(a.reward + off, congestion_reward4<true>(aw[i], conw[i], xw[i], yw[i], a.demand, W, a.wait_reward));
+  } else {
+    uint32_t off = e0;
+#pragma unroll 1
+    for (int i = 0; i < A; ++i, off += ld)
+      st_stream_f4(a.reward + off, congestion_reward4<false>(aw[i], conw[i], xw[i], yw[i], a.demand, W, nullptr));
   }
 }
 
@@ -225,13 +226,11 @@ __global__ void __launch_bounds__(kCongRollThreads, cong_min_blocks(A)) congesti
     if (a.g_mode == 1 && live) st_stream_f4(a.g_scratch + (int64_t)t * ld + e0, make_float4(pen[0], pen[1], pen[2], pen[3]));
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      float r[4];
+      const float4 r4 = a.wait_reward ? congestion_reward4<true>(aw[i], conw[i], xw[i], yw[i], a.demand, W, a.wait_reward)
+                                      : congestion_reward4<false>(aw[i], conw[i], xw[i], yw[i], a.demand, W, nullptr);
+      const float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        r[k] = congestion_reward((aw[i] >> (8 * k)) & 0xFFu, (conw[i] >> (8 * k)) & 0xFFu,
-                                 (xw[i] >> (8 * k)) & 0xFFu, (yw[i] >> (8 * k)) & 0xFFu, a.demand, W, a.wait_reward);
-        s_acc[(i * 4 + k) * kCongRollThreads + tid] += disc * (double)r[k];
-      }
+      for (int k = 0; k < 4; ++k) s_acc[(i * 4 + k) * kCongRollThreads + tid] += disc * (double)r[k];
       if (a.g_mode == 1 && live) {
         st_stream_f4(a.G + ((int64_t)t * A + i) * ld + e0, make_float4(r[0], r[1], r[2], r[3]));
       } else if (a.g_mode == 2 && live) {               // agent.py:129-132

@@ -202,15 +202,54 @@ __device__ __forceinline__ double congestion_reward_f64(uint32_t con, uint32_t n
   return __dadd_rn(__dadd_rn(q, SMARL_AVERAGE_RIDE_COMPENSATION), -SMARL_AVERAGE_RIDE_COST);
 }
 
-// Congestion.reward (congestion.py:82-87) for one agent, rounded to f32 exactly once.  The waiting
-// branch comes from the host-built table wait[con][cell] when given (same f64 expression, same single
-// rounding), otherwise it is evaluated here in f64 in the reference's operation order.
+// Waiting-branch reward from the demand table, out of line: only reached when the caller passed no host-built
+// waiting table.  (Inlined at every (agent, env lane) the float64 division was a third of the step kernels' code.)
+static __device__ __noinline__ float congestion_wait_reward_slow(uint32_t con, uint32_t nx, uint32_t ny,
+                                                                 const double* __restrict__ demand, int W) {
+  return (float)congestion_reward_f64(con, nx, ny, demand, W);
+}
+
+// Congestion.reward (congestion.py:82-87) for the agent in env lane k of the packed words, rounded to f32 exactly
+// once.  Movers (intended action < 4) get -4 - 2 con (exact: small integers); the waiting branch comes from the
+// host-built table wait[con][cell] (the reference's f64 expression, rounded once) through ONE predicated load --
+// no branch: the branchy form cost ~35 instructions per (agent, env) and 43 % of the A = 8 step kernel -- or,
+// without a table, from the out-of-line float64 evaluation.
+template <bool TABLE>
+__device__ __forceinline__ float congestion_reward_lane(uint32_t aw, uint32_t conw, uint32_t xw, uint32_t yw, int k,
+                                                        const double* __restrict__ demand, int W,
+                                                        const float* __restrict__ wait) {
+  const uint32_t sel = 0x4440u | (uint32_t)k;                      // byte k, zero-extended
+  const uint32_t act = __byte_perm(aw, 0u, sel), con = __byte_perm(conw, 0u, sel);
+  const uint32_t nx = __byte_perm(xw, 0u, sel), ny = __byte_perm(yw, 0u, sel);
+  float r = fmaf(-2.0f, (float)con, -4.0f);
+  if (TABLE) {
+    const float* p = wait + (con * (uint32_t)W + nx) * (uint32_t)W + ny;
+    asm("{\n\t.reg .pred q;\n\tsetp.ge.u32 q, %1, 4;\n\t@q ld.global.nc.f32 %0, [%2];\n\t}" : "+f"(r) : "r"(act), "l"(p));
+  } else if (act >= 4u) {
+    r = congestion_wait_reward_slow(con, nx, ny, demand, W);
+  }
+  return r;
+}
+
+// The four env lanes of one agent (TABLE: the host-built waiting table is present -- decided once per kernel, not
+// per reward).
+template <bool TABLE>
+__device__ __forceinline__ float4 congestion_reward4(uint32_t aw, uint32_t conw, uint32_t xw, uint32_t yw,
+                                                     const double* __restrict__ demand, int W,
+                                                     const float* __restrict__ wait) {
+  return make_float4(congestion_reward_lane<TABLE>(aw, conw, xw, yw, 0, demand, W, wait),
+                     congestion_reward_lane<TABLE>(aw, conw, xw, yw, 1, demand, W, wait),
+                     congestion_reward_lane<TABLE>(aw, conw, xw, yw, 2, demand, W, wait),
+                     congestion_reward_lane<TABLE>(aw, conw, xw, yw, 3, demand, W, wait));
+}
+
+// Same for already extracted fields (kept for callers that hold them).
 __device__ __forceinline__ float congestion_reward(uint32_t act, uint32_t con, uint32_t nx, uint32_t ny,
                                                    const double* __restrict__ demand, int W,
                                                    const float* __restrict__ wait) {
   if (act < 4u) return -4.0f - 2.0f * (float)con;                   // exact: small integers
   if (wait) return __ldg(wait + (con * W + nx) * W + ny);
-  return (float)congestion_reward_f64(con, nx, ny, demand, W);
+  return congestion_wait_reward_slow(con, nx, ny, demand, W);
 }
 
 }  // namespace smarl

@@ -108,20 +108,6 @@ __device__ __forceinline__ void congestion_scan(const uint4* __restrict__ rec, c
   }
 }
 
-// Congestion.reward as congestion_reward (congestion.cuh), with the float64 fallback (no host-built waiting table)
-// out of line: inlined at every (agent, env lane) it was a third of this kernel's code.
-static __device__ __noinline__ float congestion_wait_reward_f64(uint32_t con, uint32_t nx, uint32_t ny,
-                                                                const double* __restrict__ demand, int W) {
-  return (float)congestion_reward_f64(con, nx, ny, demand, W);
-}
-__device__ __forceinline__ float congestion_reward_coop(uint32_t act, uint32_t con, uint32_t nx, uint32_t ny,
-                                                        const double* __restrict__ demand, int W,
-                                                        const float* __restrict__ wait) {
-  if (act < 4u) return -4.0f - 2.0f * (float)con;                   // exact: small integers
-  if (wait) return __ldg(wait + (con * W + nx) * W + ny);
-  return congestion_wait_reward_f64(con, nx, ny, demand, W);
-}
-
 template <int A, int S, int MODE>
 __global__ void __launch_bounds__(kCongCoopThreads, 4) congestion_coop_step_kernel(const CongestionStepArgs a) {
   using C = CongCoop<A, S>;
@@ -252,12 +238,9 @@ __global__ void __launch_bounds__(kCongCoopThreads, 4) congestion_coop_step_kern
   for (int j = 0; j < B; ++j) {
     if (C::kGhost && j == B - 1 && j * S + s >= A) continue;
     const uint32_t conw = (r[j] - z[j] - k01) & __umulhi(seen[j], 0xFFu << 25);
-    float rw[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      rw[k] = congestion_reward_coop((aw[j] >> (8 * k)) & 0xFFu, (conw >> (8 * k)) & 0xFFu, (xw[j] >> (8 * k)) & 0xFFu,
-                                (yw[j] >> (8 * k)) & 0xFFu, a.demand, W, a.wait_reward);
-    st_stream_f4(a.reward + (row0 + (uint32_t)(j * S) * ld), make_float4(rw[0], rw[1], rw[2], rw[3]));
+    const float4 rw = a.wait_reward ? congestion_reward4<true>(aw[j], conw, xw[j], yw[j], a.demand, W, a.wait_reward)
+                                    : congestion_reward4<false>(aw[j], conw, xw[j], yw[j], a.demand, W, nullptr);
+    st_stream_f4(a.reward + (row0 + (uint32_t)(j * S) * ld), rw);
   }
 }
 
