@@ -361,6 +361,53 @@ def bench_policy_loop(s, a, dev):
            "value_with_policy": n / (total * 1e-3), "value_env_only": n / ((total - pol_ms) * 1e-3), "unit": UNIT,
            "policy_share": pol_ms / total,
            "policy": "BatchedDiscretePolicy (PyTorch: stacked per-agent 2A->16->5 MLPs, Categorical sampling into env.action_buffer)"}
+    # the same loop with the fused policy kernel (smarl_policy_act_discrete) reading the u8 position rows: no float
+    # observation rows, no [A, E, 16] / [A, E, 5] intermediates
+    from safe_multiagent_rl_b200.policy import FusedDiscretePolicy
+    del pol, buf, env
+    torch.cuda.empty_cache()
+    for tag, Ef in (("policy_fused", E), ("policy_fused_full", a.n_envs)):
+        envf = s.BatchedCoverageDiscrete(S, A, n_envs=Ef, weights=[1.0 + (i % 3) for i in range(A)], device=dev,
+                                         starts=np.zeros((Ef, A, 2), dtype=np.uint8))
+        g = torch.Generator(device=dev); g.manual_seed(99)
+        envf.start_x[:, :Ef] = torch.randint(0, S, (A, Ef), generator=g, device=dev, dtype=torch.uint8)
+        envf.start_y[:, :Ef] = torch.randint(0, S, (A, Ef), generator=g, device=dev, dtype=torch.uint8)
+        envf.emit_obs = False
+        polf = FusedDiscretePolicy(envf, seed=5)
+        buff = envf.new_rollout_buffer(T)
+
+        def batchf(record):
+            envf.reset()
+            for t in range(T):
+                if record:
+                    ev[t][0].record()
+                polf.act(t=t)
+                if record:
+                    ev[t][1].record()
+                envf.step(envf.action_buffer, lambdas=lam, out=(buff, t), agent_major=True)
+                if record:
+                    ev[t][2].record()
+            buff.finish(a.gamma, [25.0] * A)
+        for _ in range(2):
+            batchf(False)
+        torch.cuda.synchronize()
+        e0.record()
+        batchf(True)
+        e1.record()
+        torch.cuda.synchronize()
+        tot = e0.elapsed_time(e1)
+        pm = sum(x[0].elapsed_time(x[1]) for x in ev)
+        em = sum(x[1].elapsed_time(x[2]) for x in ev)
+        nf = float(Ef) * A * T
+        macs = 2.0 * A * 16 + 16 * 5                        # multiply-adds per agent-step of the 2A -> 16 -> 5 MLP
+        out[tag] = {"n_envs": Ef, "ms_per_batch": tot, "policy_ms": pm, "env_step_ms": em,
+                    "value_with_policy": nf / (tot * 1e-3), "unit": UNIT, "policy_share": pm / tot,
+                    "policy_tflops_fp32": 2.0 * macs * nf / (pm * 1e-3) / 1e12,
+                    "slowdown_vs_env_only": tot / (tot - pm),
+                    "policy": "FusedDiscretePolicy (smarl_policy_act_discrete: u8 positions in, u8 actions + f32 log-probs out, "
+                              "weights in shared memory, Philox inverse-CDF sampling); env steps run with obs = NULL"}
+        del envf, polf, buff
+        torch.cuda.empty_cache()
     # BASELINE configs[0] (50 envs) with the policy in the loop, replayed from one CUDA graph
     env1 = s.BatchedCoverageDiscrete(5, 3, n_envs=50, weights=[1.0, 2.0, 3.0], device=dev,
                                      starts=np.random.default_rng(1).integers(0, 5, (50, 3, 2)))

@@ -336,6 +336,37 @@ int smarl_lambda_update(double* lambdas, const double* stats, const double* thre
                         int32_t n_agents, int32_t n_constraints, smarl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * The caller of the env step: the reference's per-agent discrete policies, fused for all envs and agents.
+ * DiscretePolicy (safe_multi_agent_RL/agent.py:23-47): fc1 = Linear(state_space, 16), relu, fc2 = Linear(16, action_space),
+ * softmax, Categorical.sample / log_prob; one network per agent, each fed the joint state
+ * np.array(state).flatten() = (x0, y0, x1, y1, ...) (main.py:30-35, AbstractAgent.act agent.py:118-127).
+ * For the grid envs (CoverageDiscrete, Congestion: state_space = 2 n_agents, action_space = 5) the kernel reads the
+ * u8 position rows the step kernels maintain -- so the step may run with obs = NULL -- and writes the u8 action row
+ * the step consumes plus the f32 log-probability of the sampled action.
+ *   w1 f32 [A][2A][16] (fc1.weight transposed: [in][out]), b1 f32 [A][16], w2 f32 [A][16][5], b2 f32 [A][5]: DEVICE
+ *   pos_x,pos_y u8 [A][ld] in    actions u8 [A][ld] out    logp f32 [A][ld] out (NULL to skip)
+ * Sampling: Philox4x32-10, counter (global env id lo, hi, t | episode << 16, agent), key seed ^ "PLCY" (hi word);
+ * u = ((w0 >> 8) + 0.5) * 2^-24; action = #{c < 4 : sum_{c' <= c} e_c' <= u * sum e}, e_c = exp(logit_c - max).
+ * Streams depend on the global env id, not on sharding.  t in 0..65535.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_agents;        /* A; the observation has 2A components                                   */
+  int32_t hidden;          /* 16 (agent.py:24)                                                       */
+  int32_t n_actions;       /* 5  (env.action_space of the grid envs)                                 */
+  uint32_t episode;        /* mixed into the Philox counter so that episodes draw independent samples */
+  const float* w1;
+  const float* b1;
+  const float* w2;
+  const float* b2;
+  uint64_t seed;
+  int64_t env_offset;      /* global id of env 0 (sharding)                                          */
+  const uint32_t* episode_dev; /* optional device scalar added to `episode` (CUDA-graph replays); NULL = 0 */
+} SmarlDiscretePolicy;
+int smarl_policy_act_discrete(const SmarlDiscretePolicy* p, const uint8_t* pos_x, const uint8_t* pos_y,
+                              uint8_t* actions, float* logp, int32_t t, int64_t n_envs, int64_t ld,
+                              smarl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Multi-GPU: env instances are independent (envs/coverage.py:19, congestion.py:22,
  * collision_avoidance.py:60), so ranks own contiguous ranges of global env ids and the data path has no
  * collective.  The only exchange is the sum of the stats vectors before MetaAgent.update

@@ -102,3 +102,31 @@ def random_starts(kind, size, seed, env_ids, episode, n_rows, zoom=None, row_off
     elif kind == 3:
         xy = np.floor(xy * zoom) / zoom
     return xy
+
+
+def policy_uniforms(seed, env_ids, t, n_agents, episode=0):
+    """u [E, A] of smarl_policy_act_discrete: Philox counter (env id lo, hi, t | episode << 16, agent), key
+    (seed lo, seed hi ^ "PLCY"); u = ((w0 >> 8) + 0.5) * 2**-24 (exactly representable in float32)."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    tw = (int(t) | (int(episode) << 16)) & 0xFFFFFFFF
+    o = philox4x32_10((env_ids & MASK)[:, None], (env_ids >> np.uint64(32))[:, None], np.full((1, 1), tw, dtype=np.uint64),
+                      np.arange(n_agents, dtype=np.uint64)[None, :], seed & 0xFFFFFFFF,
+                      ((seed >> 32) & 0xFFFFFFFF) ^ 0x504C4359)
+    return ((o[0] >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
+
+
+def policy_sample(logits, u):
+    """Inverse-CDF Categorical sample as the kernel draws it: logits [..., C] (float64), u [...]:
+    a = #{c < C-1 : cumsum(e)[c] <= u * sum(e)}, e = exp(logits - max).  Returns (actions, log_prob of them,
+    margin) where margin is the relative distance of u * sum(e) to the nearest CDF step (ties are measure-zero; the
+    float32 kernel may legitimately differ where margin is below its rounding)."""
+    logits = np.asarray(logits, dtype=np.float64)
+    m = logits.max(axis=-1, keepdims=True)
+    e = np.exp(logits - m)
+    s = e.sum(axis=-1)
+    cum = np.cumsum(e, axis=-1)[..., :-1]
+    target = (np.asarray(u, dtype=np.float64) * s)[..., None]
+    a = (cum <= target).sum(axis=-1)
+    logp = np.take_along_axis(logits - m - np.log(s)[..., None], a[..., None], axis=-1)[..., 0]
+    margin = np.abs(cum - target).min(axis=-1) / s
+    return a, logp, margin

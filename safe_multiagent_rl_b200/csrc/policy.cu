@@ -1,0 +1,211 @@
+// Fused per-agent discrete policies for the grid envs (sm_100a): the caller of the env step.
+//
+// Replaces, for n_envs envs and all agents at once, DiscretePolicy.forward / act of the reference
+// (safe_multi_agent_RL/agent.py:23-47, called per agent and step from main.py:30-35 through
+// AbstractAgent.act :118-127): every agent a owns an MLP  obs[2A] -> relu(fc1) [16] -> fc2 [5] -> softmax  fed the
+// JOINT state np.array(state).flatten() = (x0, y0, x1, y1, ...), samples an action from the Categorical and keeps
+// its log-probability.
+//
+// The PyTorch glue (policy.py) materialises [A, E, 16] hiddens and [A, E, 5] logits in HBM and launches a dozen
+// kernels per step; at 2^18 envs x 16 agents it takes 98 % of the closed loop.  Here one kernel reads the u8
+// position rows the env step kernels maintain (2 B per agent, NOT the float observation), keeps every agent's
+// weights in shared memory, and writes the u8 action row and the f32 log-prob row: ~7 B per agent-step of HBM
+// traffic.  The work is 2A*16 + 16*5 multiply-adds per agent-step on the FP32 pipes (592 at A = 16), which is what
+// bounds it: this is a small dense contraction evaluated exactly in fp32 on CUDA cores (the tensor cores would need
+// a 3-way bf16 split of the weights to keep the 1e-5 log-prob parity; not done here).
+//
+// Thread mapping: one thread = one agent x four consecutive envs (64 hidden accumulators in registers); a CTA =
+// all A agents x QPT env quads, looping over tiles of 4*QPT envs (persistent grid), so the weights are staged once
+// per CTA.  Per input k a thread issues one LDS.128 for the four envs' value and four LDS.128 for the 16 weights
+// (both conflict-free broadcasts) against 64 FFMA.
+//
+// Sampling: Philox4x32-10 with counter (global env id lo, hi, t | episode << 16, agent) and key seed ^ "PLCY"
+// gives one uniform u = (w + 0.5) * 2^-32 per (env, step, agent); the action is the inverse CDF of the softmax,
+// a = #{c : sum_{c' <= c} e_c' <= u * sum_c e_c}.  Streams do not depend on sharding.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace smarl {
+
+constexpr int kPolHidden = 16;
+constexpr int kPolActions = 5;
+
+struct PolicyArgs {
+  const uint8_t* pos_x;
+  const uint8_t* pos_y;
+  uint8_t* actions;
+  float* logp;
+  const float* w1;     // [A][2A][16]
+  const float* b1;     // [A][16]
+  const float* w2;     // [A][16][5]
+  const float* b2;     // [A][5]
+  uint64_t seed;
+  int64_t env_offset;
+  int64_t n_envs;
+  int64_t ld;
+  int64_t n_tiles;
+  uint32_t t_word;     // t | episode << 16
+  const uint32_t* episode_dev;
+};
+
+template <int A>
+struct PolCfg {
+  static constexpr int IN = 2 * A;
+  // env quads per tile: all A agents x QPT quads = one CTA of 96..256 threads
+  static constexpr int QPT = A >= 16 ? 8 : (A >= 8 ? 16 : (A >= 4 ? 32 : 64));
+  static constexpr int THREADS = A * QPT;
+  static constexpr int TE = 4 * QPT;                          // envs per tile
+  static constexpr int W1S = IN * kPolHidden + 4;             // floats per agent (+4: agents land on different banks)
+  static constexpr int W2S = kPolHidden * kPolActions + 4;
+  static constexpr size_t kSmemFloats = (size_t)A * W1S + (size_t)A * W2S + (size_t)A * kPolHidden + (size_t)A * 8 +
+                                        (size_t)IN * TE;
+};
+
+template <int A>
+__global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel(const PolicyArgs a) {
+  using C = PolCfg<A>;
+  constexpr int IN = C::IN, QPT = C::QPT, TE = C::TE, H = kPolHidden, NA = kPolActions;
+  extern __shared__ float s_mem[];
+  float* s_w1 = s_mem;                               // [A][W1S]  w1[a][k][u]
+  float* s_w2 = s_w1 + A * C::W1S;                   // [A][W2S]  w2[a][u][c]
+  float* s_b1 = s_w2 + A * C::W2S;                   // [A][16]
+  float* s_b2 = s_b1 + A * H;                        // [A][8]
+  float* s_in = s_b2 + A * 8;                        // [IN][TE] the joint observation of the tile, as floats
+  const int tid = threadIdx.x;
+  for (int i = tid; i < A * IN * H; i += C::THREADS) s_w1[(i / (IN * H)) * C::W1S + i % (IN * H)] = __ldg(a.w1 + i);
+  for (int i = tid; i < A * H * NA; i += C::THREADS) s_w2[(i / (H * NA)) * C::W2S + i % (H * NA)] = __ldg(a.w2 + i);
+  for (int i = tid; i < A * H; i += C::THREADS) s_b1[i] = __ldg(a.b1 + i);
+  for (int i = tid; i < A * NA; i += C::THREADS) s_b2[(i / NA) * 8 + i % NA] = __ldg(a.b2 + i);
+  const int ag = tid / QPT, quad = tid % QPT;
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x504C4359u);   // "PLCY"
+  const uint32_t t_word = a.t_word + ((a.episode_dev ? __ldg(a.episode_dev) : 0u) << 16);
+  const float* w1 = s_w1 + ag * C::W1S;
+  const float* w2 = s_w2 + ag * C::W2S;
+
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int64_t e_tile = tile * TE;
+    __syncthreads();                                 // previous tile fully consumed (and the weights staged)
+    // stage the tile's positions as floats: row 2i = x_i, row 2i+1 = y_i (main.py:33: np.array(state).flatten())
+    for (int i = tid; i < IN * QPT; i += C::THREADS) {
+      const int row = i / QPT, qd = i % QPT;
+      const int64_t e = e_tile + 4 * qd;
+      const uint8_t* src = (row & 1) ? a.pos_y : a.pos_x;
+      const uint32_t w = e < a.ld ? ld_stream_u32(src + (int64_t)(row >> 1) * a.ld + e) : 0u;
+      *reinterpret_cast<float4*>(s_in + row * TE + 4 * qd) = bytes_to_float4(w);
+    }
+    __syncthreads();
+    const int64_t e0 = e_tile + 4 * quad;
+    // fc1 + relu (agent.py:33): h[k][u] for the four envs k of this thread
+    float h[4][H];
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+      const float b = s_b1[ag * H + u];
+      h[0][u] = h[1][u] = h[2][u] = h[3][u] = b;
+    }
+#pragma unroll 4
+    for (int k = 0; k < IN; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(s_in + k * TE + 4 * quad);
+      const float4* wr = reinterpret_cast<const float4*>(w1 + k * H);
+#pragma unroll
+      for (int v = 0; v < H / 4; ++v) {
+        const float4 w = wr[v];
+        const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[0][4 * v + j] = fmaf(x.x, ww[j], h[0][4 * v + j]);
+          h[1][4 * v + j] = fmaf(x.y, ww[j], h[1][4 * v + j]);
+          h[2][4 * v + j] = fmaf(x.z, ww[j], h[2][4 * v + j]);
+          h[3][4 * v + j] = fmaf(x.w, ww[j], h[3][4 * v + j]);
+        }
+      }
+    }
+    // fc2 (agent.py:34), softmax (:35), Categorical sample + log_prob (:44-46)
+    uint32_t act4 = 0u;
+    float lp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float l[NA];
+#pragma unroll
+      for (int c = 0; c < NA; ++c) l[c] = s_b2[ag * 8 + c];
+#pragma unroll
+      for (int u = 0; u < H; ++u) {
+        const float r = fmaxf(h[k][u], 0.f);
+#pragma unroll
+        for (int c = 0; c < NA; ++c) l[c] = fmaf(r, w2[u * NA + c], l[c]);
+      }
+      float m = l[0];
+#pragma unroll
+      for (int c = 1; c < NA; ++c) m = fmaxf(m, l[c]);
+      float ex[NA], sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NA; ++c) {
+        ex[c] = expf(l[c] - m);
+        sum += ex[c];
+      }
+      const uint64_t id = (uint64_t)(a.env_offset + e0 + k);
+      const uint4 o = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), t_word, (uint32_t)ag), key);
+      const float target = ((float)(o.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;     // u * sum, u from the top 24 bits
+      float cum = 0.f;
+      int pick = 0;
+      float l_pick = l[0];
+#pragma unroll
+      for (int c = 0; c < NA - 1; ++c) {
+        cum += ex[c];
+        if (cum <= target) {
+          pick = c + 1;
+          l_pick = l[c + 1];
+        }
+      }
+      act4 |= (uint32_t)pick << (8 * k);
+      lp[k] = (l_pick - m) - logf(sum);               // log_softmax at the sampled action
+    }
+    if (e0 < a.ld) {
+      st_stream_u32(a.actions + (int64_t)ag * a.ld + e0, act4);
+      if (a.logp) st_stream_f4(a.logp + (int64_t)ag * a.ld + e0, make_float4(lp[0], lp[1], lp[2], lp[3]));
+    }
+  }
+}
+
+}  // namespace smarl
+
+using namespace smarl;
+
+extern "C" int smarl_policy_act_discrete(const SmarlDiscretePolicy* p, const uint8_t* pos_x, const uint8_t* pos_y,
+                                         uint8_t* actions, float* logp, int32_t t, int64_t n_envs, int64_t ld,
+                                         smarl_stream_t stream) {
+  SMARL_REQUIRE(p != nullptr, "policy params is NULL");
+  if (int rc = check_layout(n_envs, ld)) return rc;
+  SMARL_REQUIRE(p->n_agents >= 1 && p->n_agents <= SMARL_MAX_AGENTS, "n_agents=%d outside 1..32", p->n_agents);
+  SMARL_REQUIRE(p->hidden == kPolHidden && p->n_actions == kPolActions,
+                "only the reference's DiscretePolicy shape (hidden 16, 5 actions) is built (got %d, %d)", p->hidden,
+                p->n_actions);
+  SMARL_REQUIRE(p->w1 && p->b1 && p->w2 && p->b2 && pos_x && pos_y && actions, "null pointer");
+  SMARL_REQUIRE(t >= 0 && t < 65536, "t=%d outside 0..65535", t);
+  SMARL_REQUIRE(aligned16(pos_x) && aligned16(pos_y) && aligned16(actions) && aligned16(logp), "pointers must be 16-byte aligned");
+  PolicyArgs a;
+  a.pos_x = pos_x; a.pos_y = pos_y; a.actions = actions; a.logp = logp; a.w1 = p->w1; a.b1 = p->b1; a.w2 = p->w2;
+  a.b2 = p->b2; a.seed = p->seed; a.env_offset = p->env_offset; a.n_envs = n_envs; a.ld = ld;
+  a.t_word = (uint32_t)t | (p->episode << 16); a.episode_dev = p->episode_dev;
+  int dev = 0, sms = 148;
+  SMARL_CUDA(cudaGetDevice(&dev));
+  SMARL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  SMARL_DISPATCH_A(p->n_agents, {
+    using C = PolCfg<kA>;
+    auto kern = policy_act_discrete_kernel<kA>;
+    const size_t smem = C::kSmemFloats * sizeof(float);
+    if (smem > 227 * 1024) {
+      set_error("policy weights of %d agents need %zu bytes of shared memory", kA, smem);
+      return SMARL_EUNSUPPORTED;
+    }
+    if (smem > 48 * 1024) SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SMARL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
+    a.n_tiles = (ld + C::TE - 1) / C::TE;
+    const int64_t grid = a.n_tiles < (int64_t)sms * per_sm ? a.n_tiles : (int64_t)sms * per_sm;
+    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
+  });
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}

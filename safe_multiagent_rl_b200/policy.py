@@ -59,6 +59,47 @@ class BatchedDiscretePolicy(nn.Module):
         return self.dist(obs).log_prob(actions)
 
 
+class FusedDiscretePolicy(BatchedDiscretePolicy):
+    """``BatchedDiscretePolicy`` whose ``act`` is ONE libsmarl kernel (smarl_policy_act_discrete): it reads the env's u8
+    position rows (not the float observation: the env may run with ``emit_obs = False``), evaluates every agent's
+    2A -> 16 -> 5 MLP with the weights in shared memory, samples the Categorical with a Philox stream keyed by
+    (global env id, episode, step, agent) and writes ``env.action_buffer`` and the log-probabilities -- about 7 bytes
+    of HBM traffic per agent-step instead of the [A, E, 16] / [A, E, 5] intermediates of the PyTorch forward.
+    ``log_prob`` / ``dist`` (the differentiable path the learners train through) stay the parent's."""
+
+    def __init__(self, env, hidden_size=16, seed=0):
+        if hidden_size != 16 or env.action_space != 5 or env.state_space != 2 * env.n_agents:
+            raise NotImplementedError("the fused kernel is built for the reference's DiscretePolicy on the grid envs: "
+                                      "state_space = 2 n_agents, hidden 16, 5 actions")
+        super().__init__(env, hidden_size)
+        from . import _lib
+        self._lib_mod, self.lib = _lib, _lib.load()
+        self.seed = int(seed)
+        self.logp = torch.zeros(env.n_agents, env.ld, dtype=torch.float32, device=env.device)
+        self._episode_dev = torch.zeros(1, dtype=torch.int32, device=env.device)
+
+    def next_episode(self):
+        """Advance the sampling stream's episode index (a device-side increment: CUDA-graph capturable)."""
+        self._episode_dev.add_(1)
+
+    @torch.no_grad()
+    def act(self, obs=None, t=None):
+        """Sample actions for step ``t`` (default: the env's step counter) into ``env.action_buffer``; returns
+        (action_buffer, actions [A, E] uint8 view, log_prob [A, E] view).  ``obs`` is ignored: the kernel reads
+        ``env.pos_x`` / ``env.pos_y``."""
+        import ctypes as C
+        env, L = self.env, self._lib_mod
+        w = [t_.detach() for t_ in (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)]
+        assert all(x.is_contiguous() and x.dtype == torch.float32 for x in w)
+        p = L.DiscretePolicyParams(env.n_agents, 16, 5, 0, L.ptr(w[0]), L.ptr(w[1]), L.ptr(w[2]), L.ptr(w[3]),
+                                   self.seed & (2 ** 64 - 1), env.env_offset, L.ptr(self._episode_dev))
+        L.check(self.lib.smarl_policy_act_discrete(C.byref(p), L.ptr(env.pos_x), L.ptr(env.pos_y),
+                                                   L.ptr(env.action_buffer), L.ptr(self.logp),
+                                                   int(env.t if t is None else t), env.n_envs, env.ld, L.stream_ptr()))
+        E = env.n_envs
+        return env.action_buffer, env.action_buffer[:, :E], self.logp[:, :E]
+
+
 class BatchedGaussianPolicy(nn.Module):
     """``ContinuousPolicy`` (agent.py:50-76) x n_agents: diagonal Gaussian with variance relu(.) + 1e-4."""
 
