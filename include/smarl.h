@@ -46,7 +46,7 @@ enum {
 };
 
 typedef void* smarl_stream_t;   /* cudaStream_t */
-enum { SMARL_ENV_COVERAGE = 0, SMARL_ENV_CONGESTION = 1, SMARL_ENV_COLLISION = 2 };
+enum { SMARL_ENV_COVERAGE = 0, SMARL_ENV_CONGESTION = 1, SMARL_ENV_COLLISION = 2, SMARL_KERNEL_POLICY = 3 };
 
 int smarl_abi_version(void);
 const char* smarl_last_error(void);
@@ -57,7 +57,10 @@ int smarl_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * lane-cooperative kernels that split one env over 2 or 4 lanes of a warp; by default the library picks the
  * measured-fastest mapping per (env kind, n_agents).  lanes: -1 = automatic (default), 0 = one thread per env
  * (Collision) / per four envs (grid envs), 2 or 4 = force the cooperative kernels where they exist (n_agents >= 9).
- * env_kind is SMARL_ENV_COVERAGE / _CONGESTION / _COLLISION.  Process-wide; returns the previous setting. */
+ * env_kind is SMARL_ENV_COVERAGE / _CONGESTION / _COLLISION.  With env_kind = SMARL_KERNEL_POLICY the knob picks the
+ * build of smarl_policy_act_discrete: -1 = automatic (tensor cores), 0 = FP32 pipes only (packed FFMA2), 1 = fc1 on
+ * the tensor cores (tcgen05.mma, accumulators in tensor memory) with groups of up to 16 agents per CTA, 2 = the same
+ * with groups of up to 8.  Process-wide; returns the previous setting. */
 int smarl_set_kernel_variant(int32_t env_kind, int32_t lanes);
 
 /* ------------------------------------------------------------------------------------
@@ -345,9 +348,13 @@ int smarl_lambda_update(double* lambdas, const double* stats, const double* thre
  * the step consumes plus the f32 log-probability of the sampled action.
  *   w1 f32 [A][2A][16] (fc1.weight transposed: [in][out]), b1 f32 [A][16], w2 f32 [A][16][5], b2 f32 [A][5]: DEVICE
  *   pos_x,pos_y u8 [A][ld] in    actions u8 [A][ld] out    logp f32 [A][ld] out (NULL to skip)
- * Sampling: Philox4x32-10, counter (global env id lo, hi, t | episode << 16, agent), key seed ^ "PLCY" (hi word);
- * u = ((w0 >> 8) + 0.5) * 2^-24; action = #{c < 4 : sum_{c' <= c} e_c' <= u * sum e}, e_c = exp(logit_c - max).
- * Streams depend on the global env id, not on sharding.  t in 0..65535.
+ * Sampling: Philox4x32-10, counter (global env id lo, hi, t | episode << 16, agent >> 2), key seed ^ "PLCY" (hi word):
+ * one block serves four consecutive agents, agent a takes word w[a & 3]; u = ((w >> 8) + 0.5) * 2^-24;
+ * action = #{c < 4 : sum_{c' <= c} e_c' <= u * sum e}, e_c = exp(logit_c - max).
+ * Streams depend on the global env id, not on sharding or on the kernel build.  t in 0..65535.
+ * Two builds (smarl_set_kernel_variant(SMARL_KERNEL_POLICY, ...)): all multiply-adds on the FP32 pipes, or fc1 as one
+ * tcgen05 GEMM per 128-env tile (bf16 positions are exact, every fp32 weight enters as three bf16 pieces, f32
+ * accumulation in tensor memory); log-probabilities of the two agree to ~1e-6.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
   int32_t n_agents;        /* A; the observation has 2A components                                   */

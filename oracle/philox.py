@@ -105,14 +105,16 @@ def random_starts(kind, size, seed, env_ids, episode, n_rows, zoom=None, row_off
 
 
 def policy_uniforms(seed, env_ids, t, n_agents, episode=0):
-    """u [E, A] of smarl_policy_act_discrete: Philox counter (env id lo, hi, t | episode << 16, agent), key
-    (seed lo, seed hi ^ "PLCY"); u = ((w0 >> 8) + 0.5) * 2**-24 (exactly representable in float32)."""
+    """u [E, A] of smarl_policy_act_discrete: Philox counter (env id lo, hi, t | episode << 16, agent >> 2), key
+    (seed lo, seed hi ^ "PLCY"); agent a takes word a & 3 of its block; u = ((w >> 8) + 0.5) * 2**-24 (exactly
+    representable in float32)."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     tw = (int(t) | (int(episode) << 16)) & 0xFFFFFFFF
     o = philox4x32_10((env_ids & MASK)[:, None], (env_ids >> np.uint64(32))[:, None], np.full((1, 1), tw, dtype=np.uint64),
-                      np.arange(n_agents, dtype=np.uint64)[None, :], seed & 0xFFFFFFFF,
+                      (np.arange(n_agents, dtype=np.uint64) >> np.uint64(2))[None, :], seed & 0xFFFFFFFF,
                       ((seed >> 32) & 0xFFFFFFFF) ^ 0x504C4359)
-    return ((o[0] >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
+    w = np.stack(o, axis=0)[np.arange(n_agents) & 3, :, np.arange(n_agents)].T          # [E, A]: word a & 3
+    return ((w >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
 
 
 def policy_sample(logits, u):

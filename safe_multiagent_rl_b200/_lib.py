@@ -119,6 +119,7 @@ PROTOTYPES = {
 
 COST_U8, COST_I32, COST_F32 = 0, 1, 2
 ENV_COVERAGE, ENV_CONGESTION, ENV_COLLISION = 0, 1, 2
+KERNEL_POLICY = 3          # smarl_set_kernel_variant: 0 = FP32 pipes, 1 / 2 = tensor cores (groups of <= 16 / <= 8 agents)
 _lib = None
 
 

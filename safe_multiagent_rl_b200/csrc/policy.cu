@@ -19,35 +19,20 @@
 // per CTA.  Per input k a thread issues one LDS.128 for the four envs' value and four LDS.128 for the 16 weights
 // (both conflict-free broadcasts) against 64 FFMA.
 //
-// Sampling: Philox4x32-10 with counter (global env id lo, hi, t | episode << 16, agent) and key seed ^ "PLCY"
-// gives one uniform u = (w + 0.5) * 2^-32 per (env, step, agent); the action is the inverse CDF of the softmax,
-// a = #{c : sum_{c' <= c} e_c' <= u * sum_c e_c}.  Streams do not depend on sharding.
+// Sampling (policy.cuh, shared with the tensor-core build): Philox4x32-10 with counter (global env id lo, hi,
+// t | episode << 16, agent >> 2) and key seed ^ "PLCY"; agent a takes word a & 3, u = ((w >> 8) + 0.5) * 2^-24; the
+// action is the inverse CDF of the softmax, a = #{c : sum_{c' <= c} e_c' <= u * sum_c e_c}.  Streams do not depend
+// on sharding, nor on which of the two builds runs.
+//
+// This file is the FP32-pipe build (all 592 multiply-adds as packed FFMA2, two per issue slot); policy_tc.cu puts fc1
+// on the tensor cores.  smarl_set_kernel_variant(SMARL_KERNEL_POLICY, 0 / 1 / 2) forces one; by default the
+// tensor-core build serves every shape it fits.
 #include <math.h>
 
-#include "common.cuh"
+#include "policy.cuh"
+#include "tc.cuh"
 
 namespace smarl {
-
-constexpr int kPolHidden = 16;
-constexpr int kPolActions = 5;
-
-struct PolicyArgs {
-  const uint8_t* pos_x;
-  const uint8_t* pos_y;
-  uint8_t* actions;
-  float* logp;
-  const float* w1;     // [A][2A][16]
-  const float* b1;     // [A][16]
-  const float* w2;     // [A][16][5]
-  const float* b2;     // [A][5]
-  uint64_t seed;
-  int64_t env_offset;
-  int64_t n_envs;
-  int64_t ld;
-  int64_t n_tiles;
-  uint32_t t_word;     // t | episode << 16
-  const uint32_t* episode_dev;
-};
 
 template <int A>
 struct PolCfg {
@@ -78,7 +63,7 @@ __global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel
   for (int i = tid; i < A * H; i += C::THREADS) s_b1[i] = __ldg(a.b1 + i);
   for (int i = tid; i < A * NA; i += C::THREADS) s_b2[(i / NA) * 8 + i % NA] = __ldg(a.b2 + i);
   const int ag = tid / QPT, quad = tid % QPT;
-  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x504C4359u);   // "PLCY"
+  const uint2 key = policy_key(a.seed);
   const uint32_t t_word = a.t_word + ((a.episode_dev ? __ldg(a.episode_dev) : 0u) << 16);
   const float* w1 = s_w1 + ag * C::W1S;
   const float* w2 = s_w2 + ag * C::W2S;
@@ -96,31 +81,29 @@ __global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel
     }
     __syncthreads();
     const int64_t e0 = e_tile + 4 * quad;
-    // fc1 + relu (agent.py:33): h[k][u] for the four envs k of this thread
-    float h[4][H];
+    // fc1 (agent.py:33) as packed FFMA2: h2[k][p] = (h[k][2p], h[k][2p+1]) for the four envs k of this thread
+    float2 h2[4][H / 2];
 #pragma unroll
-    for (int u = 0; u < H; ++u) {
-      const float b = s_b1[ag * H + u];
-      h[0][u] = h[1][u] = h[2][u] = h[3][u] = b;
+    for (int p = 0; p < H / 2; ++p) {
+      const float2 b = *reinterpret_cast<const float2*>(s_b1 + ag * H + 2 * p);
+      h2[0][p] = h2[1][p] = h2[2][p] = h2[3][p] = b;
     }
 #pragma unroll 4
     for (int k = 0; k < IN; ++k) {
       const float4 x = *reinterpret_cast<const float4*>(s_in + k * TE + 4 * quad);
+      const float2 xx[4] = {make_float2(x.x, x.x), make_float2(x.y, x.y), make_float2(x.z, x.z), make_float2(x.w, x.w)};
       const float4* wr = reinterpret_cast<const float4*>(w1 + k * H);
 #pragma unroll
       for (int v = 0; v < H / 4; ++v) {
         const float4 w = wr[v];
-        const float ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          h[0][4 * v + j] = fmaf(x.x, ww[j], h[0][4 * v + j]);
-          h[1][4 * v + j] = fmaf(x.y, ww[j], h[1][4 * v + j]);
-          h[2][4 * v + j] = fmaf(x.z, ww[j], h[2][4 * v + j]);
-          h[3][4 * v + j] = fmaf(x.w, ww[j], h[3][4 * v + j]);
+        for (int e = 0; e < 4; ++e) {
+          h2[e][2 * v] = tc::ffma2(xx[e], make_float2(w.x, w.y), h2[e][2 * v]);
+          h2[e][2 * v + 1] = tc::ffma2(xx[e], make_float2(w.z, w.w), h2[e][2 * v + 1]);
         }
       }
     }
-    // fc2 (agent.py:34), softmax (:35), Categorical sample + log_prob (:44-46)
+    // relu, fc2 (agent.py:34), softmax (:35), Categorical sample + log_prob (:44-46)
     uint32_t act4 = 0u;
     float lp[4];
 #pragma unroll
@@ -130,35 +113,15 @@ __global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel
       for (int c = 0; c < NA; ++c) l[c] = s_b2[ag * 8 + c];
 #pragma unroll
       for (int u = 0; u < H; ++u) {
-        const float r = fmaxf(h[k][u], 0.f);
+        const float r = fmaxf((u & 1) ? h2[k][u >> 1].y : h2[k][u >> 1].x, 0.f);
 #pragma unroll
         for (int c = 0; c < NA; ++c) l[c] = fmaf(r, w2[u * NA + c], l[c]);
       }
-      float m = l[0];
-#pragma unroll
-      for (int c = 1; c < NA; ++c) m = fmaxf(m, l[c]);
-      float ex[NA], sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < NA; ++c) {
-        ex[c] = expf(l[c] - m);
-        sum += ex[c];
-      }
       const uint64_t id = (uint64_t)(a.env_offset + e0 + k);
-      const uint4 o = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), t_word, (uint32_t)ag), key);
-      const float target = ((float)(o.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;     // u * sum, u from the top 24 bits
-      float cum = 0.f;
-      int pick = 0;
-      float l_pick = l[0];
-#pragma unroll
-      for (int c = 0; c < NA - 1; ++c) {
-        cum += ex[c];
-        if (cum <= target) {
-          pick = c + 1;
-          l_pick = l[c + 1];
-        }
-      }
+      const uint4 o = policy_words(id, t_word, ag >> 2, key);
+      int pick;
+      policy_head(l, word_of(o, ag & 3), pick, lp[k]);
       act4 |= (uint32_t)pick << (8 * k);
-      lp[k] = (l_pick - m) - logf(sum);               // log_softmax at the sampled action
     }
     if (e0 < a.ld) {
       st_stream_u32(a.actions + (int64_t)ag * a.ld + e0, act4);
@@ -191,6 +154,10 @@ extern "C" int smarl_policy_act_discrete(const SmarlDiscretePolicy* p, const uin
   SMARL_CUDA(cudaGetDevice(&dev));
   SMARL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t st = (cudaStream_t)stream;
+  // fc1 on the tensor cores (policy_tc.cu) unless the FP32-pipe build is forced: -1 / 1 = groups of up to 16 agents
+  // per CTA, 2 = groups of up to 8
+  const int variant = kernel_variant(SMARL_KERNEL_POLICY);
+  if (variant != 0) return launch_policy_tc(a, p->n_agents, variant == 2 ? 8 : 16, sms, st);
   SMARL_DISPATCH_A(p->n_agents, {
     using C = PolCfg<kA>;
     auto kern = policy_act_discrete_kernel<kA>;

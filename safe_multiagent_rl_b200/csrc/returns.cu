@@ -20,8 +20,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_variant[3] = {-1, -1, -1};
-int kernel_variant(int env_kind) { return (env_kind >= 0 && env_kind < 3) ? g_variant[env_kind] : -1; }
+static int g_variant[4] = {-1, -1, -1, -1};
+int kernel_variant(int env_kind) { return (env_kind >= 0 && env_kind < 4) ? g_variant[env_kind] : -1; }
 
 int check_layout(int64_t n_envs, int64_t ld) {
   SMARL_REQUIRE(n_envs >= 1, "n_envs=%lld must be >= 1", (long long)n_envs);
@@ -459,9 +459,10 @@ extern "C" int smarl_abi_version(void) { return SMARL_ABI_VERSION; }
 extern "C" const char* smarl_last_error(void) { return g_error; }
 
 extern "C" int smarl_set_kernel_variant(int32_t env_kind, int32_t lanes) {
-  if (env_kind < 0 || env_kind >= 3) return -1;
+  if (env_kind < 0 || env_kind >= 4) return -1;
   const int prev = g_variant[env_kind];
-  g_variant[env_kind] = (lanes == 0 || lanes == 2 || lanes == 4) ? lanes : -1;
+  if (env_kind == SMARL_KERNEL_POLICY) g_variant[env_kind] = (lanes >= 0 && lanes <= 2) ? lanes : -1;
+  else g_variant[env_kind] = (lanes == 0 || lanes == 2 || lanes == 4) ? lanes : -1;
   return prev;
 }
 

@@ -34,12 +34,17 @@ def reference_logits(pol, obs):
         return pol.logits(obs.double().float()).double().cpu().numpy()          # [A, E, 5]
 
 
-@pytest.mark.parametrize("A,E", [(3, 50), (16, 1000), (8, 333), (32, 70), (1, 20), (5, 4099)])
-def test_fused_policy_matches_torch_logprobs_and_the_philox_oracle(A, E):
+# builds of the kernel (smarl_set_kernel_variant): 0 = FP32 pipes (FFMA2), 1 / 2 = fc1 on the tensor cores
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("A,E", [(3, 50), (16, 1000), (8, 333), (32, 70), (1, 20), (5, 4099), (12, 260), (20, 129),
+                                 (17, 128), (24, 500)])
+def test_fused_policy_matches_torch_logprobs_and_the_philox_oracle(A, E, variant):
+    from safe_multiagent_rl_b200 import _lib
     env, pol = make(A, E, env_offset=5_000_000_000)
     obs = env.reset()
     for t in (0, 1, 7):
-        _, act, logp = pol.act(t=t)
+        with _lib.kernel_variant(_lib.KERNEL_POLICY, variant):
+            _, act, logp = pol.act(t=t)
         act_np, logp_np = act.cpu().numpy().astype(np.int64), logp.cpu().numpy()
         assert act_np.min() >= 0 and act_np.max() <= 4
         # (i) the log-probability of the sampled action, against the PyTorch glue on the float observation
@@ -55,6 +60,29 @@ def test_fused_policy_matches_torch_logprobs_and_the_philox_oracle(A, E):
         # every action is drawn with roughly its probability (the stream is not degenerate)
         assert len(np.unique(act_np)) >= (3 if A * E > 200 else 1)
         obs, _, _, _ = env.step(env.action_buffer, agent_major=True)
+
+
+@pytest.mark.parametrize("A,E,size,kind", [(16, 70_001, 32, "coverage"), (8, 33_000, 200, "congestion"),
+                                           (32, 9_000, 64, "coverage"), (3, 50_000, 5, "coverage")])
+def test_tensor_core_and_fp32_builds_agree(A, E, size, kind):
+    """The two builds draw from the same Philox stream and evaluate the same network: identical actions except where
+    the uniform sits within float32 rounding of a CDF step, log-probabilities within 2e-5 x the scale of the
+    observations (fc1 on the tensor cores is f32-grade: exact bf16 positions x three bf16 pieces per weight, f32
+    accumulation; only the order of the f32 additions differs)."""
+    from safe_multiagent_rl_b200 import _lib
+    env, pol = make(A, E, size=size, env_offset=123, kind=kind)
+    env.reset()
+    out = {}
+    for variant in (0, 1, 2):
+        with _lib.kernel_variant(_lib.KERNEL_POLICY, variant):
+            _, act, logp = pol.act(t=5)
+            out[variant] = (act.clone(), logp.clone())
+    for variant in (1, 2):
+        same = (out[variant][0] == out[0][0])
+        assert same.float().mean().item() > 0.9995
+        d = (out[variant][1] - out[0][1]).abs()[same]
+        assert d.max().item() < 2e-5 * max(1.0, size / 16), d.max().item()
+    assert torch.equal(out[1][0], out[2][0]) or (out[1][0] == out[2][0]).float().mean().item() > 0.9999
 
 
 def test_streams_follow_global_env_ids_and_episodes():
