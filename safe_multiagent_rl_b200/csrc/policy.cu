@@ -59,9 +59,9 @@ __global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel
   float* s_in = s_b2 + A * 8;                        // [IN][TE] the joint observation of the tile, as floats
   const int tid = threadIdx.x;
   for (int i = tid; i < A * IN * H; i += C::THREADS) s_w1[(i / (IN * H)) * C::W1S + i % (IN * H)] = __ldg(a.w1 + i);
-  for (int i = tid; i < A * H * NA; i += C::THREADS) s_w2[(i / (H * NA)) * C::W2S + i % (H * NA)] = __ldg(a.w2 + i);
+  for (int i = tid; i < A * H * NA; i += C::THREADS) s_w2[(i / (H * NA)) * C::W2S + i % (H * NA)] = __ldg(a.w2 + i) * kLog2e;   // logits in log2 units (policy_head)
   for (int i = tid; i < A * H; i += C::THREADS) s_b1[i] = __ldg(a.b1 + i);
-  for (int i = tid; i < A * NA; i += C::THREADS) s_b2[(i / NA) * 8 + i % NA] = __ldg(a.b2 + i);
+  for (int i = tid; i < A * NA; i += C::THREADS) s_b2[(i / NA) * 8 + i % NA] = __ldg(a.b2 + i) * kLog2e;
   const int ag = tid / QPT, quad = tid % QPT;
   const uint2 key = policy_key(a.seed);
   const uint32_t t_word = a.t_word + ((a.episode_dev ? __ldg(a.episode_dev) : 0u) << 16);
@@ -154,10 +154,10 @@ extern "C" int smarl_policy_act_discrete(const SmarlDiscretePolicy* p, const uin
   SMARL_CUDA(cudaGetDevice(&dev));
   SMARL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t st = (cudaStream_t)stream;
-  // fc1 on the tensor cores (policy_tc.cu) unless the FP32-pipe build is forced: -1 / 1 = groups of up to 16 agents
-  // per CTA, 2 = groups of up to 8
+  // fc1 on the tensor cores (policy_tc.cu) unless the FP32-pipe build is forced: -1 / 2 = groups of up to 8 agents and
+  // two env tiles per CTA iteration, 1 = groups of up to 16 agents and one tile
   const int variant = kernel_variant(SMARL_KERNEL_POLICY);
-  if (variant != 0) return launch_policy_tc(a, p->n_agents, variant == 2 ? 8 : 16, sms, st);
+  if (variant != 0) return launch_policy_tc(a, p->n_agents, variant == 1 ? 16 : 8, sms, st);
   SMARL_DISPATCH_A(p->n_agents, {
     using C = PolCfg<kA>;
     auto kern = policy_act_discrete_kernel<kA>;

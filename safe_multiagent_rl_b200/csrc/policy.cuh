@@ -8,6 +8,7 @@ namespace smarl {
 
 constexpr int kPolHidden = 16;
 constexpr int kPolActions = 5;
+constexpr float kLog2e = 1.4426950408889634f;
 
 struct PolicyArgs {
   const uint8_t* pos_x;
@@ -43,30 +44,43 @@ __device__ __forceinline__ uint32_t word_of(const uint4& o, int i) {
   return i == 0 ? o.x : (i == 1 ? o.y : (i == 2 ? o.z : o.w));
 }
 
-// softmax (agent.py:35), Categorical sample by inverse CDF and log_prob (:44-46) of one agent and env.
-// u = ((word >> 8) + 0.5) * 2^-24; action = #{c < 4 : sum_{c' <= c} e_c' <= u * sum e}, e_c = exp(l_c - max l).
-__device__ __forceinline__ void policy_head(const float (&l)[kPolActions], uint32_t word, int& pick, float& logp) {
-  float m = l[0];
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// softmax (agent.py:35), Categorical sample by inverse CDF and log_prob (:44-46) of one agent and env.  The logits
+// arrive in log2 units, l2_c = log2(e) * logit_c (both builds scale their shared-memory copies of fc2 by log2(e)), so
+// e_c = exp(logit_c - max) is one subtraction and one MUFU.EX2:
+// u = ((word >> 8) + 0.5) * 2^-24; action = #{c < 4 : sum_{c' <= c} e_c' <= u * sum e}.
+__device__ __forceinline__ void policy_head(const float (&l2)[kPolActions], uint32_t word, int& pick, float& logp) {
+  float m = l2[0];
 #pragma unroll
-  for (int c = 1; c < kPolActions; ++c) m = fmaxf(m, l[c]);
+  for (int c = 1; c < kPolActions; ++c) m = fmaxf(m, l2[c]);
   float ex[kPolActions], sum = 0.f;
 #pragma unroll
   for (int c = 0; c < kPolActions; ++c) {
-    ex[c] = __expf(l[c] - m);
+    ex[c] = ex2_ftz(l2[c] - m);
     sum += ex[c];
   }
   const float target = ((float)(word >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;
-  float cum = 0.f, l_pick = l[0];
+  float cum = 0.f, l_pick = l2[0];
   pick = 0;
 #pragma unroll
   for (int c = 0; c < kPolActions - 1; ++c) {
     cum += ex[c];
     if (cum <= target) {
       pick = c + 1;
-      l_pick = l[c + 1];
+      l_pick = l2[c + 1];
     }
   }
-  logp = (l_pick - m) - __logf(sum);                 // log_softmax at the sampled action
+  logp = ((l_pick - m) - lg2_ftz(sum)) * 0.693147180559945309f;     // log_softmax at the sampled action (sum >= 1)
 }
 #endif
 

@@ -28,43 +28,58 @@
 
 namespace smarl {
 
-template <int A, int GMAX>
+template <int A, int GMAX, int R>
 struct TcCfg {
   static constexpr int H = kPolHidden, NA = kPolActions;
   static constexpr int NGROUPS = (A + GMAX - 1) / GMAX;                    // agent groups; a CTA serves one
   static constexpr int GA = NGROUPS == 1 ? A : (((A + NGROUPS - 1) / NGROUPS + 3) & ~3);   // agents per group (multiple of 4 when split)
-  static constexpr int NWG = GA > 8 ? 2 : 1;                               // warpgroups sharing the accumulator tile
-  static constexpr int N = H * GA;                                         // accumulator columns = MMA N
-  static constexpr int COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
-  static constexpr int KST = (2 * A + 15) / 16;                            // K steps (16 inputs each) per weight piece
-  static constexpr int ACH = 2 * KST + 2;                                  // K chunks of the X image (+ the bias step)
+  static constexpr bool RAGGED = NGROUPS * GA != A;                        // the last group holds fewer agents
+  static constexpr int NWG = GA > 4 ? 2 : 1;                               // warpgroups sharing the accumulator tiles
+  static constexpr int AW = NWG == 1 ? GA : ((((GA + NWG - 1) / NWG) + 3) & ~3);   // agents per warpgroup
+  static constexpr bool FULL = !RAGGED && NWG * AW == GA;                  // every (warpgroup, agent slot) exists
+  static constexpr int N = H * GA;                                         // accumulator columns per tile = MMA N
+  static constexpr int COLS = R * N <= 32 ? 32 : (R * N <= 64 ? 64 : (R * N <= 128 ? 128 : (R * N <= 256 ? 256 : 512)));
+  static constexpr int KIN = 2 * A;                                        // observation components
+  static constexpr int KST = (KIN + 15) / 16;                              // K steps (16 inputs each) per weight piece
+  static constexpr int ACH = 2 * KST + 2;                                  // K chunks of one X image (+ the bias step)
   static constexpr int BCH = 6 * KST + 2;                                  // K chunks of the W1 image: 3 pieces + bias step
   static constexpr int THREADS = 128 * NWG;
-  static constexpr int AW = NWG == 1 ? GA : ((((GA + NWG - 1) / NWG) + 3) & ~3);   // agents per warpgroup
+  static constexpr int ROWS = 128 * R;                                     // envs per CTA iteration
   static constexpr int W2S = H * NA + 8;                                   // floats per agent: w2t[c][u], b2[5], pad
   static constexpr uint32_t A_CHUNK = 128 * 16, B_CHUNK = N * 16;          // bytes per K chunk
-  static constexpr size_t kSmemA = (size_t)ACH * A_CHUNK;
+  static constexpr uint32_t A_TILE = ACH * A_CHUNK;
+  static constexpr size_t kSmemA = (size_t)R * A_TILE;
   static constexpr size_t kSmemB = (size_t)BCH * B_CHUNK;
+  static constexpr size_t kSmemRaw = (size_t)16 * KST * ROWS;              // u8 [16 KST][ROWS]: the raw position rows
   static constexpr size_t kSmemW2 = (size_t)GA * W2S * sizeof(float);
-  static constexpr size_t kSmem = kSmemA + kSmemB + kSmemW2 + 128;
+  static constexpr size_t kSmem = kSmemA + kSmemB + kSmemRaw + kSmemW2 + 128;
   static_assert(N % 16 == 0 && N >= 16 && N <= 256, "MMA N out of range");
+  static_assert(R * N <= 512, "accumulators exceed tensor memory");
 };
 
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 
-template <int A, int GMAX>
-__global__ void __launch_bounds__(TcCfg<A, GMAX>::THREADS) policy_act_discrete_tc_kernel(const PolicyArgs a) {
-  using C = TcCfg<A, GMAX>;
-  constexpr int NWG = C::NWG, H = C::H, NA = C::NA, N = C::N, KST = C::KST, GA = C::GA, AW = C::AW;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;                              // 0 source bytes: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int A, int GMAX, int R>
+__global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discrete_tc_kernel(const PolicyArgs a) {
+  using C = TcCfg<A, GMAX, R>;
+  constexpr int NWG = C::NWG, H = C::H, NA = C::NA, N = C::N, KST = C::KST, GA = C::GA, AW = C::AW, ROWS = C::ROWS;
   extern __shared__ __align__(128) uint8_t s_raw[];
-  uint8_t* s_a = s_raw;                                             // X image   [ACH][16 row groups][8][16 B]
+  uint8_t* s_a = s_raw;                                             // X images  [R][ACH][16 row groups][8][16 B]
   uint8_t* s_b = s_a + C::kSmemA;                                   // W1 image  [BCH][N / 8][8][16 B]
-  float* s_w2 = reinterpret_cast<float*>(s_b + C::kSmemB);          // [GA][W2S]
+  uint8_t* s_pos = s_b + C::kSmemB;                                 // raw u8    [16 KST][ROWS]
+  float* s_w2 = reinterpret_cast<float*>(s_pos + C::kSmemRaw);      // [GA][W2S], scaled by log2(e)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_w2) + C::kSmemW2);
   uint32_t* s_slot = reinterpret_cast<uint32_t*>(s_bar + 1);
   const int tid = threadIdx.x;
   const int a0 = blockIdx.y * GA;                                   // first agent of this CTA's group
-  const int n_real = (A - a0) < GA ? (A - a0) : GA;                 // agents of the group that exist
+  const int n_real = C::RAGGED ? ((A - a0) < GA ? (A - a0) : GA) : GA;   // agents of the group that exist
 
   // ---- one-time setup: barrier, tensor memory, the bf16 images of the group's weights ---------------------------
   if (tid == 0) tc::mbar_init(s_bar, 1);
@@ -74,7 +89,7 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX>::THREADS) policy_act_discrete_t
     constexpr int KP = 16 * KST;
     for (int i = tid; i < GA * KP * H; i += C::THREADS) {
       const int u = i % H, k = (i / H) % KP, j = i / (H * KP);
-      float w = (j < n_real && k < 2 * A) ? __ldg(a.w1 + ((size_t)(a0 + j) * (2 * A) + k) * H + u) : 0.f;
+      float w = (j < n_real && k < C::KIN) ? __ldg(a.w1 + ((size_t)(a0 + j) * C::KIN + k) * H + u) : 0.f;
       const int n = j * H + u;
       uint8_t* dst = s_b + (size_t)(k >> 3) * C::B_CHUNK + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
 #pragma unroll
@@ -96,13 +111,16 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX>::THREADS) policy_act_discrete_t
       uint8_t* dst = s_b + (size_t)(6 * KST + (kk >> 3)) * C::B_CHUNK + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
       *reinterpret_cast<uint16_t*>(dst) = bf16_bits(v);
     }
-    // X image, constant part: chunk 2 KST = (1, 1, 1, 0, ...) for every env row, chunk 2 KST + 1 zeros
-    for (int i = tid; i < 2 * 128; i += C::THREADS) {
+    // X images, constant part: chunk 2 KST = (1, 1, 1, 0, ...) for every env row, chunk 2 KST + 1 zeros
+    for (int i = tid; i < R * 2 * 128; i += C::THREADS) {
+      const int r = i / 256, q = i % 256;
       const uint32_t one2 = 0x3F803F80u;                            // two bf16 ones
-      const uint4 v = i < 128 ? make_uint4(one2, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(s_a + (size_t)2 * KST * C::A_CHUNK + (size_t)i * 16) = v;
+      const uint4 v = q < 128 ? make_uint4(one2, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(s_a + (size_t)r * C::A_TILE + (size_t)2 * KST * C::A_CHUNK + (size_t)q * 16) = v;
     }
-    // fc2: w2t[c][u] (pairs along u feed FFMA2), then b2
+    // raw position rows beyond the 2A real ones stay zero (K padding)
+    for (int i = tid; i < (int)(C::kSmemRaw / 16); i += C::THREADS) reinterpret_cast<uint4*>(s_pos)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // fc2 in log2 units (policy_head): w2t[c][u] * log2(e) (pairs along u feed FFMA2), then b2 * log2(e)
     for (int i = tid; i < GA * C::W2S; i += C::THREADS) {
       const int j = i / C::W2S, r = i % C::W2S;
       float v = 0.f;
@@ -110,7 +128,7 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX>::THREADS) policy_act_discrete_t
         if (r < H * NA) v = __ldg(a.w2 + ((size_t)(a0 + j) * H + r % H) * NA + r / H);
         else if (r < H * NA + NA) v = __ldg(a.b2 + (size_t)(a0 + j) * NA + (r - H * NA));
       }
-      s_w2[i] = v;
+      s_w2[i] = v * kLog2e;
     }
   }
   tc::fence_async_smem();
@@ -126,103 +144,130 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX>::THREADS) policy_act_discrete_t
   const uint32_t idesc = tc::idesc_bf16_f32(128, N);
   const uint32_t sa_addr = tc::smem_u32(s_a), sb_addr = tc::smem_u32(s_b);
   const int j_lo = wg * AW;                                         // first local agent of this warpgroup
+  const float* w2_lo = s_w2 + j_lo * C::W2S;
+  const uint32_t ld32 = (uint32_t)a.ld;
+  const bool want_logp = a.logp != nullptr;
   uint32_t phase = 0;
 
-  // The observation bytes of a tile (4 agents x (x, y) per K chunk, this thread's env row) are fetched one tile ahead
-  // into registers, so their global-memory latency hides behind the previous tile's epilogue.
-  constexpr int NCH = (2 * KST + NWG - 1) / NWG;                    // K chunks staged by one thread
-  uint32_t raw[NCH][8];
-  auto fetch = [&](int64_t tile) {
-    const int64_t e = tile * 128 + row;
-    const bool live = e < a.ld;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = wg + i * NWG;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int ag = 4 * c + q;
-        const bool on = c < 2 * KST && ag < A && live;
-        raw[i][2 * q] = on ? (uint32_t)__ldg(a.pos_x + (int64_t)ag * a.ld + e) : 0u;
-        raw[i][2 * q + 1] = on ? (uint32_t)__ldg(a.pos_y + (int64_t)ag * a.ld + e) : 0u;
-      }
+  // The raw u8 position rows of the next ROWS envs travel global -> shared with cp.async (16 envs per copy) while the
+  // current envs are in the epilogue; rows past ld are zero-filled.
+  auto fetch = [&](int64_t st) {
+    const int64_t e_base = st * ROWS;
+    for (int i = tid; i < C::KIN * (ROWS / 16); i += C::THREADS) {
+      const int k = i / (ROWS / 16), q = i % (ROWS / 16);
+      const int64_t e = e_base + 16 * q;
+      const bool valid = e < a.ld;
+      const uint8_t* src = ((k & 1) ? a.pos_y : a.pos_x) + (valid ? (int64_t)(k >> 1) * a.ld + e : 0);
+      cp_async16(s_pos + (size_t)k * ROWS + 16 * q, src, valid);
     }
+    cp_async_commit();
   };
   if ((int64_t)blockIdx.x < a.n_tiles) fetch(blockIdx.x);
 
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int64_t e = tile * 128 + row;
-    const bool live = e < a.ld;
-    // ---- stage the tile's joint observation as bf16: element k = 2 i is x_i, k = 2 i + 1 is y_i (main.py:33) -----
+  for (int64_t st = blockIdx.x; st < a.n_tiles; st += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- the joint observation as bf16 K-major images: element k = 2 i is x_i, k = 2 i + 1 is y_i (main.py:33) ----
+    for (int i = tid; i < ROWS * 2 * KST; i += C::THREADS) {
+      const int rr = i % ROWS, c = i / ROWS;
+      uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = wg + i * NWG;
-      if (c < 2 * KST) {
-        uint32_t w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const __nv_bfloat162 p = __floats2bfloat162_rn((float)raw[i][2 * q], (float)raw[i][2 * q + 1]);
-          w[q] = *reinterpret_cast<const uint32_t*>(&p);
-        }
-        *reinterpret_cast<uint4*>(s_a + (size_t)c * C::A_CHUNK + (size_t)row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int q = 0; q < 4; ++q) {
+        const float x = (float)s_pos[(size_t)(8 * c + 2 * q) * ROWS + rr], y = (float)s_pos[(size_t)(8 * c + 2 * q + 1) * ROWS + rr];
+        const __nv_bfloat162 p = __floats2bfloat162_rn(x, y);
+        w[q] = *reinterpret_cast<const uint32_t*>(&p);
       }
+      *reinterpret_cast<uint4*>(s_a + (size_t)(rr >> 7) * C::A_TILE + (size_t)c * C::A_CHUNK + (size_t)(rr & 127) * 16) =
+          make_uint4(w[0], w[1], w[2], w[3]);
     }
     tc::fence_async_smem();
-    tc::fence_before_sync();              // also orders the previous tile's tcgen05.ld before the MMAs that overwrite it
+    tc::fence_before_sync();              // also orders the previous epilogue's tcgen05.ld before the MMAs that overwrite it
     __syncthreads();
     // ---- fc1 on the tensor cores: one elected thread issues, pieces lo -> mid -> hi, then the bias step ---------
     if (tid == 0) {
       tc::fence_after_sync();
 #pragma unroll
-      for (int piece = 2; piece >= 0; --piece)
+      for (int r = 0; r < R; ++r) {
+        const uint32_t sa_r = sa_addr + r * C::A_TILE, d_r = tmem + r * N;
 #pragma unroll
-        for (int ks = 0; ks < KST; ++ks)
-          tc::mma_bf16(tmem, tc::smem_desc(sa_addr + 2 * ks * C::A_CHUNK, C::A_CHUNK, 128),
-                       tc::smem_desc(sb_addr + (piece * 2 * KST + 2 * ks) * C::B_CHUNK, C::B_CHUNK, 128), idesc,
-                       !(piece == 2 && ks == 0));
-      tc::mma_bf16(tmem, tc::smem_desc(sa_addr + 2 * KST * C::A_CHUNK, C::A_CHUNK, 128),
-                   tc::smem_desc(sb_addr + 6 * KST * C::B_CHUNK, C::B_CHUNK, 128), idesc, true);
+        for (int piece = 2; piece >= 0; --piece)
+#pragma unroll
+          for (int ks = 0; ks < KST; ++ks)
+            tc::mma_bf16(d_r, tc::smem_desc(sa_r + 2 * ks * C::A_CHUNK, C::A_CHUNK, 128),
+                         tc::smem_desc(sb_addr + (piece * 2 * KST + 2 * ks) * C::B_CHUNK, C::B_CHUNK, 128), idesc,
+                         !(piece == 2 && ks == 0));
+        tc::mma_bf16(d_r, tc::smem_desc(sa_r + 2 * KST * C::A_CHUNK, C::A_CHUNK, 128),
+                     tc::smem_desc(sb_addr + 6 * KST * C::B_CHUNK, C::B_CHUNK, 128), idesc, true);
+      }
       tc::mma_commit(s_bar);
     }
-    if (tile + gridDim.x < a.n_tiles) fetch(tile + gridDim.x);
+    if (st + gridDim.x < a.n_tiles) fetch(st + gridDim.x);
     tc::mbar_wait(s_bar, phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    // ---- epilogue out of tensor memory: relu, fc2, softmax, sample, log_prob ---------------------------------
-    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t hr[2][16];
-    if (j_lo < n_real) tc::tmem_ld16_raw(t_lane + (uint32_t)(j_lo * H), hr[0]);
+    // ---- epilogue out of tensor memory: relu, fc2, softmax, sample, log_prob; a thread owns row `row` of each of the
+    //      R tiles, so every fc2 weight it loads serves R envs ---------------------------------------------------
+    const int64_t e0 = st * ROWS + row;
+    uint32_t idx[R];                                                // element index of (agent, env) in actions / logp
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      live[r] = e0 + 128 * r < a.ld;
+      idx[r] = (uint32_t)(a0 + j_lo) * ld32 + (uint32_t)(e0 + 128 * r);
+    }
+    uint4 rnd[R];
 #pragma unroll
     for (int jj = 0; jj < AW; ++jj) {
-      const int j = j_lo + jj;
-      if (j < n_real) {
-        tc::tmem_ld_wait_regs(hr[jj & 1]);
-        if (jj + 1 < AW && j + 1 < n_real) tc::tmem_ld16_raw(t_lane + (uint32_t)((j + 1) * H), hr[(jj + 1) & 1]);
-        const int ag = a0 + j;
-        if ((jj & 3) == 0) rnd = policy_words((uint64_t)(a.env_offset + e), t_word, ag >> 2, key);
-        const float* w2 = s_w2 + j * C::W2S;
-        float2 acc[NA];
+      if (C::FULL || j_lo + jj < n_real) {
+        uint32_t hr[R][16];
 #pragma unroll
-        for (int c = 0; c < NA; ++c) acc[c] = make_float2(w2[H * NA + c], 0.f);
+        for (int r = 0; r < R; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)(r * N + (j_lo + jj) * H), hr[r]);
+        const int ag = a0 + j_lo + jj;
+        if ((jj & 3) == 0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) rnd[r] = policy_words((uint64_t)(a.env_offset + e0 + 128 * r), t_word, ag >> 2, key);
+        }
+        const float* w2 = w2_lo + jj * C::W2S;
+        float2 acc[R][NA];
+#pragma unroll
+        for (int c = 0; c < NA; ++c) {
+          const float b = w2[H * NA + c];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r][c] = make_float2(b, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) tc::tmem_ld_wait_regs(hr[r]);
 #pragma unroll
         for (int p4 = 0; p4 < H / 4; ++p4) {
-          const float r0 = fmaxf(__uint_as_float(hr[jj & 1][4 * p4 + 0]), 0.f), r1 = fmaxf(__uint_as_float(hr[jj & 1][4 * p4 + 1]), 0.f);
-          const float r2 = fmaxf(__uint_as_float(hr[jj & 1][4 * p4 + 2]), 0.f), r3 = fmaxf(__uint_as_float(hr[jj & 1][4 * p4 + 3]), 0.f);
+          float2 ra[R], rb[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            ra[r] = make_float2(fmaxf(__uint_as_float(hr[r][4 * p4 + 0]), 0.f), fmaxf(__uint_as_float(hr[r][4 * p4 + 1]), 0.f));
+            rb[r] = make_float2(fmaxf(__uint_as_float(hr[r][4 * p4 + 2]), 0.f), fmaxf(__uint_as_float(hr[r][4 * p4 + 3]), 0.f));
+          }
 #pragma unroll
           for (int c = 0; c < NA; ++c) {
             const float4 w = *reinterpret_cast<const float4*>(w2 + c * H + 4 * p4);
-            acc[c] = tc::ffma2(make_float2(r0, r1), make_float2(w.x, w.y), acc[c]);
-            acc[c] = tc::ffma2(make_float2(r2, r3), make_float2(w.z, w.w), acc[c]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r][c] = tc::ffma2(ra[r], make_float2(w.x, w.y), acc[r][c]);
+              acc[r][c] = tc::ffma2(rb[r], make_float2(w.z, w.w), acc[r][c]);
+            }
           }
         }
-        float l[NA];
 #pragma unroll
-        for (int c = 0; c < NA; ++c) l[c] = acc[c].x + acc[c].y;
-        int pick;
-        float lp;
-        policy_head(l, word_of(rnd, jj & 3), pick, lp);
-        if (live) {
-          a.actions[(int64_t)ag * a.ld + e] = (uint8_t)pick;
-          if (a.logp) a.logp[(int64_t)ag * a.ld + e] = lp;
+        for (int r = 0; r < R; ++r) {
+          float l2[NA];
+#pragma unroll
+          for (int c = 0; c < NA; ++c) l2[c] = acc[r][c].x + acc[r][c].y;
+          int pick;
+          float lp;
+          policy_head(l2, word_of(rnd[r], jj & 3), pick, lp);
+          if (live[r]) {
+            a.actions[idx[r]] = (uint8_t)pick;
+            if (want_logp) a.logp[idx[r]] = lp;
+          }
+          idx[r] += ld32;
         }
       }
     }
@@ -232,11 +277,11 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX>::THREADS) policy_act_discrete_t
   if (tid < 32) tc::tmem_dealloc(tmem, C::COLS);
 }
 
-template <int A, int GMAX>
+template <int A, int GMAX, int R>
 static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
-  using C = TcCfg<A, GMAX>;
+  using C = TcCfg<A, GMAX, R>;
   PolicyArgs a = a_in;
-  auto kern = policy_act_discrete_tc_kernel<A, GMAX>;
+  auto kern = policy_act_discrete_tc_kernel<A, GMAX, R>;
   // At most 512 / COLS CTAs of tensor memory fit an SM: size the shared-memory request so that no more than that
   // become resident (a surplus CTA would spin in tcgen05.alloc until a resident one exits).
   const int tmem_ctas = 512 / C::COLS;
@@ -245,6 +290,10 @@ static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
   if (smem < floor_smem) smem = floor_smem;
   if (smem > 227 * 1024) {
     set_error("tensor-core policy: %d agents need %zu bytes of shared memory", A, smem);
+    return SMARL_EUNSUPPORTED;
+  }
+  if ((uint64_t)A * (uint64_t)a.ld >= (1ull << 32)) {
+    set_error("tensor-core policy: n_agents * ld = %llu does not fit 32-bit element indices", (unsigned long long)A * a.ld);
     return SMARL_EUNSUPPORTED;
   }
   SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -258,7 +307,7 @@ static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
   if (per_sm > by_regs) per_sm = by_regs;
   if (per_sm > 2048 / C::THREADS) per_sm = 2048 / C::THREADS;
   if (per_sm < 1) per_sm = 1;
-  a.n_tiles = (a.n_envs + 127) / 128;
+  a.n_tiles = (a.n_envs + C::ROWS - 1) / C::ROWS;                   // CTA iterations of ROWS envs
   int64_t gx = (int64_t)sms * per_sm / C::NGROUPS;
   if (gx < 1) gx = 1;
   if (gx > a.n_tiles) gx = a.n_tiles;
@@ -271,10 +320,8 @@ static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
 // (128 columns, one warpgroup, more CTAs per SM; the tile's observation is staged once per group).
 template <int A>
 static int launch_tc_any(const PolicyArgs& a, int group_max, int sms, cudaStream_t st) {
-  if constexpr (A > 8) {
-    if (group_max == 8) return launch_tc<A, 8>(a, sms, st);
-  }
-  return launch_tc<A, 16>(a, sms, st);
+  if (group_max == 16) return launch_tc<A, 16, 1>(a, sms, st);
+  return launch_tc<A, 8, 2>(a, sms, st);
 }
 
 int launch_policy_tc(const PolicyArgs& a, int n_agents, int group_max, int sms, cudaStream_t st) {
