@@ -366,7 +366,10 @@ def bench_policy_loop(s, a, dev):
     from safe_multiagent_rl_b200.policy import FusedDiscretePolicy
     del pol, buf, env
     torch.cuda.empty_cache()
-    for tag, Ef in (("policy_fused", E), ("policy_fused_full", a.n_envs)):
+    from safe_multiagent_rl_b200 import _lib as L_
+    # policy_fused / policy_fused_full: the default build (fc1 on the tensor cores, tcgen05 + TMEM);
+    # policy_fused_fp32_pipes: the FP32-pipe build of the same kernel, for comparison
+    for tag, Ef, variant in (("policy_fused", E, -1), ("policy_fused_full", a.n_envs, -1), ("policy_fused_fp32_pipes", E, 0)):
         envf = s.BatchedCoverageDiscrete(S, A, n_envs=Ef, weights=[1.0 + (i % 3) for i in range(A)], device=dev,
                                          starts=np.zeros((Ef, A, 2), dtype=np.uint8))
         g = torch.Generator(device=dev); g.manual_seed(99)
@@ -388,13 +391,14 @@ def bench_policy_loop(s, a, dev):
                 if record:
                     ev[t][2].record()
             buff.finish(a.gamma, [25.0] * A)
-        for _ in range(2):
-            batchf(False)
-        torch.cuda.synchronize()
-        e0.record()
-        batchf(True)
-        e1.record()
-        torch.cuda.synchronize()
+        with L_.kernel_variant(L_.KERNEL_POLICY, variant):
+            for _ in range(2):
+                batchf(False)
+            torch.cuda.synchronize()
+            e0.record()
+            batchf(True)
+            e1.record()
+            torch.cuda.synchronize()
         tot = e0.elapsed_time(e1)
         pm = sum(x[0].elapsed_time(x[1]) for x in ev)
         em = sum(x[1].elapsed_time(x[2]) for x in ev)
@@ -402,10 +406,14 @@ def bench_policy_loop(s, a, dev):
         macs = 2.0 * A * 16 + 16 * 5                        # multiply-adds per agent-step of the 2A -> 16 -> 5 MLP
         out[tag] = {"n_envs": Ef, "ms_per_batch": tot, "policy_ms": pm, "env_step_ms": em,
                     "value_with_policy": nf / (tot * 1e-3), "unit": UNIT, "policy_share": pm / tot,
-                    "policy_tflops_fp32": 2.0 * macs * nf / (pm * 1e-3) / 1e12,
+                    "policy_tflops_fp32_equivalent": 2.0 * macs * nf / (pm * 1e-3) / 1e12,
                     "slowdown_vs_env_only": tot / (tot - pm),
                     "policy": "FusedDiscretePolicy (smarl_policy_act_discrete: u8 positions in, u8 actions + f32 log-probs out, "
-                              "weights in shared memory, Philox inverse-CDF sampling); env steps run with obs = NULL"}
+                              "Philox inverse-CDF sampling; " +
+                              ("all multiply-adds on the FP32 pipes (packed FFMA2)" if variant == 0 else
+                               "fc1 as tcgen05.mma GEMMs per 256-env tile -- exact bf16 positions x three bf16 pieces per "
+                               "fp32 weight, f32 accumulators in tensor memory -- relu / fc2 / softmax / sampling out of TMEM") +
+                              "); env steps run with obs = NULL"}
         del envf, polf, buff
         torch.cuda.empty_cache()
     # BASELINE configs[0] (50 envs) with the policy in the loop, replayed from one CUDA graph
