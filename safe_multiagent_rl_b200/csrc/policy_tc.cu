@@ -12,15 +12,25 @@
 //     for normal weights), so X*W1 = X*hi + X*mid + X*lo with exact products and f32 accumulation in tensor memory --
 //     three passes over the same A operand with three B operands, smallest pieces first.
 //   * the bias rides along as one more K step: X gets a constant block (1,1,1,0,...) and W1 the rows (b_hi, b_mid, b_lo).
-// Measured error of the pre-activations against float64: a few 1e-7 relative (tools/umma_probe.cu, tests).
-// relu, fc2 (80 multiply-adds, packed FFMA2), softmax, the Philox inverse-CDF sample and log_prob run on the FP32 pipes
-// straight out of tensor memory: a thread owns one env (= one TMEM lane) and walks over its warpgroup's agents, 16
-// accumulator columns (tcgen05.ld.32x32b.x16) per agent.
+// Measured error of the pre-activations against float64: ~5e-8 relative (tools/umma_probe.cu pins the descriptor layout
+// and the accuracy on B200; tests/test_gpu_policy_fused.py holds the log-probabilities to 1e-5 against PyTorch).
+// relu, fc2 (80 multiply-adds as 40 packed FFMA2), softmax, the Philox inverse-CDF sample and log_prob run on the FP32
+// pipes straight out of tensor memory: a thread owns one TMEM lane = one env row of each of the R tiles of the CTA
+// iteration and walks over its warpgroup's agents, 16 accumulator columns (tcgen05.ld.32x32b.x16) per agent and tile,
+// the next agent's columns in flight while it computes.  Every fc2 weight it loads from shared memory (a 512-byte
+// broadcast per LDS.128: tools/fma_probe.cu measures ~8 cycles of the SM's load path each when all four
+// sub-partitions ask) therefore serves R = 2 envs.
 //
-// CTA = NWG warpgroups; one accumulator tile (128 lanes x 16*GA columns) per CTA; several CTAs per SM overlap one
-// CTA's staging + MMA with the others' epilogues (512 TMEM columns per SM).  Persistent over env tiles; the bf16
-// images of the group's weights are built once per CTA in shared memory from the fp32 parameters (no prepared
-// buffers in the ABI).  Operand layout: canonical K-major, no swizzle -- [K chunk of 8][row group of 8][8 rows][16 B].
+// CTA = NWG warpgroups (the same 128 lanes, different agents); a CTA iteration = R tiles of 128 envs for one group of
+// GA <= 8 agents: R * 16 * GA accumulator columns (256 of the SM's 512 at GA = 8, so two CTAs per SM overlap one
+// CTA's staging + MMA with the other's epilogue).  Persistent over the env tiles; the raw u8 position rows of the
+// next iteration travel global -> shared with cp.async during the epilogue and are converted to the bf16 K-major image
+// (canonical no-swizzle layout: [K chunk of 8][row group of 8][8 rows][16 B]) before the MMAs; the bf16 images of the
+// group's weights are built once per CTA from the fp32 parameters (no prepared buffers in the ABI).
+// Measured (B200, 2^20 envs): A = 16: 168 us per launch against 509 us for the FP32-pipe build (policy.cu) and
+// ~1960 us for the PyTorch glue; A = 32: 366 against 1810 us; A = 8: 80 against 175 us; A = 3: 39 against 50 us.
+// The epilogue is what bounds it: ~190 issued instructions per (agent, env) pair of 32 lanes at 54 % issue
+// utilisation (ncu, profiles/r02); the tensor pipe is 7 % busy.
 #include <cuda_bf16.h>
 
 #include "policy.cuh"
@@ -62,6 +72,12 @@ __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_us
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
   const uint32_t n = valid ? 16u : 0u;                              // 0 source bytes: the 16 destination bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void st_u8_if(uint8_t* p, uint32_t v, bool on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.u8 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"((uint32_t)on) : "memory");
+}
+__device__ __forceinline__ void st_f32_if(float* p, float v, bool on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((uint32_t)on) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -209,19 +225,23 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
     //      R tiles, so every fc2 weight it loads serves R envs ---------------------------------------------------
     const int64_t e0 = st * ROWS + row;
     uint32_t idx[R];                                                // element index of (agent, env) in actions / logp
-    bool live[R];
+    bool live[R], live_lp[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       live[r] = e0 + 128 * r < a.ld;
+      live_lp[r] = live[r] && want_logp;
       idx[r] = (uint32_t)(a0 + j_lo) * ld32 + (uint32_t)(e0 + 128 * r);
     }
     uint4 rnd[R];
+    uint32_t hbuf[2][R][16];                                        // the next agent's columns load while this one computes
+    if (C::FULL || j_lo < n_real) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)(r * N + j_lo * H), hbuf[0][r]);
+    }
 #pragma unroll
     for (int jj = 0; jj < AW; ++jj) {
       if (C::FULL || j_lo + jj < n_real) {
-        uint32_t hr[R][16];
-#pragma unroll
-        for (int r = 0; r < R; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)(r * N + (j_lo + jj) * H), hr[r]);
+        uint32_t (&hr)[R][16] = hbuf[jj & 1];
         const int ag = a0 + j_lo + jj;
         if ((jj & 3) == 0) {
 #pragma unroll
@@ -237,6 +257,10 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) tc::tmem_ld_wait_regs(hr[r]);
+        if (jj + 1 < AW && (C::FULL || j_lo + jj + 1 < n_real)) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)(r * N + (j_lo + jj + 1) * H), hbuf[(jj + 1) & 1][r]);
+        }
 #pragma unroll
         for (int p4 = 0; p4 < H / 4; ++p4) {
           float2 ra[R], rb[R];
@@ -263,10 +287,10 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
           int pick;
           float lp;
           policy_head(l2, word_of(rnd[r], jj & 3), pick, lp);
-          if (live[r]) {
-            a.actions[idx[r]] = (uint8_t)pick;
-            if (want_logp) a.logp[idx[r]] = lp;
-          }
+          // predicated stores, no branch: the whole epilogue of an iteration stays one basic block, so the softmax /
+          // sampling chain of one agent is scheduled under the next agent's fc2
+          st_u8_if(a.actions + idx[r], (uint32_t)pick, live[r]);
+          st_f32_if(a.logp + idx[r], lp, live_lp[r]);
           idx[r] += ld32;
         }
       }

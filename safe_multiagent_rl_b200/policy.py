@@ -62,9 +62,12 @@ class BatchedDiscretePolicy(nn.Module):
 class FusedDiscretePolicy(BatchedDiscretePolicy):
     """``BatchedDiscretePolicy`` whose ``act`` is ONE libsmarl kernel (smarl_policy_act_discrete): it reads the env's u8
     position rows (not the float observation: the env may run with ``emit_obs = False``), evaluates every agent's
-    2A -> 16 -> 5 MLP with the weights in shared memory, samples the Categorical with a Philox stream keyed by
-    (global env id, episode, step, agent) and writes ``env.action_buffer`` and the log-probabilities -- about 7 bytes
-    of HBM traffic per agent-step instead of the [A, E, 16] / [A, E, 5] intermediates of the PyTorch forward.
+    2A -> 16 -> 5 MLP -- fc1 as tcgen05 tensor-core GEMMs over 256-env tiles with f32-grade accuracy (exact bf16
+    positions x three bf16 pieces per fp32 weight, f32 accumulators in tensor memory), the rest on the FP32 pipes out of
+    tensor memory -- samples the Categorical with a Philox stream keyed by (global env id, episode, step, agent) and
+    writes ``env.action_buffer`` and the log-probabilities: about 7 bytes of HBM traffic per agent-step instead of the
+    [A, E, 16] / [A, E, 5] intermediates of the PyTorch forward.  ``_lib.kernel_variant(_lib.KERNEL_POLICY, 0)`` forces
+    the FP32-pipe build of the kernel.
     ``log_prob`` / ``dist`` (the differentiable path the learners train through) stay the parent's."""
 
     def __init__(self, env, hidden_size=16, seed=0):
