@@ -38,7 +38,7 @@
 
 namespace smarl {
 
-template <int A, int GMAX, int R>
+template <int A, int GMAX, int R, int RT>
 struct TcCfg {
   static constexpr int H = kPolHidden, NA = kPolActions;
   static constexpr int NGROUPS = (A + GMAX - 1) / GMAX;                    // agent groups; a CTA serves one
@@ -53,7 +53,8 @@ struct TcCfg {
   static constexpr int KST = (KIN + 15) / 16;                              // K steps (16 inputs each) per weight piece
   static constexpr int ACH = 2 * KST + 2;                                  // K chunks of one X image (+ the bias step)
   static constexpr int BCH = 6 * KST + 2;                                  // K chunks of the W1 image: 3 pieces + bias step
-  static constexpr int THREADS = 128 * NWG;
+  static constexpr int NWR = R / RT;                                       // warpgroup sets along the tiles: a thread owns RT of the R tiles
+  static constexpr int THREADS = 128 * NWG * NWR;
   static constexpr int ROWS = 128 * R;                                     // envs per CTA iteration
   static constexpr int W2S = H * NA + 8;                                   // floats per agent: w2t[c][u], b2[5], pad
   static constexpr uint32_t A_CHUNK = 128 * 16, B_CHUNK = N * 16;          // bytes per K chunk
@@ -65,6 +66,7 @@ struct TcCfg {
   static constexpr size_t kSmem = kSmemA + kSmemB + kSmemRaw + kSmemW2 + 128;
   static_assert(N % 16 == 0 && N >= 16 && N <= 256, "MMA N out of range");
   static_assert(R * N <= 512, "accumulators exceed tensor memory");
+  static_assert(R % RT == 0, "tiles per thread must divide the tiles per CTA");
 };
 
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
@@ -82,9 +84,10 @@ __device__ __forceinline__ void st_f32_if(float* p, float v, bool on) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int A, int GMAX, int R>
-__global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discrete_tc_kernel(const PolicyArgs a) {
-  using C = TcCfg<A, GMAX, R>;
+template <int A, int GMAX, int R, int RT>
+__global__ void __launch_bounds__(TcCfg<A, GMAX, R, RT>::THREADS, TcCfg<A, GMAX, R, RT>::THREADS >= 512 ? 2 : 0)
+    policy_act_discrete_tc_kernel(const PolicyArgs a) {
+  using C = TcCfg<A, GMAX, R, RT>;
   constexpr int NWG = C::NWG, H = C::H, NA = C::NA, N = C::N, KST = C::KST, GA = C::GA, AW = C::AW, ROWS = C::ROWS;
   extern __shared__ __align__(128) uint8_t s_raw[];
   uint8_t* s_a = s_raw;                                             // X images  [R][ACH][16 row groups][8][16 B]
@@ -153,7 +156,8 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
   tc::fence_after_sync();
   const uint32_t tmem = *s_slot;
 
-  const int wg = tid >> 7, row = tid & 127;
+  const int wg = (tid >> 7) % NWG, row = tid & 127;                 // agent warpgroup, TMEM lane
+  const int r_lo = ((tid >> 7) / NWG) * RT;                         // first of this thread's RT tiles
   const uint32_t t_lane = tmem + ((uint32_t)(row & ~31) << 16);     // this warp's 32 TMEM lanes
   const uint2 key = policy_key(a.seed);
   const uint32_t t_word = a.t_word + ((a.episode_dev ? __ldg(a.episode_dev) : 0u) << 16);
@@ -223,49 +227,49 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
     tc::fence_after_sync();
     // ---- epilogue out of tensor memory: relu, fc2, softmax, sample, log_prob; a thread owns row `row` of each of the
     //      R tiles, so every fc2 weight it loads serves R envs ---------------------------------------------------
-    const int64_t e0 = st * ROWS + row;
-    uint32_t idx[R];                                                // element index of (agent, env) in actions / logp
-    bool live[R], live_lp[R];
+    const int64_t e0 = st * ROWS + 128 * r_lo + row;
+    uint32_t idx[RT];                                                // element index of (agent, env) in actions / logp
+    bool live[RT], live_lp[RT];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < RT; ++r) {
       live[r] = e0 + 128 * r < a.ld;
       live_lp[r] = live[r] && want_logp;
       idx[r] = (uint32_t)(a0 + j_lo) * ld32 + (uint32_t)(e0 + 128 * r);
     }
-    uint4 rnd[R];
-    uint32_t hbuf[2][R][16];                                        // the next agent's columns load while this one computes
+    uint4 rnd[RT];
+    uint32_t hbuf[2][RT][16];                                        // the next agent's columns load while this one computes
     if (C::FULL || j_lo < n_real) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)(r * N + j_lo * H), hbuf[0][r]);
+      for (int r = 0; r < RT; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)((r_lo + r) * N + j_lo * H), hbuf[0][r]);
     }
 #pragma unroll
     for (int jj = 0; jj < AW; ++jj) {
       if (C::FULL || j_lo + jj < n_real) {
-        uint32_t (&hr)[R][16] = hbuf[jj & 1];
+        uint32_t (&hr)[RT][16] = hbuf[jj & 1];
         const int ag = a0 + j_lo + jj;
         if ((jj & 3) == 0) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) rnd[r] = policy_words((uint64_t)(a.env_offset + e0 + 128 * r), t_word, ag >> 2, key);
+          for (int r = 0; r < RT; ++r) rnd[r] = policy_words((uint64_t)(a.env_offset + e0 + 128 * r), t_word, ag >> 2, key);
         }
         const float* w2 = w2_lo + jj * C::W2S;
-        float2 acc[R][NA];
+        float2 acc[RT][NA];
 #pragma unroll
         for (int c = 0; c < NA; ++c) {
           const float b = w2[H * NA + c];
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r][c] = make_float2(b, 0.f);
+          for (int r = 0; r < RT; ++r) acc[r][c] = make_float2(b, 0.f);
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) tc::tmem_ld_wait_regs(hr[r]);
+        for (int r = 0; r < RT; ++r) tc::tmem_ld_wait_regs(hr[r]);
         if (jj + 1 < AW && (C::FULL || j_lo + jj + 1 < n_real)) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)(r * N + (j_lo + jj + 1) * H), hbuf[(jj + 1) & 1][r]);
+          for (int r = 0; r < RT; ++r) tc::tmem_ld16_raw(t_lane + (uint32_t)((r_lo + r) * N + (j_lo + jj + 1) * H), hbuf[(jj + 1) & 1][r]);
         }
 #pragma unroll
         for (int p4 = 0; p4 < H / 4; ++p4) {
-          float2 ra[R], rb[R];
+          float2 ra[RT], rb[RT];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
+          for (int r = 0; r < RT; ++r) {
             ra[r] = make_float2(fmaxf(__uint_as_float(hr[r][4 * p4 + 0]), 0.f), fmaxf(__uint_as_float(hr[r][4 * p4 + 1]), 0.f));
             rb[r] = make_float2(fmaxf(__uint_as_float(hr[r][4 * p4 + 2]), 0.f), fmaxf(__uint_as_float(hr[r][4 * p4 + 3]), 0.f));
           }
@@ -273,14 +277,14 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
           for (int c = 0; c < NA; ++c) {
             const float4 w = *reinterpret_cast<const float4*>(w2 + c * H + 4 * p4);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int r = 0; r < RT; ++r) {
               acc[r][c] = tc::ffma2(ra[r], make_float2(w.x, w.y), acc[r][c]);
               acc[r][c] = tc::ffma2(rb[r], make_float2(w.z, w.w), acc[r][c]);
             }
           }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < RT; ++r) {
           float l2[NA];
 #pragma unroll
           for (int c = 0; c < NA; ++c) l2[c] = acc[r][c].x + acc[r][c].y;
@@ -301,11 +305,11 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R>::THREADS) policy_act_discret
   if (tid < 32) tc::tmem_dealloc(tmem, C::COLS);
 }
 
-template <int A, int GMAX, int R>
+template <int A, int GMAX, int R, int RT>
 static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
-  using C = TcCfg<A, GMAX, R>;
+  using C = TcCfg<A, GMAX, R, RT>;
   PolicyArgs a = a_in;
-  auto kern = policy_act_discrete_tc_kernel<A, GMAX, R>;
+  auto kern = policy_act_discrete_tc_kernel<A, GMAX, R, RT>;
   // At most 512 / COLS CTAs of tensor memory fit an SM: size the shared-memory request so that no more than that
   // become resident (a surplus CTA would spin in tcgen05.alloc until a resident one exits).
   const int tmem_ctas = 512 / C::COLS;
@@ -344,8 +348,8 @@ static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
 // (128 columns, one warpgroup, more CTAs per SM; the tile's observation is staged once per group).
 template <int A>
 static int launch_tc_any(const PolicyArgs& a, int group_max, int sms, cudaStream_t st) {
-  if (group_max == 16) return launch_tc<A, 16, 1>(a, sms, st);
-  return launch_tc<A, 8, 2>(a, sms, st);
+  if (group_max == 16) return launch_tc<A, 8, 2, 1>(a, sms, st);     // variant 1: one tile per thread, twice the warps
+  return launch_tc<A, 8, 2, 2>(a, sms, st);
 }
 
 int launch_policy_tc(const PolicyArgs& a, int n_agents, int group_max, int sms, cudaStream_t st) {
