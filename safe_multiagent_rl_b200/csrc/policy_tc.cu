@@ -188,17 +188,33 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R, RT>::THREADS, TcCfg<A, GMAX,
     cp_async_wait_all();
     __syncthreads();
     // ---- the joint observation as bf16 K-major images: element k = 2 i is x_i, k = 2 i + 1 is y_i (main.py:33) ----
-    for (int i = tid; i < ROWS * 2 * KST; i += C::THREADS) {
-      const int rr = i % ROWS, c = i / ROWS;
-      uint32_t w[4];
+    // u8 -> bf16 without the conversion unit: 0x4B000000 | b is the float 2^23 + b, minus 2^23 gives b exactly, and the
+    // upper halves of two such floats are the bf16 pair (PRMT).  All loads of a thread's items are issued first.
+    {
+      constexpr int ITEMS = (ROWS * 2 * KST + C::THREADS - 1) / C::THREADS;
+      uint32_t b[ITEMS][8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float x = (float)s_pos[(size_t)(8 * c + 2 * q) * ROWS + rr], y = (float)s_pos[(size_t)(8 * c + 2 * q + 1) * ROWS + rr];
-        const __nv_bfloat162 p = __floats2bfloat162_rn(x, y);
-        w[q] = *reinterpret_cast<const uint32_t*>(&p);
+      for (int it = 0; it < ITEMS; ++it) {
+        const int i = tid + it * C::THREADS;
+        const int rr = i % ROWS, c = i / ROWS;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[it][q] = (i < ROWS * 2 * KST) ? s_pos[(size_t)(8 * c + q) * ROWS + rr] : 0u;
       }
-      *reinterpret_cast<uint4*>(s_a + (size_t)(rr >> 7) * C::A_TILE + (size_t)c * C::A_CHUNK + (size_t)(rr & 127) * 16) =
-          make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int i = tid + it * C::THREADS;
+        const int rr = i % ROWS, c = i / ROWS;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float x = __uint_as_float(0x4B000000u | b[it][2 * q]) - 8388608.0f;
+          const float y = __uint_as_float(0x4B000000u | b[it][2 * q + 1]) - 8388608.0f;
+          w[q] = __byte_perm(__float_as_uint(x), __float_as_uint(y), 0x7632);
+        }
+        if (i < ROWS * 2 * KST)
+          *reinterpret_cast<uint4*>(s_a + (size_t)(rr >> 7) * C::A_TILE + (size_t)c * C::A_CHUNK + (size_t)(rr & 127) * 16) =
+              make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();              // also orders the previous epilogue's tcgen05.ld before the MMAs that overwrite it
@@ -222,12 +238,19 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R, RT>::THREADS, TcCfg<A, GMAX,
       tc::mma_commit(s_bar);
     }
     if (st + gridDim.x < a.n_tiles) fetch(st + gridDim.x);
+    // the Philox blocks of this iteration (one per tile row and four agents) are computed while the MMAs run
+    const int64_t e0 = st * ROWS + 128 * r_lo + row;
+    uint4 rnd_all[(AW + 3) / 4][RT];
+#pragma unroll
+    for (int g4 = 0; g4 < (AW + 3) / 4; ++g4)
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+        rnd_all[g4][r] = policy_words((uint64_t)(a.env_offset + e0 + 128 * r), t_word, (a0 + j_lo + 4 * g4) >> 2, key);
     tc::mbar_wait(s_bar, phase);
     phase ^= 1u;
     tc::fence_after_sync();
     // ---- epilogue out of tensor memory: relu, fc2, softmax, sample, log_prob; a thread owns row `row` of each of the
     //      R tiles, so every fc2 weight it loads serves R envs ---------------------------------------------------
-    const int64_t e0 = st * ROWS + 128 * r_lo + row;
     uint32_t idx[RT];                                                // element index of (agent, env) in actions / logp
     bool live[RT], live_lp[RT];
 #pragma unroll
@@ -246,10 +269,9 @@ __global__ void __launch_bounds__(TcCfg<A, GMAX, R, RT>::THREADS, TcCfg<A, GMAX,
     for (int jj = 0; jj < AW; ++jj) {
       if (C::FULL || j_lo + jj < n_real) {
         uint32_t (&hr)[RT][16] = hbuf[jj & 1];
-        const int ag = a0 + j_lo + jj;
         if ((jj & 3) == 0) {
 #pragma unroll
-          for (int r = 0; r < RT; ++r) rnd[r] = policy_words((uint64_t)(a.env_offset + e0 + 128 * r), t_word, ag >> 2, key);
+          for (int r = 0; r < RT; ++r) rnd[r] = rnd_all[jj / 4][r];
         }
         const float* w2 = w2_lo + jj * C::W2S;
         float2 acc[RT][NA];
