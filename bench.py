@@ -425,6 +425,23 @@ def bench_policy_loop(s, a, dev):
     ms1 = _event_ms(loop.replay, 50)
     out["config1_graphed"] = {"n_envs": 50, "n_agents": 3, "max_t": 50, "ms_per_batch": ms1,
                               "value_with_policy": 50 * 3 * 50 / (ms1 * 1e-3), "unit": UNIT}
+    # BASELINE configs[1] (CollisionAvoidance 5x5, 3 agents, 65 536 envs, T = 50: the reference's default environment) with
+    # the reference's ContinuousPolicy (agent.py:48-76) in the loop, one CUDA graph per batch: the fused Gaussian policy
+    # kernel (smarl_policy_act_gaussian) against the PyTorch glue
+    from safe_multiagent_rl_b200.policy import BatchedGaussianPolicy, FusedGaussianPolicy
+    E2 = 65536
+    rng2 = np.random.default_rng(2)
+    env2 = s.BatchedCollisionAvoidance(5, 3, n_envs=E2, n_landmarks=1, device=dev, starts=rng2.random((E2, 3, 2)) * 5,
+                                       landmarks=rng2.random((E2, 1, 2)) * 5)
+    lam2 = torch.full((1,), 0.1, dtype=torch.float64, device=dev)
+    polg, polt = FusedGaussianPolicy(env2, seed=7), BatchedGaussianPolicy(env2)
+    c2 = {"n_envs": E2, "n_agents": 3, "max_t": 50, "unit": UNIT}
+    for tag, fn in (("fused", lambda obs, t: polg.act(t=t)), ("pytorch_glue", lambda obs, t: polt.act(obs))):
+        lp = s.GraphedClosedLoop(env2, 50, fn, lam2, 0.999, thresholds=[2.0])
+        ms2 = _event_ms(lp.replay, 20)
+        c2[tag] = {"ms_per_batch": ms2, "value_with_policy": E2 * 3 * 50 / (ms2 * 1e-3)}
+        del lp
+    out["config2_collision_gaussian_graphed"] = c2
     return out
 
 

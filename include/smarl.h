@@ -373,6 +373,36 @@ int smarl_policy_act_discrete(const SmarlDiscretePolicy* p, const uint8_t* pos_x
                               uint8_t* actions, float* logp, int32_t t, int64_t n_envs, int64_t ld,
                               smarl_stream_t stream);
 
+/* The same for the continuous envs: ContinuousPolicy (safe_multi_agent_RL/agent.py:48-76): fc1 = Linear(state_space, 16),
+ * relu, mu = fc2 (2 outputs), sigma^2 = relu(fc2_) + 1e-4, action ~ MultivariateNormal(mu, diag(sigma^2)), log_prob of
+ * it; one network per agent, each fed the joint state (main.py:30-35).  The kernel reads the f32 observation rows the
+ * step / reset kernels maintain and writes the f32 action rows the step consumes plus the log-probabilities.
+ *   w1 f32 [A][S][16] ([in][out]), b1 [A][16], w_mu / w_var f32 [A][16][2], b_mu / b_var [A][2]: DEVICE
+ *   obs f32 [S][ld] in    actions f32 [2A][ld] out (rows dx0, dy0, dx1, ...)    logp f32 [A][ld] out (NULL to skip)
+ * Sampling: Philox4x32-10, counter (global env id lo, hi, t | episode << 16, agent >> 1), key seed ^ "GAUS" (hi word):
+ * one block serves two agents, agent a takes w[2 (a & 1)], w[2 (a & 1) + 1]; u_k = ((w_k >> 9) + 0.5) * 2^-23;
+ * Box-Muller r = sqrt(-2 ln u_0), z = (r cos 2 pi u_1, r sin 2 pi u_1); action_k = mu_k + sigma_k z_k;
+ * log_prob = -1/2 sum_k ((action_k - mu_k)^2 / sigma_k^2 + ln sigma_k^2) - ln 2 pi.  t in 0..65535. */
+typedef struct {
+  int32_t n_agents;        /* A                                                                      */
+  int32_t state_size;      /* S = env.state_space: 2A, or 2A + 2L with shuffled landmarks (Collision) */
+  int32_t hidden;          /* 16 (agent.py:49)                                                       */
+  int32_t n_actions;       /* 2  (env.action_space of the continuous envs)                           */
+  uint32_t episode;
+  int32_t reserved;
+  const float* w1;
+  const float* b1;
+  const float* w_mu;
+  const float* b_mu;
+  const float* w_var;
+  const float* b_var;
+  uint64_t seed;
+  int64_t env_offset;
+  const uint32_t* episode_dev;
+} SmarlGaussianPolicy;
+int smarl_policy_act_gaussian(const SmarlGaussianPolicy* p, const float* obs, float* actions, float* logp, int32_t t,
+                              int64_t n_envs, int64_t ld, smarl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Multi-GPU: env instances are independent (envs/coverage.py:19, congestion.py:22,
  * collision_avoidance.py:60), so ranks own contiguous ranges of global env ids and the data path has no

@@ -106,8 +106,8 @@ def random_starts(kind, size, seed, env_ids, episode, n_rows, zoom=None, row_off
 
 def policy_uniforms(seed, env_ids, t, n_agents, episode=0):
     """u [E, A] of smarl_policy_act_discrete: Philox counter (env id lo, hi, t | episode << 16, agent >> 2), key
-    (seed lo, seed hi ^ "PLCY"); agent a takes word a & 3 of its block; u = ((w >> 8) + 0.5) * 2**-24 (exactly
-    representable in float32)."""
+    (seed lo, seed hi ^ "PLCY"); agent a takes word a & 3 of its block; u = ((w >> 8) + 0.5) * 2**-24 (the kernel forms
+    it in float32, where k + 0.5 rounds to even for k >= 2**23: off by 2**-25 there, below the margin the tests allow)."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     tw = (int(t) | (int(episode) << 16)) & 0xFFFFFFFF
     o = philox4x32_10((env_ids & MASK)[:, None], (env_ids >> np.uint64(32))[:, None], np.full((1, 1), tw, dtype=np.uint64),
@@ -132,3 +132,31 @@ def policy_sample(logits, u):
     logp = np.take_along_axis(logits - m - np.log(s)[..., None], a[..., None], axis=-1)[..., 0]
     margin = np.abs(cum - target).min(axis=-1) / s
     return a, logp, margin
+
+
+def gaussian_normals(seed, env_ids, t, n_agents, episode=0):
+    """z [E, A, 2] of smarl_policy_act_gaussian: Philox counter (env id lo, hi, t | episode << 16, agent >> 1), key
+    (seed lo, seed hi ^ "GAUS"); agent a takes words 2 (a & 1), 2 (a & 1) + 1; u = ((w >> 9) + 0.5) * 2**-23 (23 bits:
+    exactly representable in float32, never 0 or 1);
+    Box-Muller r = sqrt(-2 ln u0), z = (r cos 2 pi u1, r sin 2 pi u1) (float64 here)."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    tw = (int(t) | (int(episode) << 16)) & 0xFFFFFFFF
+    ag = np.arange(n_agents)
+    o = philox4x32_10((env_ids & MASK)[:, None], (env_ids >> np.uint64(32))[:, None], np.full((1, 1), tw, dtype=np.uint64),
+                      (ag.astype(np.uint64) >> np.uint64(1))[None, :], seed & 0xFFFFFFFF,
+                      ((seed >> 32) & 0xFFFFFFFF) ^ 0x47415553)
+    w = np.stack(o, axis=0)                                                              # [4, E, A]
+    wa = w[2 * (ag & 1), :, ag].T                                                        # [E, A]
+    wb = w[2 * (ag & 1) + 1, :, ag].T
+    u0 = ((wa >> np.uint32(9)).astype(np.float64) + 0.5) / 8388608.0
+    u1 = ((wb >> np.uint32(9)).astype(np.float64) + 0.5) / 8388608.0
+    r = np.sqrt(-2.0 * np.log(u0))
+    return np.stack([r * np.cos(2.0 * np.pi * u1), r * np.sin(2.0 * np.pi * u1)], axis=-1)
+
+
+def gaussian_sample(mu, var, z):
+    """actions and log-probabilities as the kernel forms them: a = mu + sqrt(var) z, log N(a; mu, diag(var))."""
+    mu, var, z = (np.asarray(x, dtype=np.float64) for x in (mu, var, z))
+    a = mu + np.sqrt(var) * z
+    logp = -0.5 * (((a - mu) ** 2 / var) + np.log(var)).sum(axis=-1) - np.log(2.0 * np.pi)
+    return a, logp

@@ -45,6 +45,13 @@ class DiscretePolicyParams(C.Structure):
                 ("env_offset", C.c_int64), ("episode_dev", c_ptr)]
 
 
+class GaussianPolicyParams(C.Structure):
+    _fields_ = [("n_agents", C.c_int32), ("state_size", C.c_int32), ("hidden", C.c_int32), ("n_actions", C.c_int32),
+                ("episode", C.c_uint32), ("reserved", C.c_int32),
+                ("w1", c_ptr), ("b1", c_ptr), ("w_mu", c_ptr), ("b_mu", c_ptr), ("w_var", c_ptr), ("b_var", c_ptr),
+                ("seed", C.c_uint64), ("env_offset", C.c_int64), ("episode_dev", c_ptr)]
+
+
 P = C.POINTER
 i32, i64, f64 = C.c_int32, C.c_int64, C.c_double
 
@@ -88,6 +95,7 @@ PROTOTYPES = {
                                                c_ptr, c_ptr, c_ptr, i32, i32, i64, i64, c_ptr]),
     "smarl_lambda_update": (C.c_int, [c_ptr, c_ptr, c_ptr, f64, i32, i32, c_ptr]),
     "smarl_policy_act_discrete": (C.c_int, [P(DiscretePolicyParams), c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
+    "smarl_policy_act_gaussian": (C.c_int, [P(GaussianPolicyParams), c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_comm_get_unique_id": (C.c_int, [c_ptr]),
     "smarl_comm_init_from_unique_id": (C.c_int, [P(c_ptr), c_ptr, i32, i32]),
     "smarl_comm_destroy": (None, [c_ptr]),

@@ -131,3 +131,43 @@ class BatchedGaussianPolicy(nn.Module):
 
     def log_prob(self, obs, actions):
         return self.dist(obs).log_prob(actions)
+
+
+class FusedGaussianPolicy(BatchedGaussianPolicy):
+    """``BatchedGaussianPolicy`` whose ``act`` is ONE libsmarl kernel (smarl_policy_act_gaussian): it reads the env's
+    f32 observation rows, evaluates every agent's ``S -> 16 -> (mu, sigma^2)`` network with the weights in shared
+    memory, samples ``a ~ N(mu, diag(sigma^2))`` by Box-Muller from a Philox stream keyed by (global env id, episode,
+    step, agent) and writes ``env.action_buffer`` (rows dx0, dy0, dx1, ...) and the log-probabilities.
+    ``log_prob`` / ``dist`` (the differentiable path) stay the parent's."""
+
+    def __init__(self, env, hidden_size=16, seed=0):
+        if hidden_size != 16 or env.action_space != 2 or not hasattr(env, "obs"):
+            raise NotImplementedError("the fused kernel is built for the reference's ContinuousPolicy on the continuous "
+                                      "envs: hidden 16, 2 actions, f32 observation rows")
+        super().__init__(env, hidden_size)
+        from . import _lib
+        self._lib_mod, self.lib = _lib, _lib.load()
+        self.seed = int(seed)
+        self.logp = torch.zeros(env.n_agents, env.ld, dtype=torch.float32, device=env.device)
+        self._episode_dev = torch.zeros(1, dtype=torch.int32, device=env.device)
+
+    def next_episode(self):
+        self._episode_dev.add_(1)
+
+    @torch.no_grad()
+    def act(self, obs=None, t=None):
+        """Sample actions for step ``t`` into ``env.action_buffer``; returns (action_buffer, actions [A, E, 2] view,
+        log_prob [A, E] view).  ``obs`` is ignored: the kernel reads ``env.obs``."""
+        import ctypes as C
+        env, L = self.env, self._lib_mod
+        w = [t_.detach() for t_ in (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc2_.weight,
+                                    self.fc2_.bias)]
+        assert all(x.is_contiguous() and x.dtype == torch.float32 for x in w)
+        S = env.obs.shape[0]
+        assert S == env.state_space == self.fc1.weight.shape[1]
+        p = L.GaussianPolicyParams(env.n_agents, S, 16, 2, 0, 0, *[L.ptr(x) for x in w], self.seed & (2 ** 64 - 1),
+                                   env.env_offset, L.ptr(self._episode_dev))
+        L.check(self.lib.smarl_policy_act_gaussian(C.byref(p), L.ptr(env.obs), L.ptr(env.action_buffer), L.ptr(self.logp),
+                                                   int(env.t if t is None else t), env.n_envs, env.ld, L.stream_ptr()))
+        A, E = env.n_agents, env.n_envs
+        return env.action_buffer, env.action_buffer[:, :E].view(A, 2, E).permute(0, 2, 1), self.logp[:, :E]

@@ -26,8 +26,14 @@ P="python tools/profile_env.py collision 32 16 1048576 6"
 $P > /dev/null && tools/ncu_capture.sh ${tag}_coll_coop_step_a16 collision_coop_step 3 $P
 P="python tools/profile_env.py collision 5 3 1048576 20"
 $P > /dev/null && tools/ncu_capture.sh ${tag}_coll_step_a3 collision_step_kernel 5 $P
-P="python tools/profile_policy.py 16 262144"
-$P > /dev/null && tools/ncu_capture.sh ${tag}_policy_a16 policy_act_discrete 3 $P
+P="python tools/profile_policy.py 16 1048576 2"      # tensor-core build (default), two tiles per thread
+$P > /dev/null && tools/ncu_capture.sh ${tag}_policy_tc_a16 policy_act_discrete_tc 3 $P
+P="python tools/profile_policy.py 16 262144 0"       # FP32-pipe build
+$P > /dev/null && tools/ncu_capture.sh ${tag}_policy_a16 policy_act_discrete_kernel 3 $P
+for a in 3 8 16 32; do python tools/profile_policy.py $a 1048576 --time; done > $out/${tag}_policy_variants_time.txt 2>&1
+for c in "3 65536" "3 1048576" "8 1048576" "16 262144"; do python tools/time_policy_gauss.py $c; done > $out/${tag}_policy_gauss_time.txt 2>&1
+timeout 60 tools/umma_probe > $out/${tag}_umma_probe.txt 2>&1
+timeout 60 tools/fma_probe > $out/${tag}_fma_probe.txt 2>&1
 for f in $out/${tag}_*_source.csv; do python tools/ncu_summary.py ${f%_source.csv} > ${f%_source.csv}_summary.txt 2>&1; done
 rm -f $out/${tag}_*_source.csv            # large; the raw + details pages and the summaries are what profiles/ keeps
 python tools/time_coop.py --envs collision,congestion,coverage --agents 12,16,20,24,28,32 > $out/${tag}_crossover.md 2>&1
