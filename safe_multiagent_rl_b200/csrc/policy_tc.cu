@@ -346,17 +346,26 @@ static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
     set_error("tensor-core policy: n_agents * ld = %llu does not fit 32-bit element indices", (unsigned long long)A * a.ld);
     return SMARL_EUNSUPPORTED;
   }
-  SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  // resident CTAs per SM: tensor memory (by construction of the shared-memory request) and registers; the occupancy
-  // calculator is not asked because it assumes the default carveout and reported 1 where 2 CTAs run
-  cudaFuncAttributes fa;
-  SMARL_CUDA(cudaFuncGetAttributes(&fa, kern));
-  int per_sm = tmem_ctas;
-  const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * C::THREADS);
-  if (per_sm > by_regs) per_sm = by_regs;
-  if (per_sm > 2048 / C::THREADS) per_sm = 2048 / C::THREADS;
-  if (per_sm < 1) per_sm = 1;
+  // per-kernel launch setup, once per device (the attribute calls cost host time on every step otherwise)
+  static int cached_dev = -1, cached_per_sm = 1;
+  int dev = 0;
+  SMARL_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // resident CTAs per SM: tensor memory (by construction of the shared-memory request) and registers; the occupancy
+    // calculator is not asked because it assumes the default carveout and reported 1 where 2 CTAs run
+    cudaFuncAttributes fa;
+    SMARL_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int per_sm = tmem_ctas;
+    const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * C::THREADS);
+    if (per_sm > by_regs) per_sm = by_regs;
+    if (per_sm > 2048 / C::THREADS) per_sm = 2048 / C::THREADS;
+    if (per_sm < 1) per_sm = 1;
+    cached_per_sm = per_sm;
+    cached_dev = dev;
+  }
+  const int per_sm = cached_per_sm;
   a.n_tiles = (a.n_envs + C::ROWS - 1) / C::ROWS;                   // CTA iterations of ROWS envs
   int64_t gx = (int64_t)sms * per_sm / C::NGROUPS;
   if (gx < 1) gx = 1;

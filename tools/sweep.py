@@ -4,6 +4,12 @@ envs 1K-16M) on one GPU: closed-loop (T step launches + returns kernel, captured
 small batches are not launch-bound) and fused open-loop rollout.  Prints a markdown table.
 
     python tools/sweep.py [--quick] > profiles/rNN/sweep.md
+
+Under torchrun (WORLD_SIZE > 1) the same table is produced for N GPUs of one box, STRONG-scaled: `envs` is the total
+batch, sharded over the ranks by contiguous global env ids (dist.shard_range); every closed-loop batch ends with the
+NCCL all-reduce of the stats vector (smarl_stats_allreduce) and the lambda update; times are the max over ranks.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sweep.py --multi
 """
 import argparse
 import os
@@ -14,8 +20,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import safe_multiagent_rl_b200 as s  # noqa: E402
+from safe_multiagent_rl_b200 import dist as sd  # noqa: E402
 
 PEAK = 6551.0
+RANK, WORLD, COMM = 0, 1, None
 
 
 def make(env_name, S, A, E, g):
@@ -62,17 +70,25 @@ def timed(fn, iters):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        torch.distributed.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
         fn()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    ms = a.elapsed_time(b) / iters
+    if WORLD > 1:                                # the slowest rank is the job's time
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
-def run(env_name, S, A, E, T):
-    g = torch.Generator(device="cuda"); g.manual_seed(0)
+def run(env_name, S, A, E_total, T):
+    g = torch.Generator(device="cuda"); g.manual_seed(RANK)
+    _, E = sd.shard_range(E_total, RANK, WORLD)   # this rank's contiguous shard (the whole batch on one GPU)
     env, K, bytes_step = make(env_name, S, A, E, g)
     if env_name in ("collision", "coverage_cont"):
         actions = torch.randn((T, 2 * A, env.ld), generator=g, device="cuda") * 0.5
@@ -95,9 +111,18 @@ def run(env_name, S, A, E, T):
     with torch.cuda.graph(graph):
         closed()
     iters = max(3, min(50, int(2e9 / (E * A * T)) + 3))
-    ms_closed = timed(graph.replay, iters)
+    thr_dev = torch.tensor(thr, dtype=torch.float64, device="cuda")
+
+    def batch():
+        graph.replay()
+        if WORLD > 1:                            # MetaAgent.update's sum over ranks + the lambda update (meta_agent.py:32-39)
+            COMM.allreduce(buf.stats_vec)
+            s._lib.check(s._lib.load().smarl_lambda_update(s._lib.ptr(lam), s._lib.ptr(buf.stats_vec), s._lib.ptr(thr_dev), 0.0,
+                                                         A, K, s._lib.stream_ptr()))
+    ms_closed = timed(batch, iters)
     out = {}
     ms_fused = timed(lambda: env.rollout(actions, lambdas=lam, gamma=gamma, thresholds=thr, out=out), iters)
+    E = E_total
     n = float(E) * A * T
     return dict(env=env_name, S=S, A=A, E=E, T=T, closed=n / ms_closed * 1e3, fused=n / ms_fused * 1e3,
                 ms_closed=ms_closed, ms_fused=ms_fused,
@@ -107,8 +132,13 @@ def run(env_name, S, A, E, T):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--multi", action="store_true", help="the reduced grid of the multi-GPU (torchrun) sweep")
     ap.add_argument("--cfg", action="append", default=[], help="env,size,agents,envs,T (repeatable): run only these")
     a = ap.parse_args()
+    RANK, WORLD, local = sd.init_from_env()
+    torch.cuda.set_device(local)
+    if WORLD > 1:
+        COMM = sd.StatsComm.from_process_group()
     cfgs = [("coverage", 5, 3, 50, 50),            # configs[0]
             ("collision", 5, 3, 65536, 50),        # configs[1]
             ("congestion", 10, 8, 1 << 20, 100),   # configs[2]
@@ -117,6 +147,16 @@ if __name__ == "__main__":
             ("coverage_disc", 5, 3, 1 << 20, 50)]
     if a.cfg:
         cfgs = [(c.split(",")[0], *map(int, c.split(",")[1:])) for c in a.cfg]
+    elif a.multi:                                    # configs[4] on N GPUs: the corners and the middle of the grid
+        cfgs = [c for c in cfgs if c[3] >= 1 << 16]
+        for env_name in ("coverage", "congestion", "collision"):
+            for S, A in [(5, 3), (16, 8), (64, 32)]:
+                for E in [1 << 16, 1 << 20, 1 << 22, 1 << 24]:
+                    if env_name == "collision" and E * A > (1 << 27):
+                        continue
+                    if E * A * 50 > 8e9 * min(WORLD, 4):
+                        continue
+                    cfgs.append((env_name, S, A, E, 50))
     elif not a.quick:                                # configs[4]: sweep
         for env_name in ("coverage", "congestion", "collision"):
             for S, A in [(5, 3), (8, 4), (16, 8), (32, 16), (64, 32)]:
@@ -126,6 +166,11 @@ if __name__ == "__main__":
                     if E * A * 50 > 4e9:
                         continue
                     cfgs.append((env_name, S, A, E, 50))
+    if RANK != 0:
+        sys.stdout = open(os.devnull, "w")
+    if WORLD > 1:
+        print(f"## {WORLD} GPUs of one box, strong scaling: `envs` is the TOTAL batch, sharded over the ranks; every closed-loop batch "
+              f"includes the NCCL stats all-reduce + lambda update; max over ranks; fractions are of {WORLD} x 6551 GB/s\n")
     print("Envelope of the kernels behind this table: n_agents <= 32; grid size <= 127 (Coverage: doubled u8 coordinates index the "
           "penalty table, fieldview^2 <= 12279 table entries) / <= 254 (Congestion); fused Coverage rollout T <= 255 (byte cost "
           "counters); per call (2 * n_agents + 1) * ld < 2^32 (32-bit element offsets: n_agents = 32 caps a call at ~6.6e7 envs; "
@@ -138,5 +183,5 @@ if __name__ == "__main__":
     for c in cfgs:
         r = run(*c)
         print(f"| {r['env']} | {r['S']} | {r['A']} | {r['E']} | {r['T']} | {r['closed']:.3g} | {r['ms_closed']:.3f} | "
-              f"{r['closed_gbs']:.0f} ({r['closed_gbs'] / PEAK:.2f}) | {r['fused']:.3g} | {r['ms_fused']:.3f} |", flush=True)
+              f"{r['closed_gbs']:.0f} ({r['closed_gbs'] / (PEAK * WORLD):.2f}) | {r['fused']:.3g} | {r['ms_fused']:.3f} |", flush=True)
         torch.cuda.empty_cache()
