@@ -63,6 +63,13 @@ int smarl_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * with groups of up to 8.  Process-wide; returns the previous setting. */
 int smarl_set_kernel_variant(int32_t env_kind, int32_t lanes);
 
+/* Programmatic dependent launch of the per-step kernels (the *_step and policy_act_* entry points): the next step's
+ * CTAs are scheduled while the current kernel drains and block in griddepcontrol.wait until it has completed, which
+ * hides most of the kernel-to-kernel launch gap of a closed loop (main.py:28-57 is T x (act, step) on one stream) --
+ * in plain streams and inside captured CUDA graphs alike.  Results never depend on it.  On by default (SMARL_PDL=0 in
+ * the environment turns it off); process-wide; returns the previous setting. */
+int smarl_set_pdl(int32_t on);
+
 /* ------------------------------------------------------------------------------------
  * Grid envs share start/reset: replaces CoverageContinuous.reset/_restart
  * (envs/coverage.py:28-52) and Congestion.reset/_restart (envs/congestion.py:34-47) for

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "smarl_last_error": (C.c_char_p, []),
     "smarl_device_info": (C.c_int, [P(C.c_int), P(C.c_int), P(C.c_int)]),
     "smarl_set_kernel_variant": (C.c_int, [i32, i32]),
+    "smarl_set_pdl": (C.c_int, [i32]),
     "smarl_grid_reset": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_random_starts_u8": (C.c_int, [i32, i32, C.c_uint64, i64, i64, c_ptr, c_ptr, i32, i64, i64, c_ptr]),
     "smarl_random_starts_f64": (C.c_int, [i32, i32, f64, C.c_uint64, i64, i64, i32, c_ptr, c_ptr, i64, i32, i64, c_ptr]),

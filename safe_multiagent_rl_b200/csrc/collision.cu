@@ -144,6 +144,7 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
 // fused +9 %); a one-wave batch like config 1 (65 536 envs) is latency-bound per thread and loses 3 % to the spills.
 template <int A, bool CAP>
 __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_kernel(const CollisionStepArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   const int64_t e = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
   if (e >= a.n_envs) return;
   const int64_t ld = a.ld;
@@ -216,13 +217,13 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_ke
 int launch_collision_step(int A, const CollisionStepArgs& a, unsigned grid, cudaStream_t s) {
   if (A <= 4 && a.n_envs >= kCollCapMinEnvs) {
     switch (A) {
-      case 1: collision_step_kernel<1, true><<<grid, kCollThreads, 0, s>>>(a); break;
-      case 2: collision_step_kernel<2, true><<<grid, kCollThreads, 0, s>>>(a); break;
-      case 3: collision_step_kernel<3, true><<<grid, kCollThreads, 0, s>>>(a); break;
-      default: collision_step_kernel<4, true><<<grid, kCollThreads, 0, s>>>(a); break;
+      case 1: SMARL_CUDA(launch_pdl(collision_step_kernel<1, true>, grid, kCollThreads, 0, s, a)); break;
+      case 2: SMARL_CUDA(launch_pdl(collision_step_kernel<2, true>, grid, kCollThreads, 0, s, a)); break;
+      case 3: SMARL_CUDA(launch_pdl(collision_step_kernel<3, true>, grid, kCollThreads, 0, s, a)); break;
+      default: SMARL_CUDA(launch_pdl(collision_step_kernel<4, true>, grid, kCollThreads, 0, s, a)); break;
     }
   } else {
-    SMARL_DISPATCH_A(A, collision_step_kernel<kA, false><<<grid, kCollThreads, 0, s>>>(a));
+    SMARL_DISPATCH_A(A, SMARL_CUDA(launch_pdl(collision_step_kernel<kA, false>, grid, kCollThreads, 0, s, a)));
   }
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;

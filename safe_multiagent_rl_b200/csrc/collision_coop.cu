@@ -273,6 +273,7 @@ __device__ __forceinline__ void collision_coop_env_step(double (&px)[CollCoop<A,
 #if SMARL_TU_IS(0)
 template <int A, int S, bool COMPACT>
 __global__ void __launch_bounds__(kCoopThreads, 5) collision_coop_step_kernel(const CollisionStepArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   using C = CollCoop<A, S>;
   constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC;
   extern __shared__ double2 s_pos[];                                  // [EPC][PA]
@@ -374,7 +375,7 @@ static int launch_step_s(int A, const CollisionStepArgs& a, cudaStream_t st) {
     if (C::kSmem > 48 * 1024)                                                                           \
       SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem)); \
     const unsigned grid = (unsigned)((a.n_envs + C::EPC - 1) / C::EPC);                                 \
-    kern<<<grid, kCoopThreads, C::kSmem, st>>>(a);                                                      \
+    SMARL_CUDA(launch_pdl(kern, grid, kCoopThreads, C::kSmem, st, a));                                                      \
   } break;
     SMARL_COOP_CASE(9) SMARL_COOP_CASE(10) SMARL_COOP_CASE(11) SMARL_COOP_CASE(12) SMARL_COOP_CASE(13)
     SMARL_COOP_CASE(14) SMARL_COOP_CASE(15) SMARL_COOP_CASE(16) SMARL_COOP_CASE(17) SMARL_COOP_CASE(18)

@@ -37,6 +37,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // smarl_set_kernel_variant's current setting for an env kind (-1 = automatic).
 int kernel_variant(int env_kind);
 
+// Programmatic dependent launch of the per-step kernels (on unless SMARL_PDL=0 in the environment).
+bool pdl_enabled();
+
 // Checks the shared layout contract of smarl.h for one call.
 int check_layout(int64_t n_envs, int64_t ld);
 
@@ -65,6 +68,35 @@ int check_layout(int64_t n_envs, int64_t ld);
   }
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL) for the per-step kernels.  A closed loop is T x (policy, step) launches on one
+// stream; with small batches (BASELINE configs[0] / [1], or 2^19 envs per GPU of the sharded configs[3]) the ~2-3 us
+// between two kernels is a large share of the step.  launch_pdl() lets the NEXT kernel's CTAs be scheduled while this
+// one still runs; pdl_prologue() -- the first statement of every such kernel -- then blocks until the previous grid
+// has COMPLETED and its memory is visible (griddepcontrol.wait), and only after that allows the kernel behind it to be
+// scheduled, so at most two grids overlap and nothing is read before the wait.  Without the launch attribute (or
+// behind a kernel that is not PDL-aware) both instructions are no-ops.  Stream capture records the edge as a
+// programmatic dependency, so CUDA-graph replays keep the overlap.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename Arg>
+inline cudaError_t launch_pdl(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 // ---------------------------------------------------------------------------------------
 // Streaming global access.  Every byte of the batched state is touched once per launch,
 // so loads bypass L1 allocation and stores are marked evict-first ("streaming").

@@ -86,6 +86,7 @@ int launch_congestion_rollout_m2(int A, const CongestionRolloutArgs& a, unsigned
 #if SMARL_TU_IS(0) || SMARL_TU_IS(1) || SMARL_TU_IS(2)
 template <int A, int MODE>
 __global__ void __launch_bounds__(kCongThreads, cong_step_min_blocks(A)) congestion_step_kernel(const CongestionStepArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   const int64_t g = (int64_t)blockIdx.x * kCongThreads + threadIdx.x;
   if (g >= a.n_groups) return;
   // 32-bit element offsets (the host checks (2A+1) * ld < 2^32): one add per row and one wide add per
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kCongThreads, cong_step_min_blocks(A)) congest
 
 #define SMARL_DEFINE_CONG_STEP(M)                                                                       \
   int launch_congestion_step_m##M(int A, const CongestionStepArgs& a, unsigned grid, cudaStream_t s) {  \
-    SMARL_DISPATCH_A(A, congestion_step_kernel<kA, M><<<grid, kCongThreads, 0, s>>>(a));                \
+    SMARL_DISPATCH_A(A, SMARL_CUDA(launch_pdl(congestion_step_kernel<kA, M>, grid, kCongThreads, 0, s, a)));                \
     SMARL_CUDA(cudaGetLastError());                                                                     \
     return SMARL_OK;                                                                                    \
   }

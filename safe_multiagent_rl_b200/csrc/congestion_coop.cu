@@ -110,6 +110,7 @@ __device__ __forceinline__ void congestion_scan(const uint4* __restrict__ rec, c
 
 template <int A, int S, int MODE>
 __global__ void __launch_bounds__(kCongCoopThreads, 4) congestion_coop_step_kernel(const CongestionStepArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   using C = CongCoop<A, S>;
   constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC, NQ = C::NQ;
   extern __shared__ uint4 s_rec[];                                 // [EPC][PQ]: Philox blocks (MODE 2), then the
@@ -255,7 +256,7 @@ static int launch_sm(int A, const CongestionStepArgs& a, cudaStream_t st) {
     if (smem > 48 * 1024)                                                                               \
       SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     const unsigned grid = (unsigned)((a.n_groups + C::EPC - 1) / C::EPC);                               \
-    kern<<<grid, kCongCoopThreads, smem, st>>>(a);                                                      \
+    SMARL_CUDA(launch_pdl(kern, grid, kCongCoopThreads, smem, st, a));                                                      \
   } break;
     SMARL_COOP_CASE(9) SMARL_COOP_CASE(10) SMARL_COOP_CASE(11) SMARL_COOP_CASE(12) SMARL_COOP_CASE(13)
     SMARL_COOP_CASE(14) SMARL_COOP_CASE(15) SMARL_COOP_CASE(16) SMARL_COOP_CASE(17) SMARL_COOP_CASE(18)

@@ -88,6 +88,7 @@ int launch_coverage_rollout(int A, const CoverageRolloutArgs& a, unsigned grid, 
 // run-time branch inside the load loop it cost the reward_rows = 1 path 13 % of its bandwidth).
 template <int A, bool KEEP>
 __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const CoverageStepArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   extern __shared__ float s_lut[];
   coverage_load_lut(s_lut, a.lut, a.lut_len);
   const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
@@ -174,9 +175,9 @@ __global__ void __launch_bounds__(kStepThreads) coverage_step_kernel(const Cover
 int launch_coverage_step(int A, const CoverageStepArgs& a, unsigned grid, cudaStream_t s) {
   const size_t smem = (size_t)(a.lut_len + 1) * sizeof(float);
   if (a.keep_pos) {
-    SMARL_DISPATCH_A(A, coverage_step_kernel<kA, true><<<grid, kStepThreads, smem, s>>>(a));
+    SMARL_DISPATCH_A(A, SMARL_CUDA(launch_pdl(coverage_step_kernel<kA, true>, grid, kStepThreads, smem, s, a)));
   } else {
-    SMARL_DISPATCH_A(A, coverage_step_kernel<kA, false><<<grid, kStepThreads, smem, s>>>(a));
+    SMARL_DISPATCH_A(A, SMARL_CUDA(launch_pdl(coverage_step_kernel<kA, false>, grid, kStepThreads, smem, s, a)));
   }
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;

@@ -56,6 +56,7 @@ struct CoverageCoopArgs {
 
 template <int A, int S>
 __global__ void __launch_bounds__(kCovCoopThreads, 4) coverage_coop_step_kernel(const CoverageCoopArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   using C = CovCoop<A, S>;
   constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC, H = C::H, PA = C::PA;
   extern __shared__ float s_lut[];                                        // [lut_len + 1] then the packed positions
@@ -191,7 +192,7 @@ static int launch_s(int A, const CoverageCoopArgs& a, cudaStream_t st) {
     if (smem > 48 * 1024)                                                                                  \
       SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     const unsigned grid = (unsigned)((a.n_groups + C::EPC - 1) / C::EPC);                                  \
-    kern<<<grid, kCovCoopThreads, smem, st>>>(a);                                                          \
+    SMARL_CUDA(launch_pdl(kern, grid, kCovCoopThreads, smem, st, a));                                                          \
   } break;
     SMARL_COOP_CASE(9) SMARL_COOP_CASE(10) SMARL_COOP_CASE(11) SMARL_COOP_CASE(12) SMARL_COOP_CASE(13)
     SMARL_COOP_CASE(14) SMARL_COOP_CASE(15) SMARL_COOP_CASE(16) SMARL_COOP_CASE(17) SMARL_COOP_CASE(18)

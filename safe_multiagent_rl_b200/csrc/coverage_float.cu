@@ -81,6 +81,7 @@ __device__ __forceinline__ void coverage_float_env_step(double (&px)[A], double 
 #if SMARL_TU_IS(0) || SMARL_TU_IS(1)
 template <int A, int MODE>
 __global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const CoverageFloatArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   const int64_t e = (int64_t)blockIdx.x * kCovFThreads + threadIdx.x;
   if (e >= a.n_envs) return;
   const int64_t ld = a.ld;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kCovFThreads) coverage_float_step_kernel(const
 
 #define SMARL_DEFINE_COVF_STEP(M)                                                                        \
   int launch_coverage_float_step_m##M(int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s) { \
-    SMARL_DISPATCH_A(A, coverage_float_step_kernel<kA, M><<<grid, kCovFThreads, 0, s>>>(a));             \
+    SMARL_DISPATCH_A(A, SMARL_CUDA(launch_pdl(coverage_float_step_kernel<kA, M>, grid, kCovFThreads, 0, s, a)));             \
     SMARL_CUDA(cudaGetLastError());                                                                      \
     return SMARL_OK;                                                                                     \
   }

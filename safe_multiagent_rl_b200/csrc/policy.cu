@@ -49,6 +49,7 @@ struct PolCfg {
 
 template <int A>
 __global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel(const PolicyArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   using C = PolCfg<A>;
   constexpr int IN = C::IN, QPT = C::QPT, TE = C::TE, H = kPolHidden, NA = kPolActions;
   extern __shared__ float s_mem[];
@@ -171,7 +172,7 @@ extern "C" int smarl_policy_act_discrete(const SmarlDiscretePolicy* p, const uin
     SMARL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
     a.n_tiles = (ld + C::TE - 1) / C::TE;
     const int64_t grid = a.n_tiles < (int64_t)sms * per_sm ? a.n_tiles : (int64_t)sms * per_sm;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
+    SMARL_CUDA(launch_pdl(kern, (unsigned)grid, C::THREADS, smem, st, a));
   });
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;

@@ -63,6 +63,7 @@ struct GaussCfg {
 
 template <int A>
 __global__ void __launch_bounds__(GaussCfg<A>::THREADS) policy_act_gaussian_kernel(const GaussArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   using C = GaussCfg<A>;
   constexpr int QPT = C::QPT, TE = C::TE, H = kPolHidden;
   const int S = a.S, W1S = S * H + 4;
@@ -192,7 +193,7 @@ extern "C" int smarl_policy_act_gaussian(const SmarlGaussianPolicy* p, const flo
     if (per_sm < 1) per_sm = 1;
     a.n_tiles = (ld + C::TE - 1) / C::TE;
     const int64_t grid = a.n_tiles < (int64_t)sms * per_sm ? a.n_tiles : (int64_t)sms * per_sm;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
+    SMARL_CUDA(launch_pdl(kern, (unsigned)grid, C::THREADS, smem, st, a));
   });
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;

@@ -87,6 +87,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int A, int GMAX, int R, int RT>
 __global__ void __launch_bounds__(TcCfg<A, GMAX, R, RT>::THREADS, TcCfg<A, GMAX, R, RT>::THREADS >= 512 ? 2 : 0)
     policy_act_discrete_tc_kernel(const PolicyArgs a) {
+  pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
   using C = TcCfg<A, GMAX, R, RT>;
   constexpr int NWG = C::NWG, H = C::H, NA = C::NA, N = C::N, KST = C::KST, GA = C::GA, AW = C::AW, ROWS = C::ROWS;
   extern __shared__ __align__(128) uint8_t s_raw[];
@@ -370,7 +371,7 @@ static int launch_tc(const PolicyArgs& a_in, int sms, cudaStream_t st) {
   int64_t gx = (int64_t)sms * per_sm / C::NGROUPS;
   if (gx < 1) gx = 1;
   if (gx > a.n_tiles) gx = a.n_tiles;
-  kern<<<dim3((unsigned)gx, C::NGROUPS), C::THREADS, smem, st>>>(a);
+  SMARL_CUDA(launch_pdl(kern, dim3((unsigned)gx, C::NGROUPS), C::THREADS, smem, st, a));
   SMARL_CUDA(cudaGetLastError());
   return SMARL_OK;
 }

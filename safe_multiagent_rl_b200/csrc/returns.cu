@@ -23,6 +23,15 @@ void set_error(const char* fmt, ...) {
 static int g_variant[4] = {-1, -1, -1, -1};
 int kernel_variant(int env_kind) { return (env_kind >= 0 && env_kind < 4) ? g_variant[env_kind] : -1; }
 
+static int g_pdl = -1;                  // -1: not read yet (SMARL_PDL=0 in the environment turns it off)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("SMARL_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 int check_layout(int64_t n_envs, int64_t ld) {
   SMARL_REQUIRE(n_envs >= 1, "n_envs=%lld must be >= 1", (long long)n_envs);
   SMARL_REQUIRE(ld >= n_envs && ld % 16 == 0, "ld=%lld must be a multiple of 16 and >= n_envs=%lld",
@@ -463,6 +472,12 @@ extern "C" int smarl_set_kernel_variant(int32_t env_kind, int32_t lanes) {
   const int prev = g_variant[env_kind];
   if (env_kind == SMARL_KERNEL_POLICY) g_variant[env_kind] = (lanes >= 0 && lanes <= 2) ? lanes : -1;
   else g_variant[env_kind] = (lanes == 0 || lanes == 2 || lanes == 4) ? lanes : -1;
+  return prev;
+}
+
+extern "C" int smarl_set_pdl(int32_t on) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl = on ? 1 : 0;
   return prev;
 }
 

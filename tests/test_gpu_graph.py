@@ -79,3 +79,74 @@ def test_graphed_closed_loop_helper_with_changing_actions():
         eager = env.rollout_closed_loop(lambda obs, t: actions[t], T, lam, 0.999, thresholds=[25.0] * A)
         for k in got:
             assert torch.equal(got[k], eager[k]), (trial, k)
+
+
+@pytest.mark.parametrize("env_name,E", [("coverage", 50), ("coverage", 300_000), ("congestion", 200_000), ("collision", 100_000)])
+def test_programmatic_dependent_launch_does_not_change_results(env_name, E):
+    """smarl_set_pdl: the step kernels are launched with programmatic stream serialization (the next step's CTAs are
+    scheduled while the current kernel drains and block in griddepcontrol.wait).  Back-to-back steps that each read
+    what the previous one wrote give bit-identical state and accounting with the overlap on and off, eagerly and
+    from a CUDA graph."""
+    import safe_multiagent_rl_b200 as s
+    from safe_multiagent_rl_b200 import _lib
+    rng = np.random.default_rng(3)
+    T = 12
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    if env_name == "coverage":
+        A = 16 if E > 50 else 3
+        env = s.BatchedCoverageDiscrete(32, A, n_envs=E, weights=[1.0 + (i % 3) for i in range(A)],
+                                        starts=rng.integers(0, 32, (E, A, 2)))
+        actions = torch.randint(0, 5, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
+        K = A
+    elif env_name == "congestion":
+        A = 8
+        st = rng.integers(0, 10, (E, A, 2)); st[:, 0] = 0
+        env = s.BatchedCongestion(10, A, n_envs=E, noise=0.1, starts=st, demand_rate=rng.random((11, 11)) * 8 + 2, seed=4)
+        actions = torch.randint(0, 5, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
+        K = 1
+    else:
+        A = 3
+        env = s.BatchedCollisionAvoidance(5, A, n_envs=E, starts=rng.random((E, A, 2)) * 5, landmarks=rng.random((E, 1, 2)) * 5)
+        actions = torch.randn((T, 2 * A, env.ld), generator=g, device="cuda") * 0.5
+        K = 1
+    lam = torch.full((K,), 0.2, dtype=torch.float64, device="cuda")
+    buf = env.new_rollout_buffer(T)
+
+    def closed():
+        if env_name == "congestion":
+            env.set_noise_episode(-1)
+        env.reset()
+        for t in range(T):
+            env.step(actions[t], lambdas=lam, out=(buf, t), agent_major=True)
+        out = buf.finish(0.99, [20.0] * K, n_active=getattr(env, "episode_len", None))
+        return {k: out[k].clone() for k in ("R", "modR", "C", "G")}, env.state().clone()
+    lib = _lib.load()
+    prev = lib.smarl_set_pdl(0)
+    try:
+        want, want_pos = closed()
+        assert lib.smarl_set_pdl(1) == 0
+        for _ in range(3):
+            got, got_pos = closed()
+            assert torch.equal(got_pos, want_pos)
+            for k in want:
+                assert torch.equal(got[k], want[k]), k
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            if env_name == "congestion":
+                env.set_noise_episode(-1)
+            env.reset()
+            for t in range(T):
+                env.step(actions[t], lambdas=lam, out=(buf, t), agent_major=True)
+            out = buf.finish(0.99, [20.0] * K, n_active=getattr(env, "episode_len", None))
+        for _ in range(3):
+            env.pos_x.zero_()
+            if env_name == "congestion":
+                env.set_noise_episode(-1)
+            graph.replay()
+            assert torch.equal(env.state(), want_pos)
+            for k in want:
+                assert torch.equal(out[k], want[k]), k
+        assert lib.smarl_set_pdl(1) == 1
+    finally:
+        lib.smarl_set_pdl(prev)
