@@ -424,7 +424,15 @@ def bench_policy_loop(s, a, dev):
     loop = s.GraphedClosedLoop(env1, 50, lambda obs, t: pol1.act(obs), lam1, 0.999, thresholds=[25.0] * 3)
     ms1 = _event_ms(loop.replay, 50)
     out["config1_graphed"] = {"n_envs": 50, "n_agents": 3, "max_t": 50, "ms_per_batch": ms1,
-                              "value_with_policy": 50 * 3 * 50 / (ms1 * 1e-3), "unit": UNIT}
+                              "value_with_policy": 50 * 3 * 50 / (ms1 * 1e-3), "unit": UNIT,
+                              "policy": "BatchedDiscretePolicy (PyTorch glue)"}
+    del loop
+    polf1 = FusedDiscretePolicy(env1, seed=3)
+    loopf = s.GraphedClosedLoop(env1, 50, lambda obs, t: polf1.act(t=t), lam1, 0.999, thresholds=[25.0] * 3)
+    msf = _event_ms(loopf.replay, 50)
+    out["config1_graphed"]["fused"] = {"ms_per_batch": msf, "value_with_policy": 50 * 3 * 50 / (msf * 1e-3),
+                                       "policy": "FusedDiscretePolicy (smarl_policy_act_discrete)"}
+    del loopf
     # BASELINE configs[1] (CollisionAvoidance 5x5, 3 agents, 65 536 envs, T = 50: the reference's default environment) with
     # the reference's ContinuousPolicy (agent.py:48-76) in the loop, one CUDA graph per batch: the fused Gaussian policy
     # kernel (smarl_policy_act_gaussian) against the PyTorch glue

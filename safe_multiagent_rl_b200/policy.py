@@ -124,7 +124,10 @@ class BatchedGaussianPolicy(nn.Module):
     def act(self, obs):
         """actions [A, E, 2] float32 -> ``env.action_buffer`` rows dx0, dy0, dx1, ... in place."""
         d = self.dist(obs)
-        a = d.sample()
+        base = d.base_dist
+        # mu + sigma * eps instead of d.sample(): torch.normal(mean, std) checks std >= 0 on the host, which a CUDA-graph
+        # capture does not allow
+        a = base.loc + base.scale * torch.randn_like(base.loc)
         A, E = self.env.n_agents, self.env.n_envs
         self.env.action_buffer[:, :E].view(A, 2, E).copy_(a.permute(0, 2, 1))
         return self.env.action_buffer, a, d.log_prob(a)
