@@ -29,7 +29,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 EXTRA = {"collision.cu": ["-fmad=false"], "collision_coop.cu": ["-fmad=false"], "coverage_float.cu": ["-fmad=false"]}
 # Heavy files (32 agent-count instantiations per kernel) are compiled as several translation units
 # in parallel: the file is built once per value of -DSMARL_TU=k (see the header of each file).
-TU_SPLIT = {"coverage.cu": 3, "congestion.cu": 7, "collision.cu": 3, "collision_coop.cu": 2, "congestion_coop.cu": 3, "coverage_float.cu": 5}
+TU_SPLIT = {"coverage.cu": 3, "congestion.cu": 7, "collision.cu": 3, "collision_coop.cu": 2, "congestion_coop.cu": 6, "coverage_float.cu": 5}
 
 
 def _nvcc() -> str:

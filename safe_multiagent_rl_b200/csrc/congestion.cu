@@ -43,36 +43,7 @@ __device__ __forceinline__ void congestion_transition(uint32_t (&xw)[A], uint32_
 // per-agent discounted sums (A x 4 envs, f64) live in shared memory, indexed
 // [agent][env lane][thread] so that every access is conflict-free.
 // ---------------------------------------------------------------------------------------
-struct CongestionRolloutArgs {
-  const uint8_t* start_x;
-  const uint8_t* start_y;
-  const uint8_t* actions;   // [T][A][ld]
-  const uint8_t* moves;     // [T][A][ld] (MODE 1)
-  const double* lambdas;
-  uint8_t* final_x;
-  uint8_t* final_y;
-  float* R;
-  float* modR;
-  int32_t* C;
-  float* G;                 // [T][A][ld]
-  float* g_scratch;         // [T][ld] penalties (g_mode 1)
-  double* partials;
-  const double* thresholds;
-  const double* demand;
-  const float* wait_reward;
-  double gamma;
-  uint64_t keep_threshold;
-  uint64_t seed;
-  int64_t env_offset;
-  int64_t n_groups;
-  int64_t n_envs;
-  int64_t ld;
-  int32_t size;
-  int32_t n_steps;
-  int32_t g_mode;
-  uint32_t episode;
-  const uint32_t* episode_dev;
-};
+// (CongestionRolloutArgs lives in congestion.cuh: the cooperative rollout kernel of congestion_coop.cu shares it)
 
 constexpr int kCongRollThreads = 64;
 
@@ -369,6 +340,15 @@ static int congestion_coop_lanes(int A) {
   return A >= 12 ? 4 : 0;       // closed loop, of the HBM peak: A = 12 0.63 -> 0.68, 16 0.56 -> 0.65, 20 0.38 -> 0.60, 32 0.30 -> 0.48
 }
 
+// The fused rollout: 0 = one thread per four envs (this file), 4 = lane-cooperative rollout (congestion_coop.cu; a
+// forced 2 also takes it, the rollout is built for four lanes only).  B200, 2^20 envs, T = 20 (profiles/r02).
+static int congestion_coop_rollout_lanes(int A) {
+  if (A < 9) return 0;
+  const int forced = kernel_variant(SMARL_ENV_CONGESTION);
+  if (forced >= 0) return forced ? 4 : 0;
+  return A >= 12 ? 4 : 0;       // fused ms per 2^20 envs x T = 20: A = 12 1.12 -> 1.09, 16 1.75 -> 1.55, 24 3.90 -> 3.01, 32 9.33 -> 4.80
+}
+
 static int check_congestion(const SmarlCongestionParams* p) {
   SMARL_REQUIRE(p != nullptr, "params is NULL");
   SMARL_REQUIRE(p->size >= 1 && p->size <= 254, "size=%d outside 1..254", p->size);
@@ -450,6 +430,15 @@ extern "C" int smarl_congestion_rollout(const SmarlCongestionParams* p, const Sm
   a.episode = p->episode; a.episode_dev = p->episode_dev;
   const unsigned grid = (unsigned)((a.n_groups + kCongRollThreads - 1) / kCongRollThreads);
   cudaStream_t s = (cudaStream_t)stream;
+  if (congestion_coop_rollout_lanes(p->n_agents)) {
+    unsigned coop_grid = 0;
+    if (int rc = p->noise_mode == 0 ? launch_congestion_coop_rollout_m0(p->n_agents, a, &coop_grid, s)
+               : p->noise_mode == 1 ? launch_congestion_coop_rollout_m1(p->n_agents, a, &coop_grid, s)
+                                    : launch_congestion_coop_rollout_m2(p->n_agents, a, &coop_grid, s))
+      return rc;
+    if (stats) return launch_stats_finalize(stats_scratch, coop_grid, p->n_agents, 1, n_envs, stats, s);
+    return SMARL_OK;
+  }
   if (int rc = launch_congestion_rollout(p->noise_mode, p->n_agents, a, grid, s)) return rc;
   if (stats)
     return launch_stats_finalize(stats_scratch, grid, p->n_agents, 1, n_envs, stats, s);

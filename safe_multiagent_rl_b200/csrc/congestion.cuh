@@ -190,9 +190,44 @@ struct CongestionStepArgs {
   const uint32_t* episode_dev;
 };
 
+struct CongestionRolloutArgs {
+  const uint8_t* start_x;
+  const uint8_t* start_y;
+  const uint8_t* actions;   // [T][A][ld]
+  const uint8_t* moves;     // [T][A][ld] (MODE 1)
+  const double* lambdas;
+  uint8_t* final_x;
+  uint8_t* final_y;
+  float* R;
+  float* modR;
+  int32_t* C;
+  float* G;                 // [T][A][ld]
+  float* g_scratch;         // [T][ld] penalties (g_mode 1)
+  double* partials;
+  const double* thresholds;
+  const double* demand;
+  const float* wait_reward;
+  double gamma;
+  uint64_t keep_threshold;
+  uint64_t seed;
+  int64_t env_offset;
+  int64_t n_groups;
+  int64_t n_envs;
+  int64_t ld;
+  int32_t size;
+  int32_t n_steps;
+  int32_t g_mode;
+  uint32_t episode;
+  const uint32_t* episode_dev;
+};
+
 int launch_congestion_coop_step_m0(int A, int S, const CongestionStepArgs& a, cudaStream_t st);
 int launch_congestion_coop_step_m1(int A, int S, const CongestionStepArgs& a, cudaStream_t st);
 int launch_congestion_coop_step_m2(int A, int S, const CongestionStepArgs& a, cudaStream_t st);
+// fused rollout, four lanes per env quad (congestion_coop.cu); *grid returns the CTA count (= rows of stats partials)
+int launch_congestion_coop_rollout_m0(int A, const CongestionRolloutArgs& a, unsigned* grid, cudaStream_t st);
+int launch_congestion_coop_rollout_m1(int A, const CongestionRolloutArgs& a, unsigned* grid, cudaStream_t st);
+int launch_congestion_coop_rollout_m2(int A, const CongestionRolloutArgs& a, unsigned* grid, cudaStream_t st);
 
 // Waiting-branch reward in f64, the reference's operation order (congestion.py:86-87).
 __device__ __forceinline__ double congestion_reward_f64(uint32_t con, uint32_t nx, uint32_t ny,

@@ -20,8 +20,10 @@
 // Philox noise (MODE 2): one generator block serves four agents of one env, so the 4 * ceil(A/4) blocks of a
 // quad are spread over the S lanes and handed out through shared memory (no lane evaluates a block twice).
 #include "congestion.cuh"
+#include "stats.cuh"
 
-// Built as three translation units, one per noise mode (build.py passes -DSMARL_TU=0|1|2).
+// Built as six translation units (build.py passes -DSMARL_TU=k): step kernels of noise mode k = 0..2, fused rollout
+// kernels of noise mode k - 3 = 0..2.
 #ifndef SMARL_TU
 #define SMARL_TU -1
 #endif
@@ -245,6 +247,303 @@ __global__ void __launch_bounds__(kCongCoopThreads, 4) congestion_coop_step_kern
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused open-loop episode on the same lane mapping (S = 4): T steps of the kernel above with the positions in
+// registers, plus the accounting of congestion_rollout_kernel (congestion.cu) -- per-agent discounted sums in f64
+// (shared memory, [own agent][env lane][thread]: conflict-free), the shared constraint's cost / penalty sums (every
+// lane of a group carries them redundantly), G in g_mode 1 / 2, block partials of the stats vector.  The one-thread
+// rollout needs 255 registers plus spills from A ~ 20 and falls BEHIND the closed loop of cooperative step launches
+// (A = 32, 2^20 envs, T = 50: 22.9 ms fused against 14.4 ms closed); this one keeps the fused path ahead.
+// Same per-(agent, env) accumulation order as the one-thread kernel: R, modR, C, G are bit-identical to it.
+// ---------------------------------------------------------------------------------------
+template <int A, int S>
+struct CongCoopRoll {
+  using C = CongCoop<A, S>;
+  static constexpr size_t kRec = (size_t)C::EPC * C::PQ * sizeof(uint4);
+  static constexpr size_t kSmem = kRec + (size_t)C::B * 4 * kCongCoopThreads * sizeof(double);
+};
+
+// Sum of v over the CTA separately for every lane slot s (lanes of one slot are EPW consecutive lanes of each warp);
+// the result for slot s' is valid on thread s' < S.  s_red: (threads / 32) * S doubles.  Fixed order.
+template <int S>
+__device__ __forceinline__ double slot_block_sum(double v, double* s_red, int s, int q) {
+  constexpr int EPW = 32 / S;
+#pragma unroll
+  for (int o = EPW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (q == 0) s_red[(threadIdx.x >> 5) * S + s] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < S) {
+#pragma unroll
+    for (int w = 0; w < kCongCoopThreads / 32; ++w) r += s_red[w * S + threadIdx.x];
+  }
+  __syncthreads();
+  return r;
+}
+
+template <int A, int S, int MODE>
+__global__ void __launch_bounds__(kCongCoopThreads, 3) congestion_coop_rollout_kernel(const CongestionRolloutArgs a) {
+  using C = CongCoop<A, S>;
+  constexpr int B = C::B, EPW = C::EPW, EPC = C::EPC, NQ = C::NQ;
+  extern __shared__ uint4 s_rec[];                                 // [EPC][PQ] records / Philox blocks, then the sums
+  double* s_acc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_rec) + CongCoopRoll<A, S>::kRec);
+  __shared__ double s_red[(kCongCoopThreads / 32) * S];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int q = lane % EPW, s = lane / EPW;
+  const int ql = warp * EPW + q;
+  const int64_t gq = (int64_t)blockIdx.x * EPC + ql;
+  const bool live = gq < a.n_groups;
+  const uint32_t ld = (uint32_t)a.ld;
+  const uint32_t e0 = (uint32_t)(live ? gq : 0) * 4u;
+  const uint32_t row0 = (uint32_t)s * ld + e0;                     // 32-bit element offsets (host-checked: A * ld < 2^32)
+  const uint32_t k01 = 0x01010101u;
+  const int T = a.n_steps, W = a.size + 1;
+  const uint32_t size4 = (uint32_t)a.size * k01;
+  const bool small_key = a.size <= 84;
+  const uint32_t never = (a.size <= 42 || (a.size > 84 && a.size <= 127)) ? 0x7F7F7F7Fu : 0xFFFFFFFFu;
+  const double lam = a.lambdas ? __ldg(a.lambdas) : 0.0;
+  const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const uint32_t episode = a.episode + ((MODE == 2 && a.episode_dev) ? __ldg(a.episode_dev) : 0u);
+  const int64_t env0 = a.env_offset + (int64_t)e0;
+  uint4* rec = s_rec + ql * C::PQ;
+
+  uint32_t xw[B], yw[B];
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    const bool own = !C::kGhost || j < B - 1 || j * S + s < A;
+    const uint32_t off = row0 + (uint32_t)(j * S) * ld;
+    xw[j] = own ? ld_stream_u32(a.start_x + off) : 0xFFFFFFFFu;
+    yw[j] = own ? ld_stream_u32(a.start_y + off) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_acc[(j * 4 + k) * kCongCoopThreads + tid] = 0.0;
+  }
+  double s_pen[4] = {0, 0, 0, 0};
+  int csum[4] = {0, 0, 0, 0};
+  double disc = 1.0;
+
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    uint32_t aw[B], mw[B];
+    {
+      const uint8_t* act_t = a.actions + (int64_t)t * A * a.ld;      // uniform; per-thread offsets stay 32-bit
+      const uint8_t* mov_t = MODE == 1 ? a.moves + (int64_t)t * A * a.ld : nullptr;
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint32_t off = row0 + (uint32_t)(j * S) * ld;
+        if (!C::kGhost || j < B - 1 || j * S + s < A) {
+          aw[j] = ld_stream_u32(act_t + off);
+          mw[j] = MODE == 1 ? ld_stream_u32(mov_t + off) : aw[j];
+        } else {
+          aw[j] = mw[j] = 0x04040404u;
+        }
+      }
+    }
+    if (MODE == 2) {                                                // as in the step kernel, with this step's t
+      uint4* wq = rec;
+#pragma unroll
+      for (int m = 0; m * S < 4 * NQ; ++m) {
+        const int b = m * S + s;
+        if (4 * NQ % S == 0 || b < 4 * NQ) {
+          const uint64_t id = (uint64_t)(env0 + (b & 3));
+          wq[b] = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t,
+                                           (uint32_t)(b >> 2) | (episode << 3)), key);
+        }
+      }
+      __syncwarp();
+      const uint32_t* ww = reinterpret_cast<const uint32_t*>(wq);
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const int i = j * S + s;
+        uint32_t m4 = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t w = ww[(((i >> 2) * 4 + k) << 2) + (i & 3)];
+          const uint32_t act = (aw[j] >> (8 * k)) & 0xFFu;
+          const uint32_t mv = ((uint64_t)w < a.keep_threshold) ? act : w % 5u;
+          m4 |= mv << (8 * k);
+        }
+        if (!C::kGhost || j < B - 1 || i < A) mw[j] = m4;
+      }
+      __syncwarp();                                                 // the records below reuse the block buffer
+    }
+
+    // transition (congestion.py:49-75) and the records every lane of the group scans
+    uint32_t k0[B], k1[B], k2[B];
+    uint32_t at_origin = 0u;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const bool own = !C::kGhost || j < B - 1 || j * S + s < A;
+      const uint32_t ox = xw[j], oy = yw[j];
+      grid_move4(xw[j], yw[j], mw[j], size4);
+      k0[j] = small_key ? ox + 2u * xw[j] : xw[j];
+      k1[j] = small_key ? oy + 2u * yw[j] : yw[j];
+      k2[j] = small_key ? 0u : (((xw[j] + k01) - ox) | (((yw[j] + k01) - oy) << 2));
+      if (!own) {
+        if (small_key) k0[j] = never;
+        else k2[j] = never;
+        xw[j] = yw[j] = 0xFFFFFFFFu;                                // a padding agent stays off the grid
+      }
+      rec[j * S + s] = make_uint4(k0[j], k1[j], k2[j], own ? ((((aw[j] >> 2) & k01) ^ k01) << 7) : 0u);
+      if (own) at_origin += zero_bytes01(xw[j] | yw[j]);           // congestion.py:97
+    }
+    __syncwarp();
+    uint32_t r[B], seen[B], z[B];
+    if (a.size <= 42) congestion_scan<A, S, 2, true>(rec, k0, k1, k2, s, r, seen, z);
+    else if (a.size <= 84) congestion_scan<A, S, 2, false>(rec, k0, k1, k2, s, r, seen, z);
+    else if (a.size <= 127) congestion_scan<A, S, 3, true>(rec, k0, k1, k2, s, r, seen, z);
+    else congestion_scan<A, S, 3, false>(rec, k0, k1, k2, s, r, seen, z);
+#pragma unroll
+    for (int off = 1; off < S; off <<= 1) at_origin += __shfl_xor_sync(0xffffffffu, at_origin, off * EPW);
+
+    // congestion.py:93-100 and meta_agent.py:21-22; identical on every lane of the group
+    const int cost[4] = {max(0, A / 3 - (int)(at_origin & 0xFFu)), max(0, A / 3 - (int)((at_origin >> 8) & 0xFFu)),
+                         max(0, A / 3 - (int)((at_origin >> 16) & 0xFFu)), max(0, A / 3 - (int)(at_origin >> 24))};
+    float pen[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pen[k] = (float)(lam * cost[k]);                              // the step kernel publishes the penalty as f32
+      s_pen[k] += disc * (double)pen[k];
+      csum[k] += cost[k];
+    }
+    if (a.g_mode == 1 && live && s == 0)
+      st_stream_f4(a.g_scratch + (int64_t)t * a.ld + e0, make_float4(pen[0], pen[1], pen[2], pen[3]));
+    float* G_t = a.G + (int64_t)t * A * a.ld;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      if (C::kGhost && j == B - 1 && j * S + s >= A) continue;
+      const uint32_t conw = (r[j] - z[j] - k01) & __umulhi(seen[j], 0xFFu << 25);
+      const float4 r4 = a.wait_reward ? congestion_reward4<true>(aw[j], conw, xw[j], yw[j], a.demand, W, a.wait_reward)
+                                      : congestion_reward4<false>(aw[j], conw, xw[j], yw[j], a.demand, W, nullptr);
+      const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_acc[(j * 4 + k) * kCongCoopThreads + tid] += disc * (double)rr[k];
+      const uint32_t off = row0 + (uint32_t)(j * S) * ld;
+      if (a.g_mode == 1 && live) {
+        st_stream_f4(G_t + off, r4);
+      } else if (a.g_mode == 2 && live) {                           // agent.py:129-132
+        st_stream_f4(G_t + off,
+                     make_float4((float)(disc * ((double)rr[0] - (double)pen[0])), (float)(disc * ((double)rr[1] - (double)pen[1])),
+                                 (float)(disc * ((double)rr[2] - (double)pen[2])), (float)(disc * ((double)rr[3] - (double)pen[3]))));
+      }
+    }
+    disc *= a.gamma;
+    __syncwarp();                                                   // the next step overwrites the records
+  }
+
+  bool valid[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) valid[k] = live && ((int64_t)e0 + k < a.n_envs);
+  double* out = a.partials ? a.partials + (int64_t)blockIdx.x * stats_len(A, 1) : nullptr;
+  if (live && s == 0) st_stream_i4(a.C + e0, make_int4(csum[0], csum[1], csum[2], csum[3]));
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    const bool own = !C::kGhost || j < B - 1 || j * S + s < A;
+    const uint32_t off = row0 + (uint32_t)(j * S) * ld;
+    double raw[4], mod[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      raw[k] = s_acc[(j * 4 + k) * kCongCoopThreads + tid];
+      mod[k] = raw[k] - s_pen[k];
+    }
+    if (live && own) {
+      if (a.final_x) st_stream_u32(a.final_x + off, xw[j]);
+      if (a.final_y) st_stream_u32(a.final_y + off, yw[j]);
+      st_stream_f4(a.R + off, make_float4((float)raw[0], (float)raw[1], (float)raw[2], (float)raw[3]));
+      st_stream_f4(a.modR + off, make_float4((float)mod[0], (float)mod[1], (float)mod[2], (float)mod[3]));
+    }
+    if (out) {                                                      // uniform
+      double v_raw = 0.0, v_mod = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v_raw += (valid[k] && own) ? raw[k] : 0.0;
+        v_mod += (valid[k] && own) ? mod[k] : 0.0;
+      }
+      const double b_raw = slot_block_sum<S>(v_raw, s_red, s, q);
+      const double b_mod = slot_block_sum<S>(v_mod, s_red, s, q);
+      if (tid < S && j * S + tid < A) {
+        out[2 + j * S + tid] = b_raw;
+        out[2 + A + j * S + tid] = b_mod;
+      }
+    }
+  }
+  if (out) {
+    const double thr = a.thresholds ? __ldg(a.thresholds) : 0.0;
+    double c = 0.0, viol = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c += (valid[k] && s == 0) ? (double)csum[k] : 0.0;
+      viol += (valid[k] && s == 0 && a.thresholds && (double)csum[k] > thr) ? 1.0 : 0.0;
+    }
+    const double bc = slot_block_sum<S>(c, s_red, s, q);
+    const double bv = slot_block_sum<S>(viol, s_red, s, q);
+    if (tid == 0) {
+      out[0] = bc;
+      out[1] = bv;
+      out[2 + 2 * A] = 0.0;
+    }
+  }
+
+  if (a.g_mode == 1) {                                              // agent.py:200-206, in place over the stored rewards
+    __threadfence_block();                                          // lane s = 0 wrote the penalties all lanes read back
+    __syncwarp();
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < B; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_acc[(j * 4 + k) * kCongCoopThreads + tid] = 0.0;
+      for (int t = T - 1; t >= 0; --t) {
+        const float4 qv = ld_f4(a.g_scratch + (int64_t)t * a.ld + e0);
+        const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+        float* G_t = a.G + (int64_t)t * A * a.ld;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          if (C::kGhost && j == B - 1 && j * S + s >= A) continue;
+          float* gp = G_t + (row0 + (uint32_t)(j * S) * ld);
+          const float4 rv = ld_f4(gp);
+          const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+          float o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            double& run = s_acc[(j * 4 + k) * kCongCoopThreads + tid];
+            run = ((double)rr[k] - (double)qq[k]) + a.gamma * run;
+            o[k] = (float)run;
+          }
+          st_stream_f4(gp, make_float4(o[0], o[1], o[2], o[3]));
+        }
+      }
+    }
+  }
+}
+
+template <int MODE>
+static int launch_roll(int A, const CongestionRolloutArgs& a, unsigned* grid_out, cudaStream_t st) {
+  switch (A) {
+#define SMARL_COOP_CASE(N)                                                                              \
+  case N: {                                                                                             \
+    using C = CongCoop<N, 4>;                                                                           \
+    auto kern = congestion_coop_rollout_kernel<N, 4, MODE>;                                             \
+    const size_t smem = CongCoopRoll<N, 4>::kSmem;                                                      \
+    if (smem + 256 > 48 * 1024)                                                                         \
+      SMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    const unsigned grid = (unsigned)((a.n_groups + C::EPC - 1) / C::EPC);                               \
+    kern<<<grid, kCongCoopThreads, smem, st>>>(a);                                                      \
+    *grid_out = grid;                                                                                   \
+  } break;
+    SMARL_COOP_CASE(9) SMARL_COOP_CASE(10) SMARL_COOP_CASE(11) SMARL_COOP_CASE(12) SMARL_COOP_CASE(13)
+    SMARL_COOP_CASE(14) SMARL_COOP_CASE(15) SMARL_COOP_CASE(16) SMARL_COOP_CASE(17) SMARL_COOP_CASE(18)
+    SMARL_COOP_CASE(19) SMARL_COOP_CASE(20) SMARL_COOP_CASE(21) SMARL_COOP_CASE(22) SMARL_COOP_CASE(23)
+    SMARL_COOP_CASE(24) SMARL_COOP_CASE(25) SMARL_COOP_CASE(26) SMARL_COOP_CASE(27) SMARL_COOP_CASE(28)
+    SMARL_COOP_CASE(29) SMARL_COOP_CASE(30) SMARL_COOP_CASE(31) SMARL_COOP_CASE(32)
+#undef SMARL_COOP_CASE
+    default:
+      set_error("cooperative Congestion kernels cover n_agents 9..32 (got %d)", A);
+      return SMARL_EUNSUPPORTED;
+  }
+  SMARL_CUDA(cudaGetLastError());
+  return SMARL_OK;
+}
+
 template <int S, int MODE>
 static int launch_sm(int A, const CongestionStepArgs& a, cudaStream_t st) {
   switch (A) {
@@ -284,6 +583,19 @@ SMARL_DEFINE_CONG_COOP(1)
 #endif
 #if SMARL_TU_IS(2)
 SMARL_DEFINE_CONG_COOP(2)
+#endif
+#define SMARL_DEFINE_CONG_COOP_ROLL(M)                                                                         \
+  int launch_congestion_coop_rollout_m##M(int A, const CongestionRolloutArgs& a, unsigned* grid, cudaStream_t st) { \
+    return launch_roll<M>(A, a, grid, st);                                                                     \
+  }
+#if SMARL_TU_IS(3)
+SMARL_DEFINE_CONG_COOP_ROLL(0)
+#endif
+#if SMARL_TU_IS(4)
+SMARL_DEFINE_CONG_COOP_ROLL(1)
+#endif
+#if SMARL_TU_IS(5)
+SMARL_DEFINE_CONG_COOP_ROLL(2)
 #endif
 
 }  // namespace smarl

@@ -89,3 +89,39 @@ def test_congestion_coop_no_noise_and_closed_loop(lanes):
     with _lib.kernel_variant(_lib.ENV_CONGESTION, lanes):
         tp.test_congestion_step_matches_oracle(3, 16, 64, 10, 0.0, 0, "philox")    # noise 0: mode 0 kernel
         tp.test_congestion_closed_loop_returns()
+
+
+@pytest.mark.parametrize("A", AGENTS)
+@pytest.mark.parametrize("g_mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", ["philox", "recorded"])
+def test_congestion_coop_rollout(A, g_mode, mode):
+    """The lane-cooperative fused rollout (congestion_coop_rollout_kernel) against the oracle: tiny grids (heavy edge
+    sharing), ragged env counts, agent counts with and without padding agents."""
+    with _lib.kernel_variant(_lib.ENV_CONGESTION, 4):
+        tp.test_congestion_fused_rollout(2 + A % 5, A, 90 + A, 9, 0.3, 800 + A, g_mode, mode)
+
+
+@pytest.mark.parametrize("size,A,E", [(10, 12, 1000), (64, 32, 777), (100, 20, 130), (200, 27, 517)])
+def test_congestion_coop_rollout_is_bit_identical_to_the_one_thread_rollout(size, A, E):
+    """Same per-(agent, env) accumulation order in both mappings: R, modR, C, G and the final positions agree bit for
+    bit; the stats vector (a sum over envs in a different order) within f64 rounding.  Covers all four edge-key widths."""
+    s = tp.smarl()
+    rng = np.random.default_rng(size + A)
+    T = 15
+    st = rng.integers(0, size + 1, (E, A, 2)); st[:, 0] = 0
+    demand = rng.random((size + 1, size + 1)) * 8 + 2
+    g = torch.Generator(device="cuda"); g.manual_seed(A)
+    lam = torch.full((1,), 0.3, dtype=torch.float64, device="cuda")
+    actions, outs = None, []
+    for lanes in (0, 4):
+        with _lib.kernel_variant(_lib.ENV_CONGESTION, lanes):
+            env = s.BatchedCongestion(size, A, n_envs=E, noise=0.2, starts=st, demand_rate=demand, seed=9)
+            if actions is None:
+                actions = torch.randint(0, 5, (T, A, env.ld), generator=g, device="cuda", dtype=torch.uint8)
+            out = env.rollout(actions, lambdas=lam, gamma=0.97, thresholds=[3.0], g_mode=1)
+            outs.append(({k: out[k].clone() for k in ("R", "modR", "C", "G")}, env.state().clone(), out["stats"].vec.clone()))
+    a, b = outs
+    assert torch.equal(a[1], b[1])
+    for k in a[0]:
+        assert torch.equal(a[0][k], b[0][k]), k
+    assert torch.allclose(a[2], b[2], rtol=1e-12, atol=1e-9)
