@@ -35,7 +35,10 @@ def heads(pol, obs):
 @pytest.mark.parametrize("kind,A,E,shuffle", [("collision", 3, 50, False), ("collision", 16, 1000, False),
                                               ("collision", 5, 4099, True), ("collision", 32, 70, False),
                                               ("coverage", 3, 333, False), ("coverage", 8, 2000, False),
-                                              ("collision", 1, 20, False)])
+                                              ("collision", 1, 20, False),
+                                              # several tiles per persistent CTA
+                                              ("collision", 16, 20000, False), ("coverage", 3, 160001, False),
+                                              ("collision", 8, 40001, True)])
 def test_fused_gaussian_policy_matches_torch_and_the_philox_oracle(kind, A, E, shuffle):
     env, pol = make(kind, A, E, env_offset=7_000_000_000, shuffle=shuffle)
     obs = env.reset()
