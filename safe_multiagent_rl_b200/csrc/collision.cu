@@ -21,31 +21,12 @@ constexpr int kPairPrefilterA = 12;   // agent count from which the pair loop is
 
 // One CollisionAvoidance.step for one env held in registers.  Returns the env reward (same for
 // every agent) and the collision count; updates px/py/done_mask in place.
+// MOVED: the transition (collision_avoidance.py:103-121) was already applied by collision_transition_compact.
 template <int A>
 __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)[A], uint32_t& done_mask,
-                                                   const float (&adx)[A], const float (&ady)[A],
                                                    const double* __restrict__ lm, int64_t ld, int L,
                                                    double size, double agents_size, double& reward,
                                                    int& collisions) {
-  // transition, collision_avoidance.py:103-121
-#pragma unroll
-  for (int i = 0; i < A; ++i) {
-    if ((done_mask >> i) & 1u) continue;
-    double dx = (double)adx[i], dy = (double)ady[i];
-    // :113  fp32-origin components: dx**2 == dx*dx exactly, so this is the reference's norm
-    // sqrt_rn is monotonic with sqrt_rn(1) == 1, so norm > 1 needs q > 1: the sqrt (and the two
-    // divisions) are only evaluated for actions that can actually be clipped.
-    const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    if (q > 1.0) {
-      const double norm = __dsqrt_rn(q);
-      if (norm > 1.0) {                                     // :114-117
-        dx = __ddiv_rn(dx, norm);
-        dy = __ddiv_rn(dy, norm);
-      }
-    }
-    px[i] = fmax(0.0, fmin(size, __dadd_rn(px[i], dx)));   // :118
-    py[i] = fmax(0.0, fmin(size, __dadd_rn(py[i], dy)));   // :119
-  }
   // landmark reach (:122-124) and per-agent min landmark distance (:158-161).  Both compare / minimise
   // square roots; sqrt_rn is monotonic, so the reach test is decided on the squared norm outside a
   // 1e-9 band around agents_size^2 and the minimum is taken over the squared distances, leaving ONE
@@ -145,8 +126,12 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
 template <int A, bool CAP>
 __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_kernel(const CollisionStepArgs a) {
   pdl_prologue();   // programmatic dependent launch: the previous grid has completed past this point (common.cuh)
-  const int64_t e = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
-  if (e >= a.n_envs) return;
+  __shared__ double2 s_clip[A <= SMARL_COLL_COMPACT_MAX_A ? kCollThreads / 32 : 1][A <= SMARL_COLL_COMPACT_MAX_A ? kClipSlots : 1];   // 4 KB, or a dummy
+  constexpr bool kCompact = A <= SMARL_COLL_COMPACT_MAX_A;
+  const int64_t eg = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
+  const bool live = eg < a.n_envs;
+  if (!kCompact && !live) return;                             // compaction is warp-wide: there every lane stays
+  const int64_t e = live ? eg : a.n_envs - 1;
   const int64_t ld = a.ld;
   double px[A], py[A];
   float adx[A], ady[A];
@@ -161,12 +146,18 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_ke
   }
   const int32_t steps_before = a.episode_len ? a.episode_len[e] : 0;
   const uint32_t all = A == 32 ? 0xFFFFFFFFu : ((1u << A) - 1u);
-  const bool active = done_mask != all;                       // main.py:51: episode already over
+  const bool active = live && done_mask != all;               // main.py:51: episode already over
   double reward = 0.0;
   int collisions = 0;
-  if (active)
-    collision_env_step<A>(px, py, done_mask, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size,
-                          reward, collisions);
+  if constexpr (kCompact) {
+    collision_transition_compact<A>(px, py, done_mask, active, adx, ady, a.size, s_clip[threadIdx.x >> 5]);
+    if (!live) return;
+    if (active)
+      collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+  } else if (active) {
+    collision_transition_inline<A>(px, py, done_mask, adx, ady, a.size);
+    collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+  }
   const float rf = (float)reward;
 #pragma unroll
   for (int i = 0; i < A; ++i) {
@@ -236,6 +227,7 @@ template <int A, bool CAP>
 //  A = 5..8 is held to 5 CTAs per SM / 96 registers: fused A = 6 +13 %, A = 8 +7 % on 2^20..2^21 envs)
 __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5 : 0))) collision_rollout_kernel(const CollisionRolloutArgs a) {
   __shared__ double s_red[kCollThreads / 32];
+  __shared__ double2 s_clip[kCollThreads / 32][kClipSlots];
   const int64_t eg = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
   const bool live = eg < a.n_envs;
   const int64_t e = live ? eg : 0;
@@ -255,15 +247,18 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5
   for (int t = 0; t < T; ++t) {
     double reward = 0.0;
     int collisions = 0;
-    if (done_mask != all) {
+    const bool active = done_mask != all;               // main.py:51 (lanes past n_envs replay env 0 and store nothing)
+    {
       float adx[A], ady[A];
 #pragma unroll
       for (int i = 0; i < A; ++i) {
-        adx[i] = a.actions[((int64_t)t * 2 * A + 2 * i) * ld + e];
-        ady[i] = a.actions[((int64_t)t * 2 * A + 2 * i + 1) * ld + e];
+        adx[i] = active ? a.actions[((int64_t)t * 2 * A + 2 * i) * ld + e] : 0.f;
+        ady[i] = active ? a.actions[((int64_t)t * 2 * A + 2 * i + 1) * ld + e] : 0.f;
       }
-      collision_env_step<A>(px, py, done_mask, adx, ady, a.landmarks + e, ld, a.L, a.size, a.agents_size,
-                            reward, collisions);
+      collision_transition_compact<A>(px, py, done_mask, active, adx, ady, a.size, s_clip[threadIdx.x >> 5]);
+    }
+    if (active) {
+      collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
       ++steps;
     }
     const float rf = (float)reward;

@@ -146,6 +146,94 @@ __device__ __forceinline__ void collision_move_agent(double& px, double& py, flo
   py = fmax(0.0, fmin(size, __dadd_rn(py, dy)));         // :119
 }
 
+// The transition of all agents of one env (collision_avoidance.py:103-121), clips inline per agent slot.
+template <int A>
+__device__ __forceinline__ void collision_transition_inline(double (&px)[A], double (&py)[A], uint32_t done_mask,
+                                                            const float (&adx)[A], const float (&ady)[A], double size) {
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    if ((done_mask >> i) & 1u) continue;
+    collision_move_agent(px[i], py[i], adx[i], ady[i], size);
+  }
+}
+
+// Agent counts up to which the one-thread STEP kernel compacts its clips over the warp (measured on B200, closed loop,
+// ms per 2^20 envs x T = 50, inline -> compacted: A = 3 2.63 -> 2.35, A = 4 3.20 -> 2.87, A = 5 4.57 -> 3.75, A = 6
+// 5.18 -> 4.75, A = 7 5.94 -> 5.56, A = 8 6.78 -> 7.82: the rank bookkeeping lifts the step kernel from ~100 to 140
+// registers there).  The fused rollout gains at every A measured (A = 8: 3.71 -> 3.35 ms).
+#ifndef SMARL_COLL_COMPACT_MAX_A
+#define SMARL_COLL_COMPACT_MAX_A 7
+#endif
+
+constexpr int kClipSlots = 64;        // compacted action clips per warp and step (two rounds of 32 lanes)
+
+// The action clip of collision_move_agent (collision_avoidance.py:113-117) for one agent whose squared norm exceeds 1,
+// out of line: norm = sqrt(dx^2 + dy^2); if norm > 1 both components are divided by it.
+static __device__ __noinline__ double2 clip_action(float adx, float ady) {
+  double dx = (double)adx, dy = (double)ady;
+  const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+  const double norm = __dsqrt_rn(q);
+  if (norm > 1.0) {
+    dx = __ddiv_rn(dx, norm);
+    dy = __ddiv_rn(dy, norm);
+  }
+  return make_double2(dx, dy);
+}
+
+// The transition of all A agents of one env per thread (collision_avoidance.py:103-121) with the action clips of the
+// WARP compacted.  The clip costs an f64 square root and two f64 divisions (~150 instructions); only actions longer
+// than 1 need it (13 % with N(0, 0.5^2) components), but some lane of every warp does for every agent slot, so inlined
+// per slot the whole warp pays it A times per step -- 450 of the ~790 instructions per env-step at A = 3.  Here every
+// agent that needs a clip gets a rank (ballot + popc), posts its f32 action to shared memory, the lanes work the
+// posted list off round-robin (ceil(n / 32) rounds instead of A) and the owners pick their f64 result up.  Ranks beyond
+// the kClipSlots slots (an unusually clip-heavy warp) are evaluated in place.  Same arithmetic, same bits.
+// Must be called by all 32 lanes of the warp; `active` = this lane's env takes the step at all.  clip: kClipSlots
+// double2 slots of this warp.
+template <int A>
+__device__ __forceinline__ void collision_transition_compact(double (&px)[A], double (&py)[A], uint32_t done_mask,
+                                                             bool active, const float (&adx)[A], const float (&ady)[A],
+                                                             double size, double2* __restrict__ clip) {
+  const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+  uint32_t need = 0u;
+  uint32_t rk[(A + 3) / 4];                             // rank per agent, one byte each (>= kClipSlots: in place)
+#pragma unroll
+  for (int w = 0; w < (A + 3) / 4; ++w) rk[w] = 0u;
+  int n_clip = 0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    const double dx = (double)adx[i], dy = (double)ady[i];
+    // :113  fp32-origin components: dx**2 == dx*dx exactly, so this is the reference's norm; sqrt_rn is monotonic
+    // with sqrt_rn(1) == 1, so norm > 1 needs q > 1
+    const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    const bool nd = active && !((done_mask >> i) & 1u) && q > 1.0;
+    const unsigned b = __ballot_sync(0xffffffffu, nd);
+    const int r = min(n_clip + __popc(b & lt), kClipSlots);
+    n_clip += __popc(b);
+    need |= nd ? (1u << i) : 0u;
+    rk[i >> 2] |= (uint32_t)r << (8 * (i & 3));
+    if (nd && r < kClipSlots) *reinterpret_cast<float2*>(clip + r) = make_float2(adx[i], ady[i]);
+  }
+  __syncwarp();
+  for (int r = (int)lane; r < min(n_clip, kClipSlots); r += 32) {
+    const float2 in = *reinterpret_cast<const float2*>(clip + r);
+    clip[r] = clip_action(in.x, in.y);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    double2 d = make_double2((double)adx[i], (double)ady[i]);
+    if ((need >> i) & 1u) {
+      const int r = (int)((rk[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+      d = r < kClipSlots ? clip[r] : clip_action(adx[i], ady[i]);
+    }
+    if (active && !((done_mask >> i) & 1u)) {
+      px[i] = fmax(0.0, fmin(size, __dadd_rn(px[i], d.x)));      // :118
+      py[i] = fmax(0.0, fmin(size, __dadd_rn(py[i], d.y)));      // :119
+    }
+  }
+  __syncwarp();                         // the slots are reused by the next step
+}
+
 // One (agent, landmark) pair: landmark reach (:122-124, np.linalg.norm = sqrt(fma(ay, ay, ax*ax)), probed on OpenBLAS)
 // decided on the squared norm outside a 1e-9 band around agents_size^2, and the running minimum of the squared
 // distance_matrix entry (:158-161; sqrt_rn is monotonic, so min_l sqrt(q_l) = sqrt(min_l q_l)).

@@ -35,7 +35,6 @@ namespace smarl {
 constexpr int kCoopThreads = 128;
 constexpr int kCoopMinA = 9;          // smallest agent count the cooperative kernels are instantiated for
 
-constexpr int kClipSlots = 64;        // compacted action clips per warp and step (two rounds of 32 lanes)
 
 template <int A, int S>
 struct CollCoop {
@@ -51,18 +50,7 @@ struct CollCoop {
                                   (size_t)(kCoopThreads / 32) * kClipSlots * sizeof(double2);
 };
 
-// The action clip of collision_move_agent (collision.cuh; collision_avoidance.py:113-117) for one agent whose squared
-// norm exceeds 1, out of line: norm = sqrt(dx^2 + dy^2); if norm > 1 both components are divided by it.
-static __device__ __noinline__ double2 clip_action(float adx, float ady) {
-  double dx = (double)adx, dy = (double)ady;
-  const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-  const double norm = __dsqrt_rn(q);
-  if (norm > 1.0) {
-    dx = __ddiv_rn(dx, norm);
-    dy = __ddiv_rn(dy, norm);
-  }
-  return make_double2(dx, dy);
-}
+// (clip_action and kClipSlots live in collision.cuh: the one-thread kernels compact their clips the same way)
 
 // Exact test of one pair (the arithmetic of pair_collides in collision.cuh) on values instead of arrays.
 static __device__ __noinline__ int pair_collides_xy(double xi, double yi, double xj, double yj, double lim2_lo,
