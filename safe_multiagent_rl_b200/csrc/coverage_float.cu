@@ -26,6 +26,7 @@ struct CoverageFloatArgs {
   int64_t n_envs;
   int64_t ld;
   double size, fieldview, max_norm, zoom, hi, cost_axis, cost_diag;
+  double m4_lo, m4_hi;        // max_norm^4 * (1 -+ 1e-9): outside this band q decides sqrt(sqrt(q)) > max_norm
   int32_t has_coarseness;
 };
 
@@ -46,10 +47,16 @@ __device__ __forceinline__ void coverage_float_env_step(double (&px)[A], double 
       double dx = (double)af[(2 * i) * ld], dy = (double)af[(2 * i + 1) * ld];
       cost[i] = __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));       // :94 np.linalg.norm(action)
       if (a.has_coarseness) {
-        const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // :65
-        if (__dsqrt_rn(norm) > a.max_norm) {                           // :67 (sic: sqrt of the norm)
-          dx = __dmul_rn(__ddiv_rn(dx, norm), a.max_norm);
-          dy = __dmul_rn(__ddiv_rn(dy, norm), a.max_norm);
+        // :65-69  norm = sqrt(dx^2 + dy^2); if sqrt(norm) > max_norm (sic: sqrt of the norm) rescale.  sqrt_rn is
+        // monotonic, so sqrt(sqrt(q)) > max_norm is decided on q outside a 1e-9 band around max_norm^4 and the two
+        // square roots are only evaluated for the few actions that are rescaled (or fall inside the band).
+        const double q = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (q > a.m4_lo) {
+          const double norm = __dsqrt_rn(q);
+          if (q > a.m4_hi || __dsqrt_rn(norm) > a.max_norm) {
+            dx = __dmul_rn(__ddiv_rn(dx, norm), a.max_norm);
+            dy = __dmul_rn(__ddiv_rn(dy, norm), a.max_norm);
+          }
         }
       }
       px[i] = fmax(0.0, fmin(a.size, __dadd_rn(px[i], dx)));            // :70
@@ -315,6 +322,11 @@ extern "C" int smarl_coverage_float_step(const SmarlCoverageFloatParams* p, doub
   a.ld = ld; a.size = (double)p->size; a.fieldview = p->fieldview; a.max_norm = p->max_norm;
   a.zoom = p->zoom; a.hi = p->hi; a.cost_axis = p->cost_axis; a.cost_diag = p->cost_diag;
   a.has_coarseness = p->has_coarseness;
+  {
+    const double m4 = (a.max_norm * a.max_norm) * (a.max_norm * a.max_norm);
+    a.m4_lo = m4 * (1.0 - 1e-9);
+    a.m4_hi = m4 * (1.0 + 1e-9);
+  }
   const unsigned grid = (unsigned)((n_envs + kCovFThreads - 1) / kCovFThreads);
   return p->mode == 0 ? launch_coverage_float_step_m0(p->n_agents, a, grid, (cudaStream_t)stream)
                       : launch_coverage_float_step_m1(p->n_agents, a, grid, (cudaStream_t)stream);
@@ -342,6 +354,11 @@ extern "C" int smarl_coverage_float_rollout(const SmarlCoverageFloatParams* p, c
   a.weights = p->weights; a.n_envs = n_envs; a.ld = ld; a.size = (double)p->size; a.fieldview = p->fieldview;
   a.max_norm = p->max_norm; a.zoom = p->zoom; a.hi = p->hi; a.cost_axis = p->cost_axis; a.cost_diag = p->cost_diag;
   a.has_coarseness = p->has_coarseness;
+  {
+    const double m4 = (a.max_norm * a.max_norm) * (a.max_norm * a.max_norm);
+    a.m4_lo = m4 * (1.0 - 1e-9);
+    a.m4_hi = m4 * (1.0 + 1e-9);
+  }
   r.final_x = final_x; r.final_y = final_y; r.R = R; r.modR = modR; r.C = C; r.G = G; r.g_scratch = g_scratch;
   r.partials = stats_scratch; r.thresholds = acc->thresholds; r.gamma = acc->gamma; r.n_steps = acc->n_steps;
   r.g_mode = acc->g_mode;
