@@ -181,9 +181,9 @@ static __device__ __noinline__ double2 clip_action(float adx, float ady) {
 }
 
 // The transition of all A agents of one env per thread (collision_avoidance.py:103-121) with the action clips of the
-// WARP compacted.  The clip costs an f64 square root and two f64 divisions (~150 instructions); only actions longer
-// than 1 need it (13 % with N(0, 0.5^2) components), but some lane of every warp does for every agent slot, so inlined
-// per slot the whole warp pays it A times per step -- 450 of the ~790 instructions per env-step at A = 3.  Here every
+// WARP compacted.  The clip costs an f64 square root and two f64 divisions (a dependent chain of ~110 instructions);
+// only actions longer than 1 need it (13 % with N(0, 0.5^2) components), but some lane of every warp does for every
+// agent slot, so inlined per slot the whole warp runs the chain A times per step, one after the other.  Here every
 // agent that needs a clip gets a rank (ballot + popc), posts its f32 action to shared memory, the lanes work the
 // posted list off round-robin (ceil(n / 32) rounds instead of A) and the owners pick their f64 result up.  Ranks beyond
 // the kClipSlots slots (an unusually clip-heavy warp) are evaluated in place.  Same arithmetic, same bits.
