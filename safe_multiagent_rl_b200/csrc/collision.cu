@@ -227,7 +227,7 @@ template <int A, bool CAP>
 //  A = 5..8 is held to 5 CTAs per SM / 96 registers: fused A = 6 +13 %, A = 8 +7 % on 2^20..2^21 envs)
 __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5 : 0))) collision_rollout_kernel(const CollisionRolloutArgs a) {
   __shared__ double s_red[kCollThreads / 32];
-  __shared__ double2 s_clip[kCollThreads / 32][kClipSlots];
+  __shared__ double2 s_clip[A <= SMARL_COLL_COMPACT_ROLLOUT_MAX_A ? kCollThreads / 32 : 1][A <= SMARL_COLL_COMPACT_ROLLOUT_MAX_A ? kClipSlots : 1];
   const int64_t eg = (int64_t)blockIdx.x * kCollThreads + threadIdx.x;
   const bool live = eg < a.n_envs;
   const int64_t e = live ? eg : 0;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5
     double reward = 0.0;
     int collisions = 0;
     const bool active = done_mask != all;               // main.py:51 (lanes past n_envs replay env 0 and store nothing)
-    {
+    if constexpr (A <= SMARL_COLL_COMPACT_ROLLOUT_MAX_A) {
       float adx[A], ady[A];
 #pragma unroll
       for (int i = 0; i < A; ++i) {
@@ -256,8 +256,18 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5
         ady[i] = active ? a.actions[((int64_t)t * 2 * A + 2 * i + 1) * ld + e] : 0.f;
       }
       collision_transition_compact<A>(px, py, done_mask, active, adx, ady, a.size, s_clip[threadIdx.x >> 5]);
-    }
-    if (active) {
+      if (active) {
+        collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+        ++steps;
+      }
+    } else if (active) {
+      float adx[A], ady[A];
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        adx[i] = a.actions[((int64_t)t * 2 * A + 2 * i) * ld + e];
+        ady[i] = a.actions[((int64_t)t * 2 * A + 2 * i + 1) * ld + e];
+      }
+      collision_transition_inline<A>(px, py, done_mask, adx, ady, a.size);
       collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
       ++steps;
     }

@@ -160,9 +160,13 @@ __device__ __forceinline__ void collision_transition_inline(double (&px)[A], dou
 // Agent counts up to which the one-thread STEP kernel compacts its clips over the warp (measured on B200, closed loop,
 // ms per 2^20 envs x T = 50, inline -> compacted: A = 3 2.63 -> 2.35, A = 4 3.20 -> 2.87, A = 5 4.57 -> 3.75, A = 6
 // 5.18 -> 4.75, A = 7 5.94 -> 5.56, A = 8 6.78 -> 7.82: the rank bookkeeping lifts the step kernel from ~100 to 140
-// registers there).  The fused rollout gains at every A measured (A = 8: 3.71 -> 3.35 ms).
+// registers there).  The fused rollout gains up to A = 8 (3.71 -> 3.35 ms per 2^20 x 8 x 50) and loses from A = 12
+// (one-thread rollout, T = 20: A = 16 4.73 -> 5.85 ms), where the lane-cooperative kernels take over anyway.
 #ifndef SMARL_COLL_COMPACT_MAX_A
 #define SMARL_COLL_COMPACT_MAX_A 7
+#endif
+#ifndef SMARL_COLL_COMPACT_ROLLOUT_MAX_A
+#define SMARL_COLL_COMPACT_ROLLOUT_MAX_A 8
 #endif
 
 constexpr int kClipSlots = 64;        // compacted action clips per warp and step (two rounds of 32 lanes)
