@@ -369,12 +369,14 @@ __global__ void collision_reset_kernel(const double* __restrict__ start_x, const
 
 // Lanes per env: 0 = one thread per env (collision.cu), 2 / 4 = lane-cooperative kernels (collision_coop.cu).
 // Crossover measured on B200 (profiles/r02): see DESIGN.md section 3.3.  smarl_set_kernel_variant overrides it.
-int collision_coop_lanes(int A, int L, int64_t ld) {
+int collision_coop_lanes(int A, int L, int64_t ld, bool rollout) {
   if (A < 9) return 0;
   if ((int64_t)(2 * A + 2 * L + 2) * ld >= (1ll << 32)) return 0;   // the cooperative kernels use 32-bit element offsets
   const int forced = kernel_variant(SMARL_ENV_COLLISION);
   if (forced >= 0) return forced;
-  if (A < 12) return 0;
+  // 2^20 envs, T = 20, one thread / 2 lanes (profiles/r02/crossover_a9_11.md): step A = 9 3.38 / 3.66 ms, A = 10 3.76 / 3.72,
+  // A = 11 6.13 / 4.19; fused rollout A = 9 2.08 / 1.80, A = 10 3.26 / 1.80, A = 11 3.62 / 2.17
+  if (A < (rollout ? 9 : 11)) return 0;
   return A <= 16 ? 2 : 4;
 }
 
@@ -427,7 +429,7 @@ extern "C" int smarl_collision_step(const SmarlCollisionParams* p, double* pos_x
   a.agents_size = p->agents_size; a.L = p->n_landmarks; a.obs_landmarks = p->obs_landmarks;
   a.normalize = p->normalize_state;
   a.reward_rows = p->reward_rows == 1 ? 1 : 0;
-  if (const int lanes = collision_coop_lanes(p->n_agents, p->n_landmarks, ld))
+  if (const int lanes = collision_coop_lanes(p->n_agents, p->n_landmarks, ld, false))
     return launch_collision_coop_step(p->n_agents, lanes, a, (cudaStream_t)stream);
   const unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
   if (int rc = launch_collision_step(p->n_agents, a, grid, (cudaStream_t)stream)) return rc;
@@ -459,7 +461,7 @@ extern "C" int smarl_collision_rollout(const SmarlCollisionParams* p, const Smar
   a.ld = ld; a.size = (double)p->size; a.agents_size = p->agents_size; a.L = p->n_landmarks;
   a.n_steps = acc->n_steps; a.g_mode = acc->g_mode;
   unsigned grid = (unsigned)((n_envs + kCollThreads - 1) / kCollThreads);
-  if (const int lanes = collision_coop_lanes(p->n_agents, p->n_landmarks, ld)) {
+  if (const int lanes = collision_coop_lanes(p->n_agents, p->n_landmarks, ld, true)) {
     const int64_t envs_per_cta = kCollThreads / lanes;     // the cooperative kernels run 128 / lanes envs per CTA
     grid = (unsigned)((n_envs + envs_per_cta - 1) / envs_per_cta);
     if (int rc = launch_collision_coop_rollout(p->n_agents, lanes, a, (cudaStream_t)stream)) return rc;

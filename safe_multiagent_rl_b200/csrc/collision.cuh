@@ -266,6 +266,6 @@ int launch_collision_rollout(int A, const CollisionRolloutArgs& a, unsigned grid
 int launch_collision_coop_step(int A, int S, const CollisionStepArgs& a, cudaStream_t s);
 int launch_collision_coop_rollout(int A, int S, const CollisionRolloutArgs& a, cudaStream_t s);
 // lanes per env of the lane-cooperative kernels for this agent count / batch (0 = one thread per env)
-int collision_coop_lanes(int A, int L, int64_t ld);
+int collision_coop_lanes(int A, int L, int64_t ld, bool rollout);
 
 }  // namespace smarl
