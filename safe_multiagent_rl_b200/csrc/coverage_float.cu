@@ -27,6 +27,7 @@ struct CoverageFloatArgs {
   int64_t ld;
   double size, fieldview, max_norm, zoom, hi, cost_axis, cost_diag;
   double m4_lo, m4_hi;        // max_norm^4 * (1 -+ 1e-9): outside this band q decides sqrt(sqrt(q)) > max_norm
+  double rzoom;               // RN(1 / zoom)
   int32_t has_coarseness;
 };
 
@@ -35,6 +36,18 @@ constexpr int kCovFThreads = 128;
 int launch_coverage_float_step(int mode, int A, const CoverageFloatArgs& a, unsigned grid, cudaStream_t s);
 
 #if SMARL_TU_IS(0) || SMARL_TU_IS(1) || SMARL_TU_IS(3) || SMARL_TU_IS(4)
+// x / zoom, correctly rounded, for the kernel-invariant divisor zoom with rzoom = RN(1 / zoom) from the host: a
+// multiply and two exact-residual corrections (5 instructions) instead of the ~45 of a float64 division, of which
+// CoverageDiscretized.transition needs two per agent-step (coverage.py:230).  q1 is a faithful quotient, and a faithful
+// quotient corrected once through the exact FMA residual with a correctly rounded reciprocal IS the rounded quotient
+// (Markstein); x is 0 or a normal number of magnitude >= ~1e-16 here, so nothing underflows.  tools/div_probe.cu checked
+// 3.3e10 operands of exactly this shape against __ddiv_rn bit for bit (profiles/r02/div_probe.txt).
+__device__ __forceinline__ double div_by_zoom(double x, double zoom, double rzoom) {
+  const double q0 = __dmul_rn(x, rzoom);
+  const double q1 = __fma_rn(__fma_rn(-q0, zoom, x), rzoom, q0);
+  return __fma_rn(__fma_rn(-q1, zoom, x), rzoom, q1);
+}
+
 // One step of one env held in registers: moves every agent, returns the per-agent costs (f64) and the
 // unweighted env reward.  `act` points at this env's lane of step t's action rows.
 template <int A, int MODE>
@@ -63,11 +76,11 @@ __device__ __forceinline__ void coverage_float_env_step(double (&px)[A], double 
       py[i] = fmax(0.0, fmin(a.size, __dadd_rn(py[i], dy)));
     } else {                                           // CoverageDiscretized.transition, coverage.py:219-234
       const uint32_t m = static_cast<const uint8_t*>(act)[i * ld];
-      // directions (:221): x +1,-1,0,0,+1,+1,-1,-1,0 ; y 0,0,-1,+1,+1,-1,+1,-1,0
-      const int dxi = (m == 0 || m == 4 || m == 5) ? 1 : ((m == 1 || m == 6 || m == 7) ? -1 : 0);
-      const int dyi = (m == 3 || m == 4 || m == 6) ? 1 : ((m == 2 || m == 5 || m == 7) ? -1 : 0);
-      px[i] = __ddiv_rn(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(px[i], a.zoom), (double)dxi))), a.zoom);   // :230
-      py[i] = __ddiv_rn(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(py[i], a.zoom), (double)dyi))), a.zoom);
+      // directions (:221): x +1,-1,0,0,+1,+1,-1,-1,0 ; y 0,0,-1,+1,+1,-1,+1,-1,0  -- two bits per action, value + 1
+      const int dxi = (int)((0x10A52u >> (2 * m)) & 3u) - 1;
+      const int dyi = (int)((0x12285u >> (2 * m)) & 3u) - 1;
+      px[i] = div_by_zoom(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(px[i], a.zoom), (double)dxi))), a.zoom, a.rzoom);   // :230
+      py[i] = div_by_zoom(fmax(0.0, fmin(a.hi, __dadd_rn(__dmul_rn(py[i], a.zoom), (double)dyi))), a.zoom, a.rzoom);
       cost[i] = m < 4 ? a.cost_axis : (m < 8 ? a.cost_diag : 0.0);     // :237
     }
   }
@@ -326,6 +339,7 @@ extern "C" int smarl_coverage_float_step(const SmarlCoverageFloatParams* p, doub
     const double m4 = (a.max_norm * a.max_norm) * (a.max_norm * a.max_norm);
     a.m4_lo = m4 * (1.0 - 1e-9);
     a.m4_hi = m4 * (1.0 + 1e-9);
+    a.rzoom = 1.0 / a.zoom;
   }
   const unsigned grid = (unsigned)((n_envs + kCovFThreads - 1) / kCovFThreads);
   return p->mode == 0 ? launch_coverage_float_step_m0(p->n_agents, a, grid, (cudaStream_t)stream)
@@ -358,6 +372,7 @@ extern "C" int smarl_coverage_float_rollout(const SmarlCoverageFloatParams* p, c
     const double m4 = (a.max_norm * a.max_norm) * (a.max_norm * a.max_norm);
     a.m4_lo = m4 * (1.0 - 1e-9);
     a.m4_hi = m4 * (1.0 + 1e-9);
+    a.rzoom = 1.0 / a.zoom;
   }
   r.final_x = final_x; r.final_y = final_y; r.R = R; r.modR = modR; r.C = C; r.G = G; r.g_scratch = g_scratch;
   r.partials = stats_scratch; r.thresholds = acc->thresholds; r.gamma = acc->gamma; r.n_steps = acc->n_steps;
