@@ -22,11 +22,11 @@ constexpr int kPairPrefilterA = 12;   // agent count from which the pair loop is
 // One CollisionAvoidance.step for one env held in registers.  Returns the env reward (same for
 // every agent) and the collision count; updates px/py/done_mask in place.
 // MOVED: the transition (collision_avoidance.py:103-121) was already applied by collision_transition_compact.
-template <int A>
+template <int A, bool LM0>
 __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)[A], uint32_t& done_mask,
                                                    const double* __restrict__ lm, int64_t ld, int L,
-                                                   double size, double agents_size, double& reward,
-                                                   int& collisions) {
+                                                   double lx0, double ly0, double size, double agents_size,
+                                                   double& reward, int& collisions) {
   // landmark reach (:122-124) and per-agent min landmark distance (:158-161).  Both compare / minimise
   // square roots; sqrt_rn is monotonic, so the reach test is decided on the squared norm outside a
   // 1e-9 band around agents_size^2 and the minimum is taken over the squared distances, leaving ONE
@@ -38,7 +38,10 @@ __device__ __forceinline__ void collision_env_step(double (&px)[A], double (&py)
 #pragma unroll
   for (int i = 0; i < A; ++i) minq[i] = 1.0e300;
   for (int l = 0; l < L; ++l) {
-    const double lx = lm[(2 * l) * ld], ly = lm[(2 * l + 1) * ld];
+    // LM0: landmark 0 was loaded by the caller together with the positions (the step kernel): loaded here, after the
+    // transition, its memory latency sat on every thread's critical path (A = 3 on 2^22 envs: 9.00 -> 8.16 ms closed
+    // loop).  The fused rollout keeps the load here (hoisted or held across the loop it measured 4-7 % slower).
+    const double lx = (LM0 && l == 0) ? lx0 : lm[(2 * l) * ld], ly = (LM0 && l == 0) ? ly0 : lm[(2 * l + 1) * ld];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       const double ax = __dadd_rn(px[i], -lx), ay = __dadd_rn(py[i], -ly);
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_ke
     ady[i] = a.actions[(2 * i + 1) * ld + e];
     done_mask |= a.done[i * ld + e] ? (1u << i) : 0u;
   }
+  const double lx0 = a.landmarks[e], ly0 = a.landmarks[ld + e];
   const int32_t steps_before = a.episode_len ? a.episode_len[e] : 0;
   const uint32_t all = A == 32 ? 0xFFFFFFFFu : ((1u << A) - 1u);
   const bool active = live && done_mask != all;               // main.py:51: episode already over
@@ -153,10 +157,10 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : 0)) collision_step_ke
     collision_transition_compact<A>(px, py, done_mask, active, adx, ady, a.size, s_clip[threadIdx.x >> 5]);
     if (!live) return;
     if (active)
-      collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+      collision_env_step<A, true>(px, py, done_mask, a.landmarks + e, ld, a.L, lx0, ly0, a.size, a.agents_size, reward, collisions);
   } else if (active) {
     collision_transition_inline<A>(px, py, done_mask, adx, ady, a.size);
-    collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+    collision_env_step<A, true>(px, py, done_mask, a.landmarks + e, ld, a.L, lx0, ly0, a.size, a.agents_size, reward, collisions);
   }
   const float rf = (float)reward;
 #pragma unroll
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5
       }
       collision_transition_compact<A>(px, py, done_mask, active, adx, ady, a.size, s_clip[threadIdx.x >> 5]);
       if (active) {
-        collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+        collision_env_step<A, false>(px, py, done_mask, a.landmarks + e, ld, a.L, 0.0, 0.0, a.size, a.agents_size, reward, collisions);
         ++steps;
       }
     } else if (active) {
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(kCollThreads, (CAP ? 8 : (A >= 5 && A <= 8 ? 5
         ady[i] = a.actions[((int64_t)t * 2 * A + 2 * i + 1) * ld + e];
       }
       collision_transition_inline<A>(px, py, done_mask, adx, ady, a.size);
-      collision_env_step<A>(px, py, done_mask, a.landmarks + e, ld, a.L, a.size, a.agents_size, reward, collisions);
+      collision_env_step<A, false>(px, py, done_mask, a.landmarks + e, ld, a.L, 0.0, 0.0, a.size, a.agents_size, reward, collisions);
       ++steps;
     }
     const float rf = (float)reward;
