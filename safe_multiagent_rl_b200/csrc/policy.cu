@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(PolCfg<A>::THREADS) policy_act_discrete_kernel
 
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t e_tile = tile * TE;
-    __syncthreads();                                 // previous tile fully consumed (and the weights staged)
+    if (tile != (int64_t)blockIdx.x) __syncthreads();   // previous tile fully consumed; the first tile's position loads
+                                                        // go out right behind the weight loads (one barrier covers both)
     // stage the tile's positions as floats: row 2i = x_i, row 2i+1 = y_i (main.py:33: np.array(state).flatten())
     for (int i = tid; i < IN * QPT; i += C::THREADS) {
       const int row = i / QPT, qd = i % QPT;

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(GaussCfg<A>::THREADS) policy_act_gaussian_kern
 
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t e_tile = tile * TE;
-    __syncthreads();                                 // previous tile fully consumed (and the weights staged)
+    if (tile != (int64_t)blockIdx.x) __syncthreads();   // previous tile fully consumed; the first tile's observation loads
+                                                        // go out right behind the weight loads (one barrier covers both)
     for (int i = tid; i < S * QPT; i += C::THREADS) {
       const int row = i / QPT, qd = i % QPT;
       const int64_t e = e_tile + 4 * qd;
