@@ -143,3 +143,30 @@ def test_meta_agent_act_records_under_the_gate_like_the_reference():
     meta.update()
     mean_c = costs.sum(0).mean(0)                            # mean over the E recorded episodes of sum_t c
     np.testing.assert_allclose(meta.lambdas.cpu().numpy(), np.maximum(lam0 + 0.5 * (mean_c - 1.0), 0), rtol=1e-12)
+
+
+@pytest.mark.parametrize("size,coarse", [(5, 6), (3, 2), (33, 6), (7, 10), (10, 3), (64, 25), (100, 7), (127, 50), (2, 1), (13, 12)])
+def test_discretized_positions_stay_bit_exact_with_the_invariant_divisor(size, coarse):
+    """CoverageDiscretized divides by the kernel-invariant zoom = coarseness / size with a multiply and two exact-residual
+    FMA corrections instead of a float64 division (coverage_float.cu, div_by_zoom).  Positions must stay bit-identical to
+    numpy's float64 x / zoom over long trajectories, for zooms with terminating and non-terminating binary expansions
+    (3/2, 6/33, 25/64, ...), many envs, all nine actions incl. walks into both walls."""
+    import numpy as np
+    import torch
+    import safe_multiagent_rl_b200 as s
+    from oracle import numpy_oracle as no
+    rng = np.random.default_rng(size * 1000 + coarse)
+    A, E, T = 3, 5000, 60
+    zoom = coarse / size
+    starts = np.floor(rng.random((E, A, 2)) * size * zoom) / zoom
+    env = s.BatchedCoverageDiscretized(size, A, n_envs=E, coarseness=coarse, starts=starts)
+    fv = no.coverage_fieldview(size, A)
+    env.reset()
+    pos = starts.copy()
+    for t in range(T):
+        # biased walks so that agents run into the walls and bounce along them
+        act = np.where(rng.random((E, A)) < 0.7, rng.integers(0, 9, (E, A)), (t // 15) % 8)
+        env.step(act.astype(np.uint8))
+        pos, _, _, _ = no.coverage_discretized_step(pos, act, size, coarse, fv, None, exact_pow=False)
+        got = np.ascontiguousarray(env.state().cpu().numpy())
+        assert np.array_equal(got.view(np.int64), np.ascontiguousarray(pos).view(np.int64)), (t, np.abs(got - pos).max())
